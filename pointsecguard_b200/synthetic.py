@@ -1,0 +1,154 @@
+"""Synthetic S3DIS-shaped inputs, labels and checkpoints.
+
+There is no dataset and no trained checkpoint in the reference drop, so every measurement and every
+parity test runs on data made here.  The generators are deterministic functions of a seed on the
+torch CPU generator, so the build container (where the real reference runs and the golden vectors
+are made) and the GPU box see identical tensors.
+
+Block layout follows PointNet/data_utils/S3DISDataLoader.py:154-165 of the reference: channels
+0:3 block-centred x,y and raw z (metres), 3:6 rgb/255, 6:9 xyz / room extent.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+NUM_CLASSES = 13
+
+# (npoint, [radius...], [nsample...], [[mlp...]...]) per set-abstraction level; FP mlps; reference:
+# PointNet/models/pointnet2_sem_seg.py:9-20 and pointnet2_sem_seg_msg.py:10-21.
+ARCH = {
+    "ssg": {
+        "sa": [
+            (1024, [0.1], [32], [[32, 32, 64]]),
+            (256, [0.2], [32], [[64, 64, 128]]),
+            (64, [0.4], [32], [[128, 128, 256]]),
+            (16, [0.8], [32], [[256, 256, 512]]),
+        ],
+        "sa_in": [9, 64, 128, 256],
+        "fp": [(768, [256, 256]), (384, [256, 256]), (320, [256, 128]), (128, [128, 128, 128])],
+    },
+    "msg": {
+        "sa": [
+            (1024, [0.05, 0.1], [16, 32], [[16, 16, 32], [32, 32, 64]]),
+            (256, [0.1, 0.2], [16, 32], [[64, 64, 128], [64, 96, 128]]),
+            (64, [0.2, 0.4], [16, 32], [[128, 196, 256], [128, 196, 256]]),
+            (16, [0.4, 0.8], [16, 32], [[256, 256, 512], [256, 384, 512]]),
+        ],
+        "sa_in": [9, 96, 256, 512],
+        "fp": [(1536, [256, 256]), (512, [256, 256]), (352, [256, 128]), (128, [128, 128, 128])],
+    },
+}
+
+
+def make_blocks(B: int, N: int = 4096, seed: int = 0, kind: str = "uniform") -> torch.Tensor:
+    """Return a [B, 9, N] float32 *non-contiguous* view (a transposed [B, N, 9] tensor), which is
+    exactly how the reference scripts hand blocks to the model (NB_nontarget_test_semseg.py:163-165).
+
+    kinds: uniform | grid | clustered | duplicates | surface
+    """
+    g = torch.Generator("cpu").manual_seed(seed)
+    pts = torch.rand(B, N, 9, generator=g, dtype=torch.float32)
+    if kind == "grid":
+        # coordinates on multiples of 2^-6 so that every distance formula is exact in fp32; many ties
+        pts[..., 0:3] = torch.floor(pts[..., 0:3] * 64.0) / 64.0
+    elif kind == "clustered":
+        # everything inside a 0.15 m cube: ball queries overflow nsample
+        pts[..., 0:3] = pts[..., 0:3] * 0.15 + 0.4
+    elif kind == "duplicates":
+        # S3DIS blocks are padded by repeating points (S3DISDataLoader.py:149-153)
+        half = N // 2
+        src = torch.randint(0, half, (B, N - half), generator=g)
+        for b in range(B):
+            pts[b, half:] = pts[b, src[b]]
+    elif kind == "surface":
+        # points on five jittered planes: realistic local density
+        plane = torch.randint(0, 5, (B, N), generator=g)
+        jitter = (torch.rand(B, N, generator=g) - 0.5) * 0.01
+        level = plane.float() * 0.2 + 0.05 + jitter
+        axis = plane % 3
+        for a in range(3):
+            sel = axis == a
+            col = pts[..., a]
+            col[sel] = level[sel]
+    elif kind != "uniform":
+        raise ValueError(f"unknown synthetic kind {kind!r}")
+    pts[..., 0:2] -= 0.5
+    pts[..., 2] *= 3.0
+    return pts.transpose(2, 1)
+
+
+def zband_labels(x: torch.Tensor) -> torch.Tensor:
+    """Spatially coherent labels for the targeted attacks: class = min(12, floor(13 z / 3))."""
+    z = x[:, 2, :]
+    return torch.clamp(torch.floor(z * (13.0 / 3.0)), 0, NUM_CLASSES - 1).to(torch.int64)
+
+
+def _conv_keys(prefix, cin, cout, ndim):
+    shape = (cout, cin, 1, 1) if ndim == 2 else (cout, cin, 1)
+    return [(prefix + ".weight", shape, cin), (prefix + ".bias", (cout,), cin)]
+
+
+def state_dict_spec(arch: str):
+    """(key, shape, fan_in | 'bn_*') list with the reference's checkpoint key names."""
+    a = ARCH[arch]
+    spec = []
+    for li, (npoint, radii, nsamples, mlps) in enumerate(a["sa"]):
+        cin0 = a["sa_in"][li] + 3
+        for bi, mlp in enumerate(mlps):
+            cin = cin0
+            for j, cout in enumerate(mlp):
+                if arch == "ssg":
+                    cp, bp = f"sa{li+1}.mlp_convs.{j}", f"sa{li+1}.mlp_bns.{j}"
+                else:
+                    cp, bp = f"sa{li+1}.conv_blocks.{bi}.{j}", f"sa{li+1}.bn_blocks.{bi}.{j}"
+                spec += _conv_keys(cp, cin, cout, 2)
+                spec += _bn_keys(bp, cout)
+                cin = cout
+    for fi, (cin, mlp) in enumerate(a["fp"]):
+        name = f"fp{4-fi}"
+        for j, cout in enumerate(mlp):
+            spec += _conv_keys(f"{name}.mlp_convs.{j}", cin, cout, 1)
+            spec += _bn_keys(f"{name}.mlp_bns.{j}", cout)
+            cin = cout
+    spec += _conv_keys("conv1", 128, 128, 1)
+    spec += _bn_keys("bn1", 128)
+    spec += _conv_keys("conv2", 128, NUM_CLASSES, 1)
+    return spec
+
+
+def _bn_keys(prefix, c):
+    return [
+        (prefix + ".weight", (c,), "bn_w"),
+        (prefix + ".bias", (c,), "bn_b"),
+        (prefix + ".running_mean", (c,), "bn_m"),
+        (prefix + ".running_var", (c,), "bn_v"),
+        (prefix + ".num_batches_tracked", (), "bn_n"),
+    ]
+
+
+def make_state_dict(arch: str = "ssg", seed: int = 1234, randomize_bn: bool = True) -> "OrderedDict[str, torch.Tensor]":
+    """A random checkpoint with the reference's key names and shapes.
+
+    Conv weights/biases ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (PyTorch's default scale).  With
+    ``randomize_bn`` the BatchNorm affine parameters and running statistics are randomised too
+    (running_mean ~ N(0,0.1), running_var ~ U(0.5,1.5), weight ~ U(0.5,1.5), bias ~ N(0,0.1));
+    default-initialised BN (mean 0 / var 1) would hide folding bugs.
+    """
+    g = torch.Generator("cpu").manual_seed(seed)
+    sd = OrderedDict()
+    for key, shape, kind in state_dict_spec(arch):
+        if kind == "bn_n":
+            sd[key] = torch.tensor(0, dtype=torch.int64)
+        elif kind == "bn_w":
+            sd[key] = torch.rand(shape, generator=g) + 0.5 if randomize_bn else torch.ones(shape)
+        elif kind == "bn_v":
+            sd[key] = torch.rand(shape, generator=g) + 0.5 if randomize_bn else torch.ones(shape)
+        elif kind in ("bn_b", "bn_m"):
+            sd[key] = torch.randn(shape, generator=g) * 0.1 if randomize_bn else torch.zeros(shape)
+        else:
+            bound = 1.0 / math.sqrt(kind)
+            sd[key] = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
+    return sd
