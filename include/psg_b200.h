@@ -1,0 +1,163 @@
+/*
+ * psg_b200.h -- C ABI of libpsg_b200.so, the B200 (sm_100a) implementation of the PointNet++
+ * semantic-segmentation attack hot path of C0ldstudy/PointSecGuard.
+ *
+ * The reference has no FFI on this path: it is Python over stock PyTorch ops.  Each entry point
+ * below therefore names the reference *Python* function(s) it replaces (file:line under
+ * /root/reference/PointNet) and is what the torch.library shim in pointsecguard_b200/ops.py binds
+ * (see INTEGRATION.md for the reference-side stub a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - functions enqueue work on `stream` and return immediately; they never synchronise, never
+ *     allocate device memory (except psg_net_create / psg_mlp_create, which upload weights once)
+ *     and never throw; return value 0 = ok, <0 = PSG_E* below;
+ *   - indices are int32 inside the library; the Python layer widens to int64 at the public API;
+ *   - "T-layout" is the library's activation layout: float T[rows/128][C/4][128][4], C padded to a
+ *     multiple of 16 (pointsecguard_b200/csrc/psg_common.cuh).  A T-layout view is passed
+ *     as (base pointer, padded width in 16-byte chunks, first chunk of the column slice).
+ */
+#ifndef PSG_B200_H
+#define PSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSG_OK 0
+#define PSG_EINVAL (-1)
+#define PSG_EUNSUPPORTED (-2)
+#define PSG_EWORKSPACE (-3)
+#define PSG_ECUDA (-4)
+
+typedef void *psg_stream_t; /* cudaStream_t */
+
+int psg_version(void);
+
+/* ---- geometric primitives (API layouts: xyz [P,N,3] row-major float32) ----------------------- */
+
+/* farthest_point_sample, pointnet_util.py:63-84.  `start` holds the torch.randint draw of line 75
+ * (made by the caller on the CPU generator).  Cloud of problem p is xyz + (p % nclouds) * N * 3, so
+ * several problems (attack iterations) may share one cloud.  out_xyz (optional) receives the
+ * sampled coordinates = index_points(xyz, fps_idx) of :126. */
+size_t psg_fps_workspace(int P, int N);
+int psg_fps(const float *xyz, int nclouds, int P, int N, int npoint, const int32_t *start,
+            int32_t *out_idx, float *out_xyz, void *workspace, size_t workspace_bytes, psg_stream_t stream);
+
+/* square_distance, pointnet_util.py:19-40: out[b,i,j] = ((-2 src_i.dst_j) + |src_i|^2) + |dst_j|^2 */
+int psg_square_distance(const float *src, const float *dst, int B, int N, int M, float *out, psg_stream_t stream);
+
+/* query_ball_point, pointnet_util.py:87-107; nr = 1 or 2 radii sharing one scan (MSG :246-248). */
+int psg_ball_query(const float *xyz, int nclouds, int P, int N, const float *new_xyz, int S, int nr,
+                   const double *radius_host, const int *nsample_host, int32_t *out0, int32_t *out1,
+                   psg_stream_t stream);
+
+/* 3-NN + inverse-distance weights, pointnet_util.py:301-307.  w / d2 optional. */
+int psg_three_nn(const float *xyz1, int nclouds1, int P, int N, const float *xyz2, int S, int32_t *idx,
+                 float *w, float *d2, psg_stream_t stream);
+
+/* index_points, pointnet_util.py:43-60, row-major points [B,N,C], idx int64 [B,M] -> out [B,M,C] */
+int psg_index_points(const float *points, const int64_t *idx, int B, int N, int C, int64_t M, float *out,
+                     psg_stream_t stream);
+
+/* ---- T-layout building blocks (module-level composition, pointnet_util.py:166-320) ----------- */
+int psg_pack_channels_first(const float *x, int64_t sb, int64_t sc, int64_t sn, int B, int C, int N,
+                            float *t_base, int t_wchunks, int t_c0, float *xyz_out, psg_stream_t stream);
+int psg_unpack_channels_first(const float *t_base, int t_wchunks, int t_c0, int B, int C, int N, float *y,
+                              int accumulate, psg_stream_t stream);
+/* sample_and_group gather + centre + concat, pointnet_util.py:126-137 / :245-255 (internal column
+ * order [features | xyz - centre | 0 pad]) */
+int psg_group_points(const float *feats_base, int feats_wchunks, int D, const float *xyz, int nclouds, int Nsrc,
+                     const float *new_xyz, const int32_t *idx, int P, int S, int K, float *out_base,
+                     int out_cpad, psg_stream_t stream);
+int psg_group_max(const float *in_base, int in_wchunks, int64_t groups, int K, int C, float *out_base,
+                  int out_wchunks, int out_c0, uint8_t *argmax, psg_stream_t stream);
+int psg_group_max_backward(const float *dout_base, int dout_wchunks, int dout_c0, const float *out_base,
+                           int out_wchunks, int out_c0, const uint8_t *argmax, int64_t groups, int K, int C,
+                           float *dy_base, int dy_wchunks, psg_stream_t stream);
+int psg_interpolate(const float *feats_base, int feats_wchunks, int S, const int32_t *idx, const float *w,
+                    int64_t P, int N, int ncols, float *out_base, int out_wchunks, int out_c0, psg_stream_t stream);
+size_t psg_csr_workspace(int64_t P, int M, int R);
+int psg_csr_build_by_source(const int32_t *keys, int64_t P, int M, int R, int32_t *offsets, int32_t *perm,
+                            void *workspace, psg_stream_t stream);
+int psg_segment_sum(const float *src_base, int src_wchunks, int src_c0, int64_t src_rows_per_problem, int div,
+                    const float *weights, const int32_t *offsets, const int32_t *perm, int M, int R, int64_t P,
+                    int ncols, float *dst_base, int dst_wchunks, int dst_c0, int accumulate, psg_stream_t stream);
+
+/* one folded conv(1x1)+BN layer: W [cout][cin] and b [cout] on the HOST; uploads packed copies */
+typedef struct psg_mlp psg_mlp;
+psg_mlp *psg_mlp_create(const float *w_host, const float *b_host, int cin, int cout);
+void psg_mlp_destroy(psg_mlp *m);
+/* forward: out = act([a1 | a2] W^T + b), relu = 1/0.  Widths in 16-byte chunks. */
+int psg_mlp_forward(const psg_mlp *m, const float *a1_base, int a1_wchunks, int a1_c0, int k1chunks,
+                    const float *a2_base, int a2_wchunks, int a2_c0, int k2chunks, int64_t rows,
+                    float *out_base, int out_wchunks, int relu, int mode, psg_stream_t stream);
+/* dgrad: dx = (dy W) [. (mask > 0) if mask_base]; dy is grad w.r.t. the pre-activation */
+int psg_mlp_backward(const psg_mlp *m, const float *dy_base, int dy_wchunks, int64_t rows, float *dx_base,
+                     int dx_wchunks, const float *mask_base, int mask_wchunks, int mode, psg_stream_t stream);
+
+/* ---- whole-network engine (pointnet2_sem_seg.py:22-40, pointnet2_sem_seg_msg.py:23-41) -------- */
+typedef struct { int cin, cout; const float *w_host; const float *b_host; } psg_mlp_desc;
+typedef struct {
+    int npoint, nbranch;
+    double radius[2];           /* squared in double like pointnet_util.py:102 does */
+    int nsample[2];
+    int nlayers[2];
+    psg_mlp_desc mlp[2][3];     /* first layer's input columns ordered [features | xyz] */
+} psg_sa_desc;
+typedef struct { int d1, d2, nlayers; psg_mlp_desc mlp[3]; } psg_fp_desc;
+typedef struct {
+    int in_channels, num_classes;
+    psg_sa_desc sa[4];
+    psg_fp_desc fp[4];          /* fp[f]: fine level f, coarse level f+1 (reference fp1 = fp[0]) */
+    psg_mlp_desc conv1, conv2;
+    int mlp_mode;               /* 0 = fp32 CUDA-core GEMM (exact), 1 = tcgen05 TF32 */
+} psg_net_desc;
+
+typedef struct psg_net psg_net;
+psg_net *psg_net_create(const psg_net_desc *desc);
+void psg_net_destroy(psg_net *net);
+int psg_net_set_mlp_mode(psg_net *net, int mode);
+/* B blocks of N points; geometry slots for T forward passes (T*B FPS problems batched) */
+size_t psg_net_workspace(const psg_net *net, int B, int N, int T);
+int psg_net_bind(psg_net *net, int B, int N, int T, void *workspace, size_t workspace_bytes);
+/* x [B,C,N] with element strides (sb, sc, sn): packs features and xyz */
+int psg_net_set_input(psg_net *net, const float *x, int64_t sb, int64_t sc, int64_t sn, psg_stream_t stream);
+/* starts int32 [4][T][B]: FPS start index per level / forward / block (pointnet_util.py:75 draws) */
+int psg_net_geometry(psg_net *net, const int32_t *starts, int T, psg_stream_t stream);
+/* forward pass t: logp [B,N,ncls] and l4_points [B,C4,16] (either may be null) */
+int psg_net_forward(psg_net *net, int t, float *logp, float *l4_points, psg_stream_t stream);
+/* gradient of a cost w.r.t. the logits of the last forward:
+ *   kind 0: generic upstream dlogp [B,N,ncls];
+ *   kind 1: cross-entropy (softmax - onehot(label or target)) * scale   (nontarget.py:34, target.py:38)
+ *   kind 2: C&W f (nontarget.py:120-128), scale = sign, kappa */
+int psg_net_loss_grad(psg_net *net, int kind, const float *dlogp, const int32_t *labels, int target, float scale,
+                      float kappa, float *loss_rows, psg_stream_t stream);
+/* input-gradient backward of forward t; grad_x [B,C,N] (feature path; may be null) */
+int psg_net_backward(psg_net *net, int t, float *grad_x, psg_stream_t stream);
+/* nontarget.py:37-39 / target.py:41-43 fused: adv [B,C,N] contiguous, ori [B,nc,N], mask [B,N] or null */
+int psg_net_pgd_update(psg_net *net, float *adv, const float *ori, const uint8_t *mask, int c0, int nc,
+                       float alpha_signed, float eps, float lo, float hi, psg_stream_t stream);
+/* whole NB / tar-NB loop (nontarget.py:28-39, target.py:31-43): geometry for `iters` forwards must
+ * have been built; labels int32 [B,N] (kind-1 loss), target < 0 for the non-targeted attack. */
+int psg_nb_attack(psg_net *net, float *adv, const float *ori, const uint8_t *mask, const int32_t *labels,
+                  int target, int iters, int t0, float alpha, float eps, float scale, psg_stream_t stream);
+/* confusion matrix conf[label][pred] += 1 (int64 [ncls][ncls]), NB_nontarget_test_semseg.py:193-211 */
+int psg_confusion_matrix(const float *logp, const int32_t *labels, int64_t rows, int ncls, int64_t *conf,
+                         psg_stream_t stream);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t psg_launch_count(void);
+/* per-kernel-family device timing of the engine (CUDA event pairs on the launching stream);
+ * collect() synchronises the device, fills ms / launch counts per family and resets. */
+int psg_prof_enable(int on);
+int psg_prof_ncat(void);
+const char *psg_prof_name(int cat);
+int psg_prof_collect(double *ms_by_cat, int64_t *count_by_cat);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,178 @@
+// fps.cu -- farthest point sampling (reference: PointNet/models/pointnet_util.py:63-84).
+//
+// One persistent CTA per problem (= one cloud of one forward pass).  The running min-distance
+// lives in registers, the cloud in registers + shared memory, and each of the npoint dependent
+// rounds costs ONE block barrier: a per-thread scan, two warp REDUX instructions (max of the
+// distance bits, then min index among the maxima = torch.max's first-max tie-break), one shared
+// write per warp, the barrier, and a second REDUX pair that every warp performs redundantly on the
+// 32 per-warp candidates.  Distances use the oracle's exact op order (no FMA).
+//
+// Many problems (blocks x attack iterations) are launched at once, which is what turns the
+// latency-bound recurrence into a throughput problem on 148 SMs (SURVEY.md finding 2).
+#include "psg_common.cuh"
+#include "psg_internal.h"
+
+namespace {
+
+constexpr int kIntMax = 0x7fffffff;
+
+__device__ __forceinline__ void warp_argmax(unsigned &bits, int &idx)
+{
+    unsigned m = __reduce_max_sync(0xffffffffu, bits);
+    int cand = (bits == m) ? idx : kIntMax;
+    idx = __reduce_min_sync(0xffffffffu, cand);
+    bits = m;
+}
+
+// MODE 0: coordinates in registers (+ shared copy for the centroid broadcast), N <= THREADS*PPT
+// MODE 1: coordinates only in shared memory (N <= 16384), min-distance in registers
+template <int THREADS, int PPT, int MODE>
+__global__ void __launch_bounds__(THREADS)
+fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, int N, int npoint,
+           const int *__restrict__ start, int *__restrict__ out_idx, float *__restrict__ out_xyz)
+{
+    extern __shared__ float smem[];
+    float *sx = smem, *sy = smem + N, *sz = smem + 2 * N;
+    unsigned *red_v = reinterpret_cast<unsigned *>(smem + 3 * N);   // [2][32]
+    int *red_i = reinterpret_cast<int *>(red_v + 64);               // [2][32]
+
+    const int p = blockIdx.x;
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    constexpr int NW = THREADS / 32;
+    const float *cloud = xyz + (long long)(p % nclouds) * cloud_stride;
+
+    float px[MODE == 0 ? PPT : 1], py[MODE == 0 ? PPT : 1], pz[MODE == 0 ? PPT : 1];
+    float mind[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        int i = k * THREADS + t;
+        mind[k] = 1e10f;
+        if (i < N) {
+            float x = cloud[3 * i], y = cloud[3 * i + 1], z = cloud[3 * i + 2];
+            sx[i] = x; sy[i] = y; sz[i] = z;
+            if (MODE == 0) { px[k] = x; py[k] = y; pz[k] = z; }
+        } else if (MODE == 0) { px[k] = py[k] = pz[k] = 0.f; }
+    }
+    int far = start[p];
+    __syncthreads();
+
+    int buf = 0;
+    for (int it = 0; it < npoint; ++it) {
+        const float cx = sx[far], cy = sy[far], cz = sz[far];
+        if (t == 0) {
+            out_idx[(long long)p * npoint + it] = far;
+            if (out_xyz) {
+                float *o = out_xyz + ((long long)p * npoint + it) * 3;
+                o[0] = cx; o[1] = cy; o[2] = cz;
+            }
+        }
+        unsigned best = 0u; int besti = kIntMax;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            int i = k * THREADS + t;
+            if (i < N) {
+                float d = (MODE == 0) ? psg_fpsdist(px[k], py[k], pz[k], cx, cy, cz)
+                                      : psg_fpsdist(sx[i], sy[i], sz[i], cx, cy, cz);
+                if (d < mind[k]) mind[k] = d;
+                unsigned b = __float_as_uint(mind[k]);
+                if (b > best || besti == kIntMax) { best = b; besti = i; }   // i ascends with k
+            }
+        }
+        warp_argmax(best, besti);
+        if (NW > 1) {
+            if (lane == 0) { red_v[buf * 32 + warp] = best; red_i[buf * 32 + warp] = besti; }
+            __syncthreads();
+            best = lane < NW ? red_v[buf * 32 + lane] : 0u;
+            besti = lane < NW ? red_i[buf * 32 + lane] : kIntMax;
+            warp_argmax(best, besti);
+            buf ^= 1;
+        }
+        far = besti;
+    }
+}
+
+// Fallback for clouds that fit neither registers nor shared memory (N > 16384): coordinates are
+// re-read from L2 every round and the min-distance lives in a caller-provided workspace.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+fps_global_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, int N, int npoint,
+                  const int *__restrict__ start, int *__restrict__ out_idx, float *__restrict__ out_xyz,
+                  float *__restrict__ mind_ws)
+{
+    __shared__ unsigned red_v[64];
+    __shared__ int red_i[64];
+    const int p = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int NW = THREADS / 32;
+    const float *cloud = xyz + (long long)(p % nclouds) * cloud_stride;
+    float *mind = mind_ws + (long long)p * N;
+    for (int i = t; i < N; i += THREADS) mind[i] = 1e10f;
+    int far = start[p];
+    int buf = 0;
+    for (int it = 0; it < npoint; ++it) {
+        const float cx = cloud[3 * far], cy = cloud[3 * far + 1], cz = cloud[3 * far + 2];
+        if (t == 0) {
+            out_idx[(long long)p * npoint + it] = far;
+            if (out_xyz) {
+                float *o = out_xyz + ((long long)p * npoint + it) * 3;
+                o[0] = cx; o[1] = cy; o[2] = cz;
+            }
+        }
+        unsigned best = 0u; int besti = kIntMax;
+        for (int i = t; i < N; i += THREADS) {
+            float d = psg_fpsdist(cloud[3 * i], cloud[3 * i + 1], cloud[3 * i + 2], cx, cy, cz);
+            float m = mind[i];
+            if (d < m) { m = d; mind[i] = d; }
+            unsigned b = __float_as_uint(m);
+            if (b > best || besti == kIntMax) { best = b; besti = i; }
+        }
+        warp_argmax(best, besti);
+        if (lane == 0) { red_v[buf * 32 + warp] = best; red_i[buf * 32 + warp] = besti; }
+        __syncthreads();
+        best = lane < NW ? red_v[buf * 32 + lane] : 0u;
+        besti = lane < NW ? red_i[buf * 32 + lane] : kIntMax;
+        warp_argmax(best, besti);
+        buf ^= 1;
+        far = besti;
+    }
+}
+
+template <int THREADS, int PPT, int MODE>
+int launch_fps(const float *xyz, long long cloud_stride, int nclouds, int P, int N, int npoint,
+               const int *start, int *out_idx, float *out_xyz, cudaStream_t st)
+{
+    size_t smem = (size_t)3 * N * sizeof(float) + 128 * sizeof(int);
+    auto kern = fps_kernel<THREADS, PPT, MODE>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return PSG_ECUDA;
+    }
+    kern<<<P, THREADS, smem, st>>>(xyz, cloud_stride, nclouds, N, npoint, start, out_idx, out_xyz);
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}
+
+}  // namespace
+
+size_t psg_fps_workspace_bytes(int P, int N)
+{
+    return N > 16384 ? (size_t)P * N * sizeof(float) : 0;
+}
+
+int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P, int N, int npoint,
+                   const int *start, int *out_idx, float *out_xyz, void *ws, size_t ws_bytes,
+                   cudaStream_t st)
+{
+    if (P <= 0 || N <= 0 || npoint <= 0 || nclouds <= 0) return PSG_EINVAL;
+    if (N <= 64) return launch_fps<64, 1, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    if (N <= 256) return launch_fps<256, 1, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    if (N <= 1024) return launch_fps<512, 2, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    if (N <= 2048) return launch_fps<512, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    if (N <= 4096) return launch_fps<1024, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    if (N <= 16384) return launch_fps<1024, 16, 1>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    if (ws_bytes < psg_fps_workspace_bytes(P, N) || !ws) return PSG_EWORKSPACE;
+    fps_global_kernel<1024><<<P, 1024, 0, st>>>(xyz, cloud_stride, nclouds, N, npoint, start, out_idx, out_xyz,
+                                                (float *)ws);
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}

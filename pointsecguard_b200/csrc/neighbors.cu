@@ -1,0 +1,210 @@
+// neighbors.cu -- ball query, 3-NN (+ inverse-distance weights) and the dense square_distance op.
+// Reference: PointNet/models/pointnet_util.py:19-40 (square_distance), :87-107 (query_ball_point),
+// :301-307 (3-NN + weights inside PointNetFeaturePropagation.forward).
+//
+// The reference materialises [B,S,N] distance and index tensors and fully sorts them.  Here the
+// cloud is staged once per CTA in shared memory (SoA + |p|^2) and
+//   * ball query: one warp per centroid scans the cloud 32 points at a time, compacts the in-radius
+//     lanes with a ballot/popc prefix, stops as soon as every radius has nsample hits, and pads with
+//     the first hit.  Up to two radii (the MSG pair) share one scan.
+//   * 3-NN: one thread per fine point keeps a register top-3 over the (broadcast) coarse points;
+//     strict '<' keeps the lowest index among equal distances.
+// Distances are computed in the oracle's exact op order so the indices are bit-identical.
+#include "psg_common.cuh"
+#include "psg_internal.h"
+
+namespace {
+
+constexpr int kBallChunk = 4096;   // points staged per pass: 4 arrays * 16 KB = 64 KB
+
+template <int NR>
+__global__ void __launch_bounds__(1024)
+ball_query_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, int N,
+                  const float *__restrict__ new_xyz, int S, float r2a, float r2b, int Ka, int Kb,
+                  int *__restrict__ outa, int *__restrict__ outb)
+{
+    extern __shared__ float smem[];
+    float *sx = smem, *sy = sx + kBallChunk, *sz = sy + kBallChunk, *sn = sz + kBallChunk;
+    const int p = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const int s = blockIdx.x * nwarps + warp;
+    const float *cloud = xyz + (long long)(p % nclouds) * cloud_stride;
+    const bool active = s < S;
+
+    float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
+    if (active) {
+        const float *q = new_xyz + ((long long)p * S + s) * 3;
+        qx = q[0]; qy = q[1]; qz = q[2];
+        qn = psg_sqnorm(qx, qy, qz);
+    }
+    int *oa = outa + ((long long)p * S + (active ? s : 0)) * Ka;
+    int *ob = (NR == 2) ? outb + ((long long)p * S + (active ? s : 0)) * Kb : nullptr;
+    int cnta = 0, cntb = 0, firsta = -1, firstb = -1;
+    bool done = !active;
+
+    for (int base0 = 0; base0 < N; base0 += kBallChunk) {
+        const int n = min(kBallChunk, N - base0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float *c = cloud + (long long)(base0 + i) * 3;
+            float x = c[0], y = c[1], z = c[2];
+            sx[i] = x; sy[i] = y; sz[i] = z; sn[i] = psg_sqnorm(x, y, z);
+        }
+        __syncthreads();
+        if (done) continue;
+        for (int b = 0; b < n; b += 32) {
+            const int i = b + lane;
+            bool ha = false, hb = false;
+            if (i < n) {
+                float d = psg_sqdist(qx, qy, qz, qn, sx[i], sy[i], sz[i], sn[i]);
+                ha = !(d > r2a);
+                if (NR == 2) hb = !(d > r2b);
+            }
+            unsigned ma = __ballot_sync(0xffffffffu, ha && cnta < Ka);
+            if (ma) {
+                if (firsta < 0) firsta = base0 + b + __ffs(ma) - 1;
+                int pos = cnta + __popc(ma & ((1u << lane) - 1u));
+                if (ha && pos < Ka) oa[pos] = base0 + i;
+                cnta = min(Ka, cnta + __popc(ma));
+            }
+            if (NR == 2) {
+                unsigned mb = __ballot_sync(0xffffffffu, hb && cntb < Kb);
+                if (mb) {
+                    if (firstb < 0) firstb = base0 + b + __ffs(mb) - 1;
+                    int pos = cntb + __popc(mb & ((1u << lane) - 1u));
+                    if (hb && pos < Kb) ob[pos] = base0 + i;
+                    cntb = min(Kb, cntb + __popc(mb));
+                }
+            }
+            if (cnta >= Ka && (NR == 1 || cntb >= Kb)) { done = true; break; }
+        }
+    }
+    if (active) {
+        // pointnet_util.py:104-106: unfilled slots take the first hit (N if there was none)
+        const int fa = firsta < 0 ? N : firsta;
+        for (int k = cnta + lane; k < Ka; k += 32) oa[k] = fa;
+        if (NR == 2) {
+            const int fb = firstb < 0 ? N : firstb;
+            for (int k = cntb + lane; k < Kb; k += 32) ob[k] = fb;
+        }
+    }
+}
+
+constexpr int kNnChunk = 2048;
+
+__global__ void __launch_bounds__(256)
+three_nn_kernel(const float *__restrict__ xyz1, long long stride1, int nclouds1, int N,
+                const float *__restrict__ xyz2, int S,
+                int *__restrict__ idx, float *__restrict__ wout, float *__restrict__ d2out)
+{
+    __shared__ float sx[kNnChunk], sy[kNnChunk], sz[kNnChunk], sn[kNnChunk];
+    const int p = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float *fine = xyz1 + (long long)(p % nclouds1) * stride1;
+    const float *coarse = xyz2 + (long long)p * S * 3;
+    float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
+    if (i < N) { qx = fine[3 * i]; qy = fine[3 * i + 1]; qz = fine[3 * i + 2]; qn = psg_sqnorm(qx, qy, qz); }
+    float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY;
+    int i0 = -1, i1 = -1, i2 = -1;
+    for (int base = 0; base < S; base += kNnChunk) {
+        const int n = min(kNnChunk, S - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const float *c = coarse + (long long)(base + j) * 3;
+            float x = c[0], y = c[1], z = c[2];
+            sx[j] = x; sy[j] = y; sz[j] = z; sn[j] = psg_sqnorm(x, y, z);
+        }
+        __syncthreads();
+        if (i >= N) continue;
+        for (int j = 0; j < n; ++j) {
+            float d = psg_sqdist(qx, qy, qz, qn, sx[j], sy[j], sz[j], sn[j]);
+            if (d < d2 || i2 < 0) {
+                const int jj = base + j;
+                if (d < d1 || i1 < 0) {
+                    d2 = d1; i2 = i1;
+                    if (d < d0 || i0 < 0) { d1 = d0; i1 = i0; d0 = d; i0 = jj; }
+                    else { d1 = d; i1 = jj; }
+                } else { d2 = d; i2 = jj; }
+            }
+        }
+    }
+    if (i < N) {
+        long long o = ((long long)p * N + i) * 3;
+        idx[o] = i0; idx[o + 1] = i1; idx[o + 2] = i2;
+        // pointnet_util.py:305-307: recip = 1/(d+1e-8); w = recip / (r0 + r1 + r2)
+        float r0 = __fdiv_rn(1.0f, __fadd_rn(d0, 1e-8f));
+        float r1 = __fdiv_rn(1.0f, __fadd_rn(d1, 1e-8f));
+        float r2 = __fdiv_rn(1.0f, __fadd_rn(d2, 1e-8f));
+        float nrm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        if (wout) { wout[o] = __fdiv_rn(r0, nrm); wout[o + 1] = __fdiv_rn(r1, nrm); wout[o + 2] = __fdiv_rn(r2, nrm); }
+        if (d2out) { d2out[o] = d0; d2out[o + 1] = d1; d2out[o + 2] = d2; }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+square_distance_kernel(const float *__restrict__ src, const float *__restrict__ dst, int N, int M,
+                       float *__restrict__ out)
+{
+    const int b = blockIdx.z;
+    const int i = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const float *s = src + ((long long)b * N + i) * 3;
+    const float *d = dst + ((long long)b * M + j) * 3;
+    float sx = s[0], sy = s[1], sz = s[2], dx = d[0], dy = d[1], dz = d[2];
+    out[((long long)b * N + i) * M + j] =
+        psg_sqdist(sx, sy, sz, psg_sqnorm(sx, sy, sz), dx, dy, dz, psg_sqnorm(dx, dy, dz));
+}
+
+}  // namespace
+
+int psg_ball_query_launch(const float *xyz, long long cloud_stride, int nclouds, int P, int N,
+                          const float *new_xyz, int S, int nr, const double *radius, const int *nsample,
+                          int *out0, int *out1, cudaStream_t st)
+{
+    if (P <= 0 || N <= 0 || S <= 0 || nr < 1 || nr > 2) return PSG_EINVAL;
+    const int warps = S >= 32 ? 32 : (S >= 8 ? 8 : 1);
+    dim3 grid((S + warps - 1) / warps, P);
+    const size_t smem = 4 * kBallChunk * sizeof(float);
+    // pointnet_util.py:102 compares the float32 tensor against radius**2 (a Python double, cast to
+    // the tensor dtype by the comparison)
+    const float r2a = (float)(radius[0] * radius[0]);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(ball_query_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(ball_query_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return PSG_ECUDA;
+        attr_done = true;
+    }
+    if (nr == 1) {
+        ball_query_kernel<1><<<grid, warps * 32, smem, st>>>(xyz, cloud_stride, nclouds, N, new_xyz, S, r2a, 0.f,
+                                                            nsample[0], 0, out0, nullptr);
+    } else {
+        const float r2b = (float)(radius[1] * radius[1]);
+        ball_query_kernel<2><<<grid, warps * 32, smem, st>>>(xyz, cloud_stride, nclouds, N, new_xyz, S, r2a, r2b,
+                                                            nsample[0], nsample[1], out0, out1);
+    }
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}
+
+int psg_three_nn_launch(const float *xyz1, long long stride1, int nclouds1, int P, int N,
+                        const float *xyz2, int S, int *idx, float *w, float *d2, cudaStream_t st)
+{
+    if (P <= 0 || N <= 0 || S < 3) return PSG_EINVAL;
+    dim3 grid((N + 255) / 256, P);
+    three_nn_kernel<<<grid, 256, 0, st>>>(xyz1, stride1, nclouds1, N, xyz2, S, idx, w, d2);
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}
+
+int psg_square_distance_launch(const float *src, const float *dst, int B, int N, int M, float *out,
+                               cudaStream_t st)
+{
+    if (B <= 0 || N <= 0 || M <= 0 || N > 65535 || B > 65535) return PSG_EINVAL;
+    dim3 grid((M + 255) / 256, N, B);
+    square_distance_kernel<<<grid, 256, 0, st>>>(src, dst, N, M, out);
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}

@@ -1,0 +1,676 @@
+// net.cu -- the whole-network engine: PointNet++ sem-seg forward, input-gradient backward and the
+// norm-bounded attack loop as plain sequences of kernel launches on one stream.
+//
+// Reference: PointNet/models/pointnet2_sem_seg.py:22-40, pointnet2_sem_seg_msg.py:23-41 (forward),
+// PointNet/models/pointnet_util.py:166-320 (SA / SA-MSG / FP modules), autograd of the same for the
+// backward, PointNet/attacks/torchattacks/attacks/nontarget.py:28-39 and target.py:31-43 (loops).
+//
+// Design:
+//   * Geometry (FPS, ball query, 3-NN, and the source-sorted CSRs the deterministic gather-backward
+//     needs) depends only on xyz and on the FPS start draws, so for colour attacks it is computed
+//     for all T forwards of an attack in one batched pass (T*B FPS problems fill the 148 SMs) and
+//     kept resident as int32 indices + fp32 weights.
+//   * Activations live in T-layout (psg_common.cuh); every conv(1x1)+BN(eval)+ReLU is one GEMM with
+//     the BN folded into W,b; FP concat is a two-source A operand; dgrad only, no wgrad.
+//   * No allocation, no synchronisation, no host round trip inside forward / backward / attack.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/psg_b200.h"
+#include "psg_common.cuh"
+#include "psg_internal.h"
+
+long long g_psg_launch_count = 0;
+
+// ------------------------------------------------------------------------------------------------
+// per-kernel-family device timing (bench.py's live roofline measurement).  When enabled, every
+// launch of the engine is bracketed by a CUDA event pair on the launching stream; collect() syncs
+// and sums the elapsed times per family.  Off by default (zero overhead, graph-capture safe).
+// ------------------------------------------------------------------------------------------------
+enum { PF_FPS, PF_BALL, PF_NN3, PF_CSR, PF_PACK, PF_GROUP, PF_GEMM_FWD, PF_MAXPOOL, PF_INTERP, PF_HEAD, PF_LOSS,
+       PF_GEMM_BWD, PF_MAXPOOL_BWD, PF_SEGSUM, PF_COPY, PF_PGD, PF_NCAT };
+static const char *kProfNames[PF_NCAT] = {"fps", "ball_query", "three_nn", "csr_build", "pack", "group", "gemm_fwd",
+                                          "maxpool", "interp", "head", "loss_grad", "gemm_bwd", "maxpool_bwd", "segsum",
+                                          "copy_cols", "pgd_update"};
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cat; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+    int cat; cudaStream_t st; cudaEvent_t a; bool on;
+    ProfScope(int c, cudaStream_t s) : cat(c), st(s), a(nullptr), on(g_prof_on)
+    {
+        if (on) { a = prof_event(); cudaEventRecord(a, st); }
+    }
+    void end()
+    {
+        if (on) { cudaEvent_t b = prof_event(); cudaEventRecord(b, st); g_prof_recs.push_back(ProfRec{a, b, cat}); }
+    }
+};
+}  // namespace
+
+extern "C" int psg_prof_enable(int on) { g_prof_on = on != 0; return PSG_OK; }
+extern "C" int psg_prof_ncat(void) { return PF_NCAT; }
+extern "C" const char *psg_prof_name(int cat) { return cat >= 0 && cat < PF_NCAT ? kProfNames[cat] : ""; }
+extern "C" int psg_prof_collect(double *ms_by_cat, int64_t *count_by_cat)
+{
+    if (cudaDeviceSynchronize() != cudaSuccess) return PSG_ECUDA;
+    for (int c = 0; c < PF_NCAT; ++c) { if (ms_by_cat) ms_by_cat[c] = 0.0; if (count_by_cat) count_by_cat[c] = 0; }
+    for (const ProfRec &r : g_prof_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        if (ms_by_cat) ms_by_cat[r.cat] += ms;
+        if (count_by_cat) count_by_cat[r.cat] += 1;
+        g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    return PSG_OK;
+}
+
+#define PSG_RUN(cat, call)                \
+    do {                                  \
+        ProfScope ps__(cat, st);          \
+        int rc__ = (call);                \
+        ps__.end();                       \
+        if (rc__ != PSG_OK) return rc__;  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// one folded layer
+// ------------------------------------------------------------------------------------------------
+struct psg_mlp {
+    int cin, cout;
+    int kpad;        // input columns, multiple of 16
+    int npad;        // output columns, multiple of 16
+    int nwf, nwb;    // packed widths (multiples of 64) of the forward / dgrad weight copies
+    float *wf;       // [kpad/4][nwf][4]   wf[(k/4, n, k%4)] = W[n][k]
+    float *wb;       // [npad/4][nwb][4]   wb[(n/4, k, n%4)] = W[n][k]
+    float *bias;     // [nwf]
+    float *wf_tf32, *wb_tf32;   // UMMA-canonical copies for the tcgen05 path (gemm_tc.cu), may be null
+};
+
+extern "C" psg_mlp *psg_mlp_create(const float *w, const float *b, int cin, int cout)
+{
+    if (!w || cin <= 0 || cout <= 0) return nullptr;
+    psg_mlp *m = new (std::nothrow) psg_mlp();
+    if (!m) return nullptr;
+    m->cin = cin; m->cout = cout;
+    m->kpad = round_up(cin, 16);
+    m->npad = round_up(cout, 16);
+    m->nwf = round_up(m->npad, 64);
+    m->nwb = round_up(m->kpad, 64);
+    std::vector<float> hf((size_t)m->kpad * m->nwf, 0.f), hb((size_t)m->npad * m->nwb, 0.f), hbias(m->nwf, 0.f);
+    for (int n = 0; n < cout; ++n) {
+        for (int k = 0; k < cin; ++k) {
+            const float v = w[(size_t)n * cin + k];
+            hf[((size_t)(k >> 2) * m->nwf + n) * 4 + (k & 3)] = v;
+            hb[((size_t)(n >> 2) * m->nwb + k) * 4 + (n & 3)] = v;
+        }
+        hbias[n] = b ? b[n] : 0.f;
+    }
+    m->wf = m->wb = m->bias = m->wf_tf32 = m->wb_tf32 = nullptr;
+    bool ok = cudaMalloc(&m->wf, hf.size() * 4) == cudaSuccess && cudaMalloc(&m->wb, hb.size() * 4) == cudaSuccess &&
+              cudaMalloc(&m->bias, hbias.size() * 4) == cudaSuccess;
+    ok = ok && cudaMemcpy(m->wf, hf.data(), hf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(m->wb, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(m->bias, hbias.data(), hbias.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) { psg_mlp_destroy(m); return nullptr; }
+    return m;
+}
+
+extern "C" void psg_mlp_destroy(psg_mlp *m)
+{
+    if (!m) return;
+    cudaFree(m->wf); cudaFree(m->wb); cudaFree(m->bias); cudaFree(m->wf_tf32); cudaFree(m->wb_tf32);
+    delete m;
+}
+
+static int run_gemm(const PsgGemmArgs &g, int mode, cudaStream_t st)
+{
+    return mode == 1 ? psg_gemm_tc(g, st) : psg_gemm_simt(g, st);
+}
+
+// forward of one layer: Out = act([A1 | A2] W^T + b)
+static int mlp_fwd(const psg_mlp *m, TView a1, int k1chunks, TView a2, int k2chunks, long long rows, TView out,
+                   int relu, int mode, cudaStream_t st)
+{
+    if ((k1chunks + k2chunks) * 4 != m->kpad) return PSG_EINVAL;
+    PsgGemmArgs g;
+    g.A1 = a1; g.k1chunks = k1chunks; g.A2 = a2; g.k2chunks = k2chunks;
+    g.W = m->wf; g.Nw = m->nwf; g.bias = m->bias; g.Out = out; g.nout_pad = m->npad;
+    g.Mask = TView{nullptr, 0, 0};
+    g.mtiles = (int)(round_up_ll(rows, 128) / 128);
+    g.epi = relu ? PSG_EPI_BIAS_RELU : PSG_EPI_BIAS;
+    return run_gemm(g, mode, st);
+}
+
+// dgrad of one layer: dX = (dY W) [. (mask > 0)]
+static int mlp_bwd(const psg_mlp *m, TView dy, long long rows, TView dx, const TView *mask, int mode, cudaStream_t st)
+{
+    PsgGemmArgs g;
+    g.A1 = dy; g.k1chunks = m->npad / 4; g.A2 = TView{nullptr, 0, 0}; g.k2chunks = 0;
+    g.W = m->wb; g.Nw = m->nwb; g.bias = nullptr; g.Out = dx; g.nout_pad = m->kpad;
+    g.Mask = mask ? *mask : TView{nullptr, 0, 0};
+    g.mtiles = (int)(round_up_ll(rows, 128) / 128);
+    g.epi = mask ? PSG_EPI_MASK : PSG_EPI_NONE;
+    return run_gemm(g, mode, st);
+}
+
+extern "C" int psg_mlp_forward(const psg_mlp *m, const float *a1_base, int a1_wchunks, int a1_c0, int k1chunks,
+                               const float *a2_base, int a2_wchunks, int a2_c0, int k2chunks, int64_t rows,
+                               float *out_base, int out_wchunks, int relu, int mode, psg_stream_t stream)
+{
+    if (!m || !a1_base || !out_base || rows <= 0) return PSG_EINVAL;
+    return mlp_fwd(m, TView{(float *)a1_base, a1_wchunks, a1_c0}, k1chunks, TView{(float *)a2_base, a2_wchunks, a2_c0},
+                   k2chunks, rows, TView{out_base, out_wchunks, 0}, relu, mode, (cudaStream_t)stream);
+}
+
+extern "C" int psg_mlp_backward(const psg_mlp *m, const float *dy_base, int dy_wchunks, int64_t rows, float *dx_base,
+                                int dx_wchunks, const float *mask_base, int mask_wchunks, int mode, psg_stream_t stream)
+{
+    if (!m || !dy_base || !dx_base || rows <= 0) return PSG_EINVAL;
+    TView mk{(float *)mask_base, mask_wchunks, 0};
+    return mlp_bwd(m, TView{(float *)dy_base, dy_wchunks, 0}, rows, TView{dx_base, dx_wchunks, 0},
+                   mask_base ? &mk : nullptr, mode, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the network
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Bump {
+    char *base;
+    size_t off;
+    template <class T> T *take(size_t n)
+    {
+        off = (off + 1023) & ~(size_t)1023;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+    float *tl(long long rows, int cpad) { return take<float>(tl_bytes(rows, cpad) / sizeof(float)); }
+};
+
+struct Branch {
+    int K, nl;
+    psg_mlp *mlp[3];
+    int gpad;              // padded width of the grouped input (D + 3 -> multiple of 16)
+    int col0;              // first output column inside the level's feature tensor
+    float *G, *Y[3];
+    unsigned char *arg;
+    int *ball;             // [T*B][S][K]
+    int *csr_off, *csr_perm;   // [T*B][R+1], [T*B][S*K]
+};
+
+struct SaLevel {
+    int S, nbr;
+    double radius[2];
+    Branch br[2];
+};
+
+struct FpLevel {
+    int nl;
+    psg_mlp *mlp[3];
+    int C1, C2;            // skip width (fine level features), interpolated width (coarse features)
+    float *I, *Y[3];
+    int *nn_idx;           // [T*B][Nf][3]
+    float *nn_w;           // [T*B][Nf][3]
+    int *csr_off, *csr_perm;   // [T*B][Nc+1], [T*B][Nf*3]
+};
+
+}  // namespace
+
+struct psg_net {
+    int in_channels, ncls, mode;
+    SaLevel sa[4];
+    FpLevel fp[4];
+    psg_mlp *conv1, *conv2;
+    // bound problem
+    int B, N, T;
+    int npts[5], cfeat[5], wfeat[5];
+    float *xyz0;           // [B][N][3]
+    float *xyz[5];         // [T*B][S_l][3], l = 1..4
+    int *fps_idx[5];
+    int *starts;           // [4][T][B]
+    void *fps_ws; size_t fps_ws_bytes;
+    void *csr_ws;
+    float *feats[5], *dfeat[5];
+    float *H, *Z, *dZ;
+    float *S[2]; size_t scratch_floats;
+    bool bound;
+    int last_t;
+};
+
+static psg_mlp *make_layer(const psg_mlp_desc &d) { return psg_mlp_create(d.w_host, d.b_host, d.cin, d.cout); }
+
+extern "C" psg_net *psg_net_create(const psg_net_desc *d)
+{
+    if (!d || d->in_channels < 3 || d->in_channels > 16 || d->num_classes < 2 || d->num_classes > 16) return nullptr;
+    psg_net *n = new (std::nothrow) psg_net();
+    if (!n) return nullptr;
+    memset(n, 0, sizeof(*n));
+    n->in_channels = d->in_channels; n->ncls = d->num_classes; n->mode = d->mlp_mode;
+    bool ok = true;
+    int cprev = d->in_channels;
+    n->cfeat[0] = cprev; n->wfeat[0] = round_up(cprev, 16);
+    for (int l = 0; l < 4 && ok; ++l) {
+        const psg_sa_desc &s = d->sa[l];
+        SaLevel &L = n->sa[l];
+        L.S = s.npoint; L.nbr = s.nbranch;
+        if (s.nbranch < 1 || s.nbranch > 2 || s.npoint < 3) { ok = false; break; }
+        int col = 0;
+        for (int b = 0; b < s.nbranch && ok; ++b) {
+            Branch &R = L.br[b];
+            L.radius[b] = s.radius[b];
+            R.K = s.nsample[b]; R.nl = s.nlayers[b];
+            if ((R.K != 16 && R.K != 32) || R.nl < 1 || R.nl > 3) { ok = false; break; }
+            R.gpad = round_up(cprev + 3, 16);
+            int cin = cprev + 3;
+            for (int j = 0; j < R.nl; ++j) {
+                if (s.mlp[b][j].cin != cin) { ok = false; break; }
+                R.mlp[j] = make_layer(s.mlp[b][j]);
+                if (!R.mlp[j]) { ok = false; break; }
+                cin = s.mlp[b][j].cout;
+            }
+            if (!ok) break;
+            if (cin % 16) { ok = false; break; }      // branch outputs are concatenated on 16-column boundaries
+            R.col0 = col; col += cin;
+        }
+        cprev = col;
+        n->cfeat[l + 1] = col; n->wfeat[l + 1] = col;
+    }
+    // FP levels: fp[f] has fine level f, coarse level f+1; runs f = 3, 2, 1, 0
+    int cup = n->wfeat[4];
+    for (int f = 3; f >= 0 && ok; --f) {
+        const psg_fp_desc &s = d->fp[f];
+        FpLevel &F = n->fp[f];
+        F.nl = s.nlayers;
+        F.C1 = f > 0 ? n->wfeat[f] : 0;
+        F.C2 = cup;
+        if (F.nl < 1 || F.nl > 3 || s.mlp[0].cin != F.C1 + F.C2) { ok = false; break; }
+        int cin = s.mlp[0].cin;
+        for (int j = 0; j < F.nl; ++j) {
+            if (s.mlp[j].cin != cin) { ok = false; break; }
+            F.mlp[j] = make_layer(s.mlp[j]);
+            if (!F.mlp[j]) { ok = false; break; }
+            cin = s.mlp[j].cout;
+        }
+        if (cin % 16) ok = false;
+        cup = cin;
+    }
+    if (ok) {
+        n->conv1 = make_layer(d->conv1);
+        n->conv2 = make_layer(d->conv2);
+        ok = n->conv1 && n->conv2 && d->conv1.cin == cup && d->conv2.cin == d->conv1.cout && d->conv2.cout == n->ncls &&
+             d->conv1.cout % 16 == 0;
+    }
+    if (!ok) { psg_net_destroy(n); return nullptr; }
+    return n;
+}
+
+extern "C" void psg_net_destroy(psg_net *n)
+{
+    if (!n) return;
+    for (int l = 0; l < 4; ++l)
+        for (int b = 0; b < 2; ++b)
+            for (int j = 0; j < 3; ++j) psg_mlp_destroy(n->sa[l].br[b].mlp[j]);
+    for (int f = 0; f < 4; ++f)
+        for (int j = 0; j < 3; ++j) psg_mlp_destroy(n->fp[f].mlp[j]);
+    psg_mlp_destroy(n->conv1); psg_mlp_destroy(n->conv2);
+    delete n;
+}
+
+extern "C" int psg_net_set_mlp_mode(psg_net *n, int mode)
+{
+    if (!n || mode < 0 || mode > 1) return PSG_EINVAL;
+    n->mode = mode;
+    return PSG_OK;
+}
+
+// carve (or, with base == null, only size) the workspace
+static size_t plan(psg_net *n, int B, int N, int T, char *base)
+{
+    Bump bp{base, 0};
+    const long long P = (long long)T * B;
+    n->npts[0] = N;
+    for (int l = 0; l < 4; ++l) n->npts[l + 1] = n->sa[l].S;
+    n->xyz0 = bp.take<float>((size_t)B * N * 3);
+    n->starts = bp.take<int>((size_t)4 * P);
+    n->fps_ws_bytes = 0;
+    size_t csr_scratch = 0, scratch = 0;
+    for (int l = 1; l <= 4; ++l) {
+        const int S = n->npts[l], R = n->npts[l - 1];
+        n->xyz[l] = bp.take<float>((size_t)P * S * 3);
+        n->fps_idx[l] = bp.take<int>((size_t)P * S);
+        size_t w = psg_fps_workspace_bytes((int)P, R);
+        if (w > n->fps_ws_bytes) n->fps_ws_bytes = w;
+        SaLevel &L = n->sa[l - 1];
+        for (int b = 0; b < L.nbr; ++b) {
+            Branch &Br = L.br[b];
+            const long long M = (long long)S * Br.K;
+            Br.ball = bp.take<int>((size_t)P * M);
+            Br.csr_off = bp.take<int>((size_t)P * (R + 1));
+            Br.csr_perm = bp.take<int>((size_t)P * M);
+            size_t c = psg_csr_scratch_bytes(P, (int)M, R);
+            if (c > csr_scratch) csr_scratch = c;
+            const long long rows = (long long)B * M;
+            Br.G = bp.tl(rows, Br.gpad);
+            size_t wmax = Br.gpad;
+            for (int j = 0; j < Br.nl; ++j) {
+                Br.Y[j] = bp.tl(rows, Br.mlp[j]->npad);
+                if ((size_t)Br.mlp[j]->npad > wmax) wmax = Br.mlp[j]->npad;
+            }
+            Br.arg = bp.take<unsigned char>((size_t)B * S * Br.mlp[Br.nl - 1]->npad);
+            size_t s = (size_t)round_up_ll(rows, 128) * wmax;
+            if (s > scratch) scratch = s;
+        }
+    }
+    for (int f = 0; f < 4; ++f) {
+        FpLevel &F = n->fp[f];
+        const int Nf = n->npts[f], Nc = n->npts[f + 1];
+        F.nn_idx = bp.take<int>((size_t)P * Nf * 3);
+        F.nn_w = bp.take<float>((size_t)P * Nf * 3);
+        F.csr_off = bp.take<int>((size_t)P * (Nc + 1));
+        F.csr_perm = bp.take<int>((size_t)P * Nf * 3);
+        size_t c = psg_csr_scratch_bytes(P, Nf * 3, Nc);
+        if (c > csr_scratch) csr_scratch = c;
+        const long long rows = (long long)B * Nf;
+        F.I = bp.tl(rows, F.C2);
+        size_t wmax = F.C1 + F.C2;
+        for (int j = 0; j < F.nl; ++j) {
+            F.Y[j] = bp.tl(rows, F.mlp[j]->npad);
+            if ((size_t)F.mlp[j]->npad > wmax) wmax = F.mlp[j]->npad;
+        }
+        if (f == 0 && (size_t)n->conv1->npad > wmax) wmax = n->conv1->npad;
+        size_t s = (size_t)round_up_ll(rows, 128) * wmax;
+        if (s > scratch) scratch = s;
+    }
+    for (int l = 0; l <= 4; ++l) {
+        n->feats[l] = bp.tl((long long)B * n->npts[l], n->wfeat[l]);
+        n->dfeat[l] = bp.tl((long long)B * n->npts[l], n->wfeat[l]);
+        size_t s = (size_t)round_up_ll((long long)B * n->npts[l], 128) * n->wfeat[l];
+        if (s > scratch) scratch = s;
+    }
+    n->H = bp.tl((long long)B * N, n->conv1->npad);
+    n->Z = bp.tl((long long)B * N, n->conv2->npad);
+    n->dZ = bp.tl((long long)B * N, n->conv2->npad);
+    n->scratch_floats = scratch;
+    n->S[0] = bp.take<float>(scratch);
+    n->S[1] = bp.take<float>(scratch);
+    n->fps_ws = bp.take<char>(n->fps_ws_bytes ? n->fps_ws_bytes : 16);
+    n->csr_ws = bp.take<char>(csr_scratch);
+    return bp.off + 1024;
+}
+
+extern "C" size_t psg_net_workspace(const psg_net *net, int B, int N, int T)
+{
+    if (!net || B <= 0 || N < 3 || T <= 0) return 0;
+    psg_net tmp = *net;
+    return plan(&tmp, B, N, T, nullptr);
+}
+
+extern "C" int psg_net_bind(psg_net *n, int B, int N, int T, void *ws, size_t ws_bytes)
+{
+    if (!n || !ws || B <= 0 || N < 3 || T <= 0) return PSG_EINVAL;
+    if (((uintptr_t)ws & 1023) != 0) return PSG_EINVAL;
+    for (int l = 0; l < 4; ++l)
+        if (n->sa[l].S > (l == 0 ? N : n->sa[l - 1].S)) return PSG_EINVAL;
+    psg_net tmp = *n;
+    size_t need = plan(&tmp, B, N, T, nullptr);
+    if (ws_bytes < need) return PSG_EWORKSPACE;
+    plan(n, B, N, T, (char *)ws);
+    n->B = B; n->N = N; n->T = T; n->bound = true; n->last_t = -1;
+    return PSG_OK;
+}
+
+#define PSG_TRY(expr)                     \
+    do {                                  \
+        int rc__ = (expr);                \
+        if (rc__ != PSG_OK) return rc__;  \
+    } while (0)
+
+extern "C" int psg_net_set_input(psg_net *n, const float *x, int64_t sb, int64_t sc, int64_t sn, psg_stream_t stream)
+{
+    if (!n || !n->bound || !x) return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    PSG_RUN(PF_PACK, psg_pack_cf(x, sb, sc, sn, n->B, n->in_channels, n->N, TView{n->feats[0], n->wfeat[0] / 4, 0},
+                                 n->wfeat[0], n->xyz0, st));
+    return PSG_OK;
+}
+
+// coordinates of level l for forward t
+static inline const float *lvl_xyz(const psg_net *n, int l, int t)
+{
+    return l == 0 ? n->xyz0 : n->xyz[l] + (size_t)t * n->B * n->npts[l] * 3;
+}
+
+extern "C" int psg_net_geometry(psg_net *n, const int32_t *starts, int T, psg_stream_t stream)
+{
+    if (!n || !n->bound || !starts || T <= 0 || T > n->T) return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = n->B;
+    const int P = T * B;
+    // starts arrive as [4][T][B] for this call's T (device memory)
+    for (int l = 1; l <= 4; ++l) {
+        const int R = n->npts[l - 1], S = n->npts[l];
+        const float *cloud = l == 1 ? n->xyz0 : n->xyz[l - 1];
+        const int nclouds = l == 1 ? B : P;
+        const long long stride = (long long)R * 3;
+        PSG_RUN(PF_FPS, psg_fps_launch(cloud, stride, nclouds, P, R, S, starts + (size_t)(l - 1) * P, n->fps_idx[l], n->xyz[l],
+                               n->fps_ws, n->fps_ws_bytes, st));
+        SaLevel &L = n->sa[l - 1];
+        // MSG: the two radii of a level share one scan of the cloud (pointnet_util.py:246-248)
+        int ns[2] = {L.br[0].K, L.nbr > 1 ? L.br[1].K : 0};
+        PSG_RUN(PF_BALL, psg_ball_query_launch(cloud, stride, nclouds, P, R, n->xyz[l], S, L.nbr, L.radius, ns, L.br[0].ball,
+                                      L.nbr > 1 ? L.br[1].ball : nullptr, st));
+        for (int b = 0; b < L.nbr; ++b)
+            PSG_RUN(PF_CSR, psg_csr_build(L.br[b].ball, P, S * L.br[b].K, R, L.br[b].csr_off, L.br[b].csr_perm, n->csr_ws, st));
+    }
+    for (int f = 0; f < 4; ++f) {
+        FpLevel &F = n->fp[f];
+        const int Nf = n->npts[f], Nc = n->npts[f + 1];
+        const float *fine = f == 0 ? n->xyz0 : n->xyz[f];
+        PSG_RUN(PF_NN3, psg_three_nn_launch(fine, (long long)Nf * 3, f == 0 ? B : P, P, Nf, n->xyz[f + 1], Nc, F.nn_idx, F.nn_w,
+                                    nullptr, st));
+        PSG_RUN(PF_CSR, psg_csr_build(F.nn_idx, P, Nf * 3, Nc, F.csr_off, F.csr_perm, n->csr_ws, st));
+    }
+    return PSG_OK;
+}
+
+static inline TView tv(float *p, int width, int col0 = 0) { return TView{p, width / 4, col0 / 4}; }
+
+extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points, psg_stream_t stream)
+{
+    if (!n || !n->bound || t < 0 || t >= n->T) return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = n->B, mode = n->mode;
+    const TView none{nullptr, 0, 0};
+    for (int l = 1; l <= 4; ++l) {
+        SaLevel &L = n->sa[l - 1];
+        const int S = L.S, R = n->npts[l - 1], D = n->cfeat[l - 1];
+        for (int b = 0; b < L.nbr; ++b) {
+            Branch &Br = L.br[b];
+            const long long rows = (long long)B * S * Br.K;
+            PSG_RUN(PF_GROUP, psg_group(tv(n->feats[l - 1], n->wfeat[l - 1]), D, lvl_xyz(n, l - 1, t), (long long)R * 3, B, R,
+                              lvl_xyz(n, l, t), Br.ball + (size_t)t * B * S * Br.K, B, S, Br.K, tv(Br.G, Br.gpad), Br.gpad,
+                              st));
+            TView cur = tv(Br.G, Br.gpad);
+            int kw = Br.gpad;
+            for (int j = 0; j < Br.nl; ++j) {
+                TView out = tv(Br.Y[j], Br.mlp[j]->npad);
+                PSG_RUN(PF_GEMM_FWD, mlp_fwd(Br.mlp[j], cur, kw / 4, none, 0, rows, out, 1, mode, st));
+                cur = out; kw = Br.mlp[j]->npad;
+            }
+            PSG_RUN(PF_MAXPOOL, psg_maxpool(cur, (long long)B * S, Br.K, kw, tv(n->feats[l], n->wfeat[l], Br.col0), Br.arg, st));
+        }
+    }
+    // feature propagation, coarse to fine
+    float *up = n->feats[4];
+    int upw = n->wfeat[4];
+    for (int f = 3; f >= 0; --f) {
+        FpLevel &F = n->fp[f];
+        const int Nf = n->npts[f], Nc = n->npts[f + 1];
+        const long long rows = (long long)B * Nf;
+        PSG_RUN(PF_INTERP, psg_interp(tv(up, upw), Nc, F.nn_idx + (size_t)t * B * Nf * 3, F.nn_w + (size_t)t * B * Nf * 3, B, Nf,
+                           F.C2 / 4, tv(F.I, F.C2), st));
+        TView a1 = F.C1 ? tv(n->feats[f], n->wfeat[f]) : tv(F.I, F.C2);
+        TView a2 = F.C1 ? tv(F.I, F.C2) : none;
+        int k1 = F.C1 ? F.C1 / 4 : F.C2 / 4, k2 = F.C1 ? F.C2 / 4 : 0;
+        for (int j = 0; j < F.nl; ++j) {
+            TView out = tv(F.Y[j], F.mlp[j]->npad);
+            PSG_RUN(PF_GEMM_FWD, mlp_fwd(F.mlp[j], a1, k1, a2, k2, rows, out, 1, mode, st));
+            a1 = out; k1 = F.mlp[j]->npad / 4; a2 = none; k2 = 0;
+        }
+        up = F.Y[F.nl - 1]; upw = F.mlp[F.nl - 1]->npad;
+    }
+    const long long rows0 = (long long)B * n->N;
+    PSG_RUN(PF_GEMM_FWD, mlp_fwd(n->conv1, tv(up, upw), upw / 4, none, 0, rows0, tv(n->H, n->conv1->npad), 1, mode, st));
+    PSG_RUN(PF_GEMM_FWD, mlp_fwd(n->conv2, tv(n->H, n->conv1->npad), n->conv1->npad / 4, none, 0, rows0, tv(n->Z, n->conv2->npad), 0,
+                    mode, st));
+    if (logp) PSG_RUN(PF_HEAD, psg_head_logsoftmax(tv(n->Z, n->conv2->npad), rows0, n->ncls, logp, st));
+    if (l4_points) PSG_RUN(PF_PACK, psg_unpack_cf(tv(n->feats[4], n->wfeat[4]), B, n->cfeat[4], n->npts[4], l4_points, 0, st));
+    n->last_t = t;
+    return PSG_OK;
+}
+
+extern "C" int psg_net_loss_grad(psg_net *n, int kind, const float *dlogp, const int32_t *labels, int target, float scale,
+                                 float kappa, float *loss_rows, psg_stream_t stream)
+{
+    if (!n || !n->bound) return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)n->B * n->N;
+    TView z = tv(n->Z, n->conv2->npad), dz = tv(n->dZ, n->conv2->npad);
+    switch (kind) {
+    case 0:
+        if (!dlogp) return PSG_EINVAL;
+        PSG_RUN(PF_LOSS, psg_dz_from_dlogp(z, dlogp, rows, n->ncls, dz, st));
+        return PSG_OK;
+    case 1:
+        if (!labels && target < 0) return PSG_EINVAL;
+        PSG_RUN(PF_LOSS, psg_dz_ce(z, labels, target, rows, n->ncls, scale, dz, st));
+        return PSG_OK;
+    case 2:
+        if (!labels && target < 0) return PSG_EINVAL;
+        PSG_RUN(PF_LOSS, psg_dz_cw(z, labels, target, rows, n->ncls, kappa, scale, dz, loss_rows, st));
+        return PSG_OK;
+    }
+    return PSG_EINVAL;
+}
+
+// Backward through a chain of folded layers.  `top` is the gradient w.r.t. the pre-activation of
+// the last layer; Ys[j] the forward output of layer j.  Ping-pongs between the two scratch buffers,
+// starting with the one `top` does not live in; returns the buffer index holding dIn.
+static int chain_bwd(psg_net *n, psg_mlp *const *mlps, float *const *Ys, int nl, long long rows, TView top, int top_buf,
+                     int *out_buf, cudaStream_t st)
+{
+    TView cur = top;
+    int dstb = top_buf == 0 ? 1 : 0;
+    for (int j = nl - 1; j >= 0; --j) {
+        TView dx = tv(n->S[dstb], mlps[j]->kpad);
+        if (j > 0) {
+            TView mk = tv(Ys[j - 1], mlps[j - 1]->npad);
+            PSG_RUN(PF_GEMM_BWD, mlp_bwd(mlps[j], cur, rows, dx, &mk, n->mode, st));
+        } else {
+            PSG_RUN(PF_GEMM_BWD, mlp_bwd(mlps[j], cur, rows, dx, nullptr, n->mode, st));
+        }
+        cur = dx;
+        *out_buf = dstb;
+        dstb ^= 1;
+    }
+    return PSG_OK;
+}
+
+extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t stream)
+{
+    if (!n || !n->bound || t < 0 || t >= n->T || t != n->last_t) return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = n->B;
+    // ---- head + feature propagation, fine to coarse ----
+    TView top = tv(n->dZ, n->conv2->npad);
+    int top_buf = -1;
+    for (int f = 0; f <= 3; ++f) {
+        FpLevel &F = n->fp[f];
+        const int Nf = n->npts[f], Nc = n->npts[f + 1];
+        const long long rows = (long long)B * Nf;
+        psg_mlp *mlps[5]; float *Ys[5]; int nl = 0;
+        for (int j = 0; j < F.nl; ++j) { mlps[nl] = F.mlp[j]; Ys[nl] = F.Y[j]; ++nl; }
+        if (f == 0) { mlps[nl] = n->conv1; Ys[nl] = n->H; ++nl; mlps[nl] = n->conv2; Ys[nl] = n->Z; ++nl; }
+        int cat_buf = 0;
+        PSG_TRY(chain_bwd(n, mlps, Ys, nl, rows, top, top_buf, &cat_buf, st));
+        const int catw = F.C1 + F.C2;
+        if (F.C1) PSG_RUN(PF_COPY, psg_copy_cols(tv(n->S[cat_buf], catw), tv(n->dfeat[f], n->wfeat[f]), rows, F.C1, 0, st));
+        // interpolation backward: scatter the three weighted copies to the coarse level, in CSR order
+        const size_t go = (size_t)t * B;
+        if (f < 3) {
+            FpLevel &C = n->fp[f + 1];
+            const int cw = C.mlp[C.nl - 1]->npad;
+            const int dst_buf = cat_buf ^ 1;
+            TView dst = tv(n->S[dst_buf], cw);
+            TView mk = tv(C.Y[C.nl - 1], cw);
+            PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[cat_buf], catw, F.C1), Nf, 3, F.nn_w + go * Nf * 3, F.csr_off + go * (Nc + 1),
+                               F.csr_perm + go * Nf * 3, Nf * 3, Nc, B, F.C2, dst, 0, &mk, st));
+            top = dst; top_buf = dst_buf;
+        } else {
+            PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[cat_buf], catw, F.C1), Nf, 3, F.nn_w + go * Nf * 3, F.csr_off + go * (Nc + 1),
+                               F.csr_perm + go * Nf * 3, Nf * 3, Nc, B, F.C2, tv(n->dfeat[4], n->wfeat[4]), 0, nullptr, st));
+        }
+    }
+    // ---- set abstraction, coarse to fine ----
+    for (int l = 4; l >= 1; --l) {
+        SaLevel &L = n->sa[l - 1];
+        const int S = L.S, R = n->npts[l - 1], D = n->cfeat[l - 1];
+        for (int b = 0; b < L.nbr; ++b) {
+            Branch &Br = L.br[b];
+            const long long rows = (long long)B * S * Br.K;
+            const int cw = Br.mlp[Br.nl - 1]->npad;
+            TView dy = tv(n->S[0], cw);
+            PSG_RUN(PF_MAXPOOL_BWD, psg_maxpool_bwd(tv(n->dfeat[l], n->wfeat[l], Br.col0), tv(n->feats[l], n->wfeat[l], Br.col0), Br.arg,
+                                    (long long)B * S, Br.K, cw, dy, st));
+            int gbuf = 0;
+            PSG_TRY(chain_bwd(n, Br.mlp, Br.Y, Br.nl, rows, dy, 0, &gbuf, st));
+            const size_t go = (size_t)t * B;
+            const int M = S * Br.K;
+            PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[gbuf], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,
+                               B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, st));
+        }
+    }
+    if (grad_x) PSG_RUN(PF_PACK, psg_unpack_cf(tv(n->dfeat[0], n->wfeat[0]), B, n->in_channels, n->N, grad_x, 0, st));
+    return PSG_OK;
+}
+
+extern "C" int psg_net_pgd_update(psg_net *n, float *adv, const float *ori, const uint8_t *mask, int c0, int nc,
+                                  float alpha_signed, float eps, float lo, float hi, psg_stream_t stream)
+{
+    if (!n || !n->bound || !adv || !ori || c0 < 0 || nc <= 0 || c0 + nc > n->in_channels) return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    PSG_RUN(PF_PGD, psg_pgd_update(adv, ori, tv(n->dfeat[0], n->wfeat[0]), tv(n->feats[0], n->wfeat[0]), mask, n->B,
+                                   n->in_channels, n->N, c0, nc, alpha_signed, eps, lo, hi, st));
+    return PSG_OK;
+}
+
+extern "C" int psg_nb_attack(psg_net *n, float *adv, const float *ori, const uint8_t *mask, const int32_t *labels,
+                             int target, int iters, int t0, float alpha, float eps, float scale, psg_stream_t stream)
+{
+    if (!n || !n->bound || iters < 0 || t0 < 0 || t0 + iters > n->T) return PSG_EINVAL;
+    // non-targeted: ascent on the true-label cost (nontarget.py:37); targeted: descent on the
+    // target-label cost (target.py:41)
+    const float a = target >= 0 ? -alpha : alpha;
+    for (int i = 0; i < iters; ++i) {
+        PSG_TRY(psg_net_forward(n, t0 + i, nullptr, nullptr, stream));
+        PSG_TRY(psg_net_loss_grad(n, 1, nullptr, labels, target, scale, 0.f, nullptr, stream));
+        PSG_TRY(psg_net_backward(n, t0 + i, nullptr, stream));
+        PSG_TRY(psg_net_pgd_update(n, adv, ori, mask, 3, 3, a, eps, 0.f, 1.f, stream));
+    }
+    return PSG_OK;
+}
+
+extern "C" int64_t psg_launch_count(void) { return g_psg_launch_count; }
+extern "C" int psg_version(void) { return 100; }

@@ -1,0 +1,65 @@
+// psg_internal.h -- launcher prototypes shared by the translation units of libpsg_b200.
+// Nothing here is part of the C ABI (see include/psg_b200.h for that).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "psg_common.cuh"
+
+enum { PSG_EPI_BIAS_RELU = 0, PSG_EPI_BIAS = 1, PSG_EPI_MASK = 2, PSG_EPI_NONE = 3 };
+
+struct PsgGemmArgs {
+    TView A1; int k1chunks;     // first K1 = 4*k1chunks columns of the A operand
+    TView A2; int k2chunks;     // optional second source (FP concat); k2chunks = 0 if unused
+    const float *W; int Nw;     // packed weights [K/4][Nw][4], Nw = output channels padded to 64
+    const float *bias;          // [nout_pad] (zero padded) or null
+    TView Out; int nout_pad;    // columns written (multiple of 16)
+    TView Mask;                 // PSG_EPI_MASK: forward activation of the layer below
+    int mtiles;                 // padded rows / 128
+    int epi;
+};
+
+// fps.cu
+size_t psg_fps_workspace_bytes(int P, int N);
+int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P, int N, int npoint,
+                   const int *start, int *out_idx, float *out_xyz, void *ws, size_t ws_bytes, cudaStream_t st);
+// neighbors.cu
+int psg_ball_query_launch(const float *xyz, long long cloud_stride, int nclouds, int P, int N,
+                          const float *new_xyz, int S, int nr, const double *radius, const int *nsample,
+                          int *out0, int *out1, cudaStream_t st);
+int psg_three_nn_launch(const float *xyz1, long long stride1, int nclouds1, int P, int N,
+                        const float *xyz2, int S, int *idx, float *w, float *d2, cudaStream_t st);
+int psg_square_distance_launch(const float *src, const float *dst, int B, int N, int M, float *out, cudaStream_t st);
+// gather.cu
+int psg_pack_cf(const float *x, long long sb, long long sc, long long sn, int B, int C, int N, TView out,
+                int cpad, float *xyz, cudaStream_t st);
+int psg_unpack_cf(TView in, int B, int C, int N, float *y, int accumulate, cudaStream_t st);
+int psg_pack_rm(const float *x, long long rows, int C, TView out, int cpad, cudaStream_t st);
+int psg_unpack_rm(TView in, long long rows, int C, float *y, cudaStream_t st);
+int psg_group(TView feats, int D, const float *xyz, long long cloud_stride, int nclouds, int Nsrc,
+              const float *new_xyz, const int *idx, int P, int S, int K, TView out, int cpad, cudaStream_t st);
+int psg_maxpool(TView in, long long groups, int K, int C, TView out, unsigned char *arg, cudaStream_t st);
+int psg_maxpool_bwd(TView dout, TView outv, const unsigned char *arg, long long groups, int K, int C, TView dy,
+                    cudaStream_t st);
+int psg_interp(TView feats, int S, const int *idx, const float *w, long long P, int N, int nch, TView out,
+               cudaStream_t st);
+size_t psg_csr_scratch_bytes(long long P, int M, int R);
+int psg_csr_build(const int *keys, long long P, int M, int R, int *offs, int *perm, void *scratch, cudaStream_t st);
+int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, const int *offs, const int *perm,
+               int M, int R, long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, cudaStream_t st);
+int psg_copy_cols(TView src, TView dst, long long rows, int ncols, int accumulate, cudaStream_t st);
+int psg_index_points_rm(const float *pts, const long long *idx, int B, int N, int C, long long M, float *out,
+                        cudaStream_t st);
+// gemm_simt.cu / gemm_tc.cu
+int psg_gemm_simt(const PsgGemmArgs &g, cudaStream_t st);
+int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st);
+// elementwise.cu
+int psg_head_logsoftmax(TView z, long long rows, int ncls, float *logp, cudaStream_t st);
+int psg_dz_from_dlogp(TView z, const float *dlogp, long long rows, int ncls, TView dz, cudaStream_t st);
+int psg_dz_ce(TView z, const int *labels, int target, long long rows, int ncls, float scale, TView dz,
+              cudaStream_t st);
+int psg_dz_cw(TView z, const int *labels, int target, long long rows, int ncls, float kappa, float sign, TView dz,
+              float *loss_rows, cudaStream_t st);
+int psg_pgd_update(float *adv, const float *ori, TView grad, TView feats0, const unsigned char *mask, int B, int C,
+                   int N, int c0, int nc, float alpha_signed, float eps, float lo, float hi, cudaStream_t st);
+int psg_confusion(const float *logp, const int *labels, long long rows, int ncls, long long *conf, cudaStream_t st);

@@ -1,0 +1,179 @@
+"""Host-side owner of one ``psg_net`` (csrc/net.cu): folds eval-mode BatchNorm into the 1x1 convs,
+hands the folded weights to the C library, owns the device workspace and draws the FPS start
+indices exactly like the reference does.
+
+Reference: PointNet/models/pointnet2_sem_seg.py:6-40, pointnet2_sem_seg_msg.py:6-41 (architecture),
+PointNet/models/pointnet_util.py:75 (``torch.randint`` FPS start on the CPU generator, once per SA
+level per forward).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+MLP_FP32 = 0     # CUDA-core fp32 GEMMs (parity mode)
+MLP_TF32 = 1     # tcgen05 TF32 tensor-core GEMMs
+
+
+def fold_conv_bn(w: torch.Tensor, b: torch.Tensor, bn: Dict[str, torch.Tensor] | None, eps: float = 1e-5):
+    """conv(1x1) followed by eval-mode BatchNorm as one affine map, folded in float64."""
+    w2 = w.detach().double().cpu().reshape(w.shape[0], w.shape[1])
+    b2 = b.detach().double().cpu() if b is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    if bn is not None:
+        scale = bn["weight"].detach().double().cpu() / torch.sqrt(bn["running_var"].detach().double().cpu() + eps)
+        w2 = w2 * scale[:, None]
+        b2 = (b2 - bn["running_mean"].detach().double().cpu()) * scale + bn["bias"].detach().double().cpu()
+    return w2.float().contiguous().numpy(), b2.float().contiguous().numpy()
+
+
+class Engine:
+    """One bound network.  ``layers`` is the architecture description produced by the model
+    classes (models/pointnet2_sem_seg*.py):
+
+        {"in_channels": 9, "num_classes": 13,
+         "sa": [{"npoint", "radius": [..], "nsample": [..], "mlps": [[(w, b), ...], ...]}, ...] x4,
+         "fp": [[(w, b), ...] for fp1, fp2, fp3, fp4],      # fine -> coarse
+         "conv1": (w, b), "conv2": (w, b)}
+
+    where every (w, b) is already folded and the first SA layer's input columns are ordered
+    [features | xyz].
+    """
+
+    def __init__(self, layers: dict, device: torch.device, mlp_mode: int = MLP_FP32):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("pointsecguard_b200 runs on CUDA devices only (no CPU fallback)")
+        self._keep: List[np.ndarray] = []
+        d = L.NetDesc()
+        d.in_channels = layers["in_channels"]
+        d.num_classes = layers["num_classes"]
+        d.mlp_mode = mlp_mode
+        for li, sa in enumerate(layers["sa"]):
+            s = d.sa[li]
+            s.npoint = sa["npoint"]
+            s.nbranch = len(sa["radius"])
+            for bi in range(s.nbranch):
+                s.radius[bi] = float(sa["radius"][bi])
+                s.nsample[bi] = int(sa["nsample"][bi])
+                s.nlayers[bi] = len(sa["mlps"][bi])
+                for j, (w, b) in enumerate(sa["mlps"][bi]):
+                    self._fill(s.mlp[bi][j], w, b)
+        for fi, mlps in enumerate(layers["fp"]):
+            f = d.fp[fi]
+            f.nlayers = len(mlps)
+            for j, (w, b) in enumerate(mlps):
+                self._fill(f.mlp[j], w, b)
+        self._fill(d.conv1, *layers["conv1"])
+        self._fill(d.conv2, *layers["conv2"])
+        self.npoints = [sa["npoint"] for sa in layers["sa"]]
+        self.num_classes = layers["num_classes"]
+        self.in_channels = layers["in_channels"]
+        self.c4 = sum(m[-1][0].shape[0] for m in layers["sa"][3]["mlps"])
+        with torch.cuda.device(self.device):
+            self._net = L.psg_net_create(C.byref(d))
+        self._keep.clear()
+        if not self._net:
+            raise L.PsgError("psg_net_create failed (unsupported architecture or out of device memory)")
+        self.B = self.N = self.T = 0
+        self._ws = None
+        self.mlp_mode = mlp_mode
+
+    def _fill(self, m: L.MlpDesc, w: np.ndarray, b: np.ndarray):
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        self._keep += [w, b]
+        m.cout, m.cin = w.shape
+        m.w_host = w.ctypes.data
+        m.b_host = b.ctypes.data
+
+    def __del__(self):
+        net, self._net = getattr(self, "_net", None), None
+        if net:
+            L.psg_net_destroy(net)
+
+    # ------------------------------------------------------------------------------------------
+    def set_mlp_mode(self, mode: int):
+        L.psg_net_set_mlp_mode(self._net, mode)
+        self.mlp_mode = mode
+
+    def bind(self, B: int, N: int, T: int):
+        """(Re)allocate the workspace for B blocks of N points and T forwards' worth of geometry."""
+        if (B, N) == (self.B, self.N) and T <= self.T:
+            return
+        need = L.psg_net_workspace(self._net, B, N, T)
+        if need == 0:
+            raise L.PsgError("psg_net_workspace: invalid problem size")
+        self._ws = None
+        self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        base = (self._ws.data_ptr() + 1023) & ~1023
+        L.psg_net_bind(self._net, B, N, T, base, need)
+        self.B, self.N, self.T = B, N, T
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def draw_starts(self, T: int) -> torch.Tensor:
+        """FPS start indices for T forwards, drawn on the global CPU generator in the reference's
+        call order (per forward: level 1..4, each ``torch.randint(0, N_level, (B,))``,
+        pointnet_util.py:75).  Returns int32 [4, T, B] (CPU)."""
+        sizes = [self.N] + self.npoints[:3]
+        out = torch.empty(4, T, self.B, dtype=torch.int32)
+        for t in range(T):
+            for l in range(4):
+                out[l, t] = torch.randint(0, sizes[l], (self.B,), dtype=torch.long).to(torch.int32)
+        return out
+
+    def set_input(self, x: torch.Tensor):
+        if x.dim() != 3 or x.shape[0] != self.B or x.shape[1] != self.in_channels or x.shape[2] != self.N:
+            raise ValueError(f"expected [{self.B},{self.in_channels},{self.N}], got {tuple(x.shape)}")
+        if x.dtype != torch.float32 or x.device != self.device:
+            raise TypeError("input must be a float32 tensor on the engine's CUDA device")
+        sb, sc, sn = x.stride()
+        L.psg_net_set_input(self._net, x.data_ptr(), sb, sc, sn, self._stream())
+
+    def geometry(self, starts: torch.Tensor):
+        """starts: int32 [4, T, B] (CPU or device)."""
+        T = starts.shape[1]
+        if T > self.T or starts.shape[2] != self.B:
+            raise ValueError("geometry: starts do not match the bound problem")
+        self._starts_dev = starts.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+        L.psg_net_geometry(self._net, self._starts_dev.data_ptr(), T, self._stream())
+
+    def forward(self, t: int = 0, want_logp: bool = True, want_l4: bool = False):
+        logp = torch.empty(self.B, self.N, self.num_classes, dtype=torch.float32, device=self.device) if want_logp else None
+        l4 = torch.empty(self.B, self.c4, self.npoints[3], dtype=torch.float32, device=self.device) if want_l4 else None
+        L.psg_net_forward(self._net, t, logp.data_ptr() if want_logp else None, l4.data_ptr() if want_l4 else None,
+                          self._stream())
+        return logp, l4
+
+    def loss_grad_generic(self, dlogp: torch.Tensor):
+        dlogp = dlogp.contiguous()
+        L.psg_net_loss_grad(self._net, 0, dlogp.data_ptr(), None, -1, 1.0, 0.0, None, self._stream())
+
+    def loss_grad_ce(self, labels: torch.Tensor | None, target: int, scale: float):
+        L.psg_net_loss_grad(self._net, 1, None, labels.data_ptr() if labels is not None else None, target, scale, 0.0,
+                            None, self._stream())
+
+    def loss_grad_cw(self, labels: torch.Tensor | None, target: int, sign: float, kappa: float, loss_rows=None):
+        L.psg_net_loss_grad(self._net, 2, None, labels.data_ptr() if labels is not None else None, target, sign, kappa,
+                            loss_rows.data_ptr() if loss_rows is not None else None, self._stream())
+
+    def backward(self, t: int = 0, want_grad: bool = True):
+        g = torch.empty(self.B, self.in_channels, self.N, dtype=torch.float32, device=self.device) if want_grad else None
+        L.psg_net_backward(self._net, t, g.data_ptr() if want_grad else None, self._stream())
+        return g
+
+    def pgd_update(self, adv, ori, mask, c0, nc, alpha_signed, eps, lo=0.0, hi=1.0):
+        L.psg_net_pgd_update(self._net, adv.data_ptr(), ori.data_ptr(), mask.data_ptr() if mask is not None else None,
+                             c0, nc, alpha_signed, eps, lo, hi, self._stream())
+
+    def nb_attack(self, adv, ori, mask, labels, target, iters, t0, alpha, eps, scale):
+        L.psg_nb_attack(self._net, adv.data_ptr(), ori.data_ptr(), mask.data_ptr() if mask is not None else None,
+                        labels.data_ptr() if labels is not None else None, target, iters, t0, alpha, eps, scale,
+                        self._stream())

@@ -1,0 +1,114 @@
+"""GPU parity of the geometric primitives: the CUDA kernels (through the drop-in Python API ->
+torch.ops.psg.* -> C ABI) against the golden vectors of the executed reference and against the CPU
+oracle, bit for bit."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from pointsecguard_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["uniform", "grid", "clustered", "duplicates", "surface"]
+CASES = [(k, 2, 1024, 256, [(0.2, 32), (0.1, 16)], 3) for k in KINDS] + \
+        [("sa1", 1, 4096, 1024, [(0.1, 32), (0.05, 16)], 4)]
+
+
+@pytest.fixture(scope="module")
+def PU():
+    from pointsecguard_b200.models import pointnet_util
+    return pointnet_util
+
+
+def _xyz(kind, B, N, seed):
+    x = syn.make_blocks(B, N, seed, "uniform" if kind == "sa1" else kind)
+    return x[:, :3].permute(0, 2, 1).contiguous()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_primitives_match_reference_goldens(golden_dir, PU, case):
+    kind, B, N, S, balls, seed = case
+    g = dict(np.load(os.path.join(golden_dir, f"geom_{kind}.npz")))
+    xyz = _xyz(kind, B, N, seed).cuda()
+    torch.manual_seed(seed + 100)               # same CPU-generator draw as the reference made
+    fps = PU.farthest_point_sample(xyz, S)
+    assert fps.dtype == torch.int64
+    assert np.array_equal(fps.cpu().numpy(), g["fps"])
+    new_xyz = PU.index_points(xyz, fps)
+    assert torch.equal(new_xyz.cpu(), _xyz(kind, B, N, seed)[torch.arange(B)[:, None], fps.cpu()])
+    for r, k in balls:
+        idx = PU.query_ball_point(r, k, xyz, new_xyz)
+        assert np.array_equal(idx.cpu().numpy(), g[f"ball_r{r}_k{k}"]), (kind, r, k)
+    # MSG pair sharing one scan gives the same two index sets
+    (r0, k0), (r1, k1) = balls
+    i0, i1 = torch.ops.psg.ball_query2(r0, k0, r1, k1, xyz, new_xyz)
+    assert np.array_equal(i0.cpu().numpy(), g[f"ball_r{r0}_k{k0}"])
+    assert np.array_equal(i1.cpu().numpy(), g[f"ball_r{r1}_k{k1}"])
+    d = PU.square_distance(xyz, new_xyz)
+    assert np.array_equal(d[:, :4].cpu().numpy(), g["sqd_rows"])
+    assert np.uint32(zlib.crc32(d.cpu().numpy().tobytes())) == g["sqd_crc"]
+    idx, d2, w = torch.ops.psg.three_nn(xyz, new_xyz)
+    assert np.array_equal(d2.cpu().numpy(), g["nn_d2"])
+    assert np.array_equal(w.cpu().numpy(), g["nn_w"])
+    # the reference's sort is unstable: differing indices are allowed only at bit-equal distances
+    mine, ref = idx.cpu().numpy(), g["nn_idx"]
+    dn = d.cpu().numpy()
+    for b, i, k in np.argwhere(mine != ref):
+        assert dn[b, i, mine[b, i, k]] == dn[b, i, ref[b, i, k]]
+
+
+@pytest.mark.parametrize("N,S", [(64, 16), (256, 64), (1024, 256), (4096, 1024), (6000, 300), (16384, 512), (20000, 64)])
+def test_fps_sizes_against_oracle(PU, N, S):
+    from oracle import geom as G
+    B = 3
+    gcpu = torch.Generator().manual_seed(N)
+    xyz = torch.rand(B, N, 3, generator=gcpu)
+    xyz[1] = torch.floor(xyz[1] * 16) / 16          # heavy ties: first-max tie-break must hold
+    start = torch.randint(0, N, (B,), generator=gcpu)
+    ref = G.fps(xyz, S, start)
+    out = torch.ops.psg.fps(xyz.cuda(), S, start)
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("N,S,r,k", [(4096, 1024, 0.1, 32), (1024, 256, 0.2, 32), (300, 7, 0.4, 16), (9000, 100, 0.3, 32),
+                                     (64, 16, 0.8, 32)])
+def test_ball_query_and_three_nn_against_oracle(PU, N, S, r, k):
+    from oracle import geom as G
+    B = 2
+    gcpu = torch.Generator().manual_seed(N + S)
+    xyz = torch.rand(B, N, 3, generator=gcpu)
+    xyz[1, : N // 2] = xyz[1, N // 2: N // 2 * 2]    # duplicates
+    sel = torch.stack([torch.randperm(N, generator=gcpu)[:S] for _ in range(B)])
+    new_xyz = xyz[torch.arange(B)[:, None], sel]
+    ref = G.ball_query(r, k, xyz, new_xyz)
+    out = PU.query_ball_point(r, k, xyz.cuda(), new_xyz.cuda())
+    assert torch.equal(out.cpu(), ref)
+    ridx, rd2, rw = G.three_nn(xyz, new_xyz)
+    idx, d2, w = torch.ops.psg.three_nn(xyz.cuda(), new_xyz.cuda())
+    assert torch.equal(idx.cpu(), ridx) and torch.equal(d2.cpu(), rd2) and torch.equal(w.cpu(), rw)
+
+
+def test_ball_query_far_centroid_pads_with_N(PU):
+    """A centroid with no point in range leaves N in every slot, as the reference does."""
+    xyz = torch.rand(1, 128, 3).cuda()
+    far = torch.full((1, 2, 3), 50.0).cuda()
+    idx = PU.query_ball_point(0.1, 8, xyz, far)
+    assert (idx == 128).all()
+
+
+def test_index_points_shapes(PU):
+    pts = torch.rand(2, 100, 7).cuda()
+    idx = torch.randint(0, 100, (2, 5, 3)).cuda()
+    out = PU.index_points(pts, idx)
+    assert out.shape == (2, 5, 3, 7)
+    assert torch.equal(out, pts[torch.arange(2).view(2, 1, 1), idx])
+    idx2 = torch.randint(0, 100, (2, 9)).cuda()
+    assert torch.equal(PU.index_points(pts, idx2), pts[torch.arange(2).view(2, 1), idx2])
+
+
+def test_cpu_tensors_are_refused(PU):
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.psg.square_distance(torch.rand(1, 4, 3), torch.rand(1, 4, 3))
