@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- PGD attack steps/sec on 4096-pt PointNet++ sem-seg blocks (BASELINE.json metric).
+
+A *step* is one PGD iteration (one forward + one input-gradient backward + the fused perturbation
+update) for a batch of 16 S3DIS-shaped 4096-point blocks per GPU: BASELINE.json configs[1]
+(PointNet++ SSG sem-seg, norm-bounded targeted PGD, B=16x4096, random-init weights, synthetic data).
+The timed region is one ``tar_NB_attack(iters=K)`` call: the batched geometry pass (FPS, ball query,
+3-NN, CSRs for all K forwards), the FPS start draws on the CPU generator, and the K-step loop.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU); every rank attacks its own 16 blocks (weak
+scaling, no data-path collective) and the per-class counters are all-reduced over NCCL afterwards.
+``--impl reference`` times the CPU restatement of the reference's own PyTorch path (oracle/, with
+the reference's op-for-op geometry) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+B_PER_GPU = 16
+N_POINTS = 4096
+EPS, ALPHA, TARGET, ORIGIN = 0.5, 0.1, 7, 11          # NB_target_test_semseg.py:177, :48-49
+FLOPS_PER_BLOCK_STEP = 3.880e9                        # forward + dgrad, SSG, N=4096
+METRIC = "pgd_attack_steps_per_sec"
+UNIT = "steps/s (1 step = fwd + input-grad bwd + update of 16 blocks x 4096 pts per GPU)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.maxclk = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxclk = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.maxclk, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.maxclk, "reasons": sorted(self.reasons)}
+
+
+def make_inputs(B, seed):
+    from pointsecguard_b200 import synthetic as syn
+    x = syn.make_blocks(B, N_POINTS, seed, "uniform")
+    labels = syn.zband_labels(x)
+    mask = labels == ORIGIN                                  # per-block masks, [B,N]
+    return x, labels, mask
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's PyTorch path)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, sample_blocks=2):
+    """Times `steps` PGD iterations of the reference algorithm on `sample_blocks` blocks on all host
+    threads and scales to the 16-block step.  Returns (steps_per_s, cores, sample string)."""
+    from oracle import attacks_oracle as AO
+    from oracle import pointnet2_oracle as PO
+    from pointsecguard_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    PO.GEOMETRY = "torch"          # op-for-op the reference's geometry (Python FPS loop, matmul + sort)
+    model = PO.OracleModel(syn.make_state_dict("ssg"), "ssg")
+    x, labels, mask = make_inputs(sample_blocks, 0)
+    torch.manual_seed(0)
+    if warmup > 0:
+        AO.tar_nb_attack(model, x, labels.numpy(), eps=EPS, alpha=ALPHA, iters=min(warmup, 1), target=TARGET, mask=mask)
+    t0 = time.perf_counter()
+    AO.tar_nb_attack(model, x, labels.numpy(), eps=EPS, alpha=ALPHA, iters=steps, target=TARGET, mask=mask)
+    dt = time.perf_counter() - t0
+    sps = steps / dt * sample_blocks / B_PER_GPU
+    sample = (f"tar-NB SSG, {sample_blocks} of the 16 blocks x {steps} iters on {cores} threads "
+              f"({dt:.1f} s), reference op-for-op geometry; scaled to 16-block steps")
+    return sps, cores, sample, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    sps, cores, sample, dt = cpu_reference(min(steps, 8), args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: PointNet++ SSG sem_seg, norm-bounded targeted PGD, B=16x4096 per GPU, "
+                               "random-init weights, synthetic S3DIS-shaped blocks"},
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_native(args, rank, world, local_rank):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pointsecguard_b200 import _lib as L
+    from pointsecguard_b200 import synthetic as syn, torchattacks
+    from pointsecguard_b200 import metrics as MT
+    from pointsecguard_b200.models.pointnet2_sem_seg import get_model
+
+    model = get_model(13)
+    model.load_state_dict(syn.make_state_dict("ssg"))
+    model = model.to(dev).eval()
+    if args.mlp == "tf32":
+        from pointsecguard_b200.engine import MLP_TF32
+        model.set_mlp_mode(MLP_TF32)
+    x_host, labels, mask = make_inputs(B_PER_GPU, seed=rank)      # every rank attacks its own blocks
+    x_pin = x_host.contiguous().pin_memory()                      # [B,9,N] contiguous pinned host copy
+    x_dev = x_host.to(dev)
+    lab_np = labels.numpy().astype(np.float64)
+    K, W = args.steps, args.warmup
+    atk = torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=K, target=TARGET, mask=mask)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: W untimed steps (also builds the engine and its workspace)
+    if W > 0:
+        torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=W, target=TARGET, mask=mask)(x_dev, lab_np)
+    model.engine(dev).bind(B_PER_GPU, N_POINTS, min(K, max(1, 1024 // B_PER_GPU)))
+    torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=1, target=TARGET, mask=mask)(x_dev, lab_np)
+
+    # ---- device-resident timing: exactly K steps ----
+    clocks = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.manual_seed(0)
+    barrier()
+    clocks.start()
+    l0 = L.psg_launch_count()
+    e0.record()
+    adv = atk(x_dev, lab_np)
+    e1.record()
+    barrier()
+    launches = L.psg_launch_count() - l0
+    clk = clocks.finish()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * K / (ms_total / 1e3)
+
+    # ---- end to end through the public API from pinned host memory, result read back ----
+    torch.manual_seed(0)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    xd = x_pin.to(dev, non_blocking=True)
+    adv2 = atk(xd, lab_np)
+    adv_host = adv2.to("cpu", non_blocking=False)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / (float(ms2.item()) / 1e3)
+    h2d = x_pin.numel() * 4 / K
+    d2h = adv_host.numel() * 4 / K
+    same_as_resident = bool(torch.equal(adv_host, adv.cpu()))
+
+    # ---- metrics + the only collective: per-class counters all-reduced over NCCL ----
+    torch.manual_seed(1)
+    logp_adv, _ = model(adv)
+    counters = MT.attack_counters(logp_adv, labels.to(dev), mask.to(dev), TARGET)
+    if world > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    summary = MT.summarize(counters.cpu(), 13)
+
+    line = None
+    if rank == 0:
+        # ---- live per-kernel-family timing (CUDA event pairs on the launching stream) ----
+        import ctypes as C
+        L.psg_prof_enable(1)
+        kp = min(K, 10)
+        torch.manual_seed(0)
+        torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=kp, target=TARGET, mask=mask)(x_dev, lab_np)
+        ncat = L.psg_prof_ncat()
+        msb = (C.c_double * ncat)()
+        cnt = (C.c_int64 * ncat)()
+        L.psg_prof_collect(msb, cnt)
+        L.psg_prof_enable(0)
+        fam = {L.psg_prof_name(i).decode(): {"ms_per_step": msb[i] / kp, "launches_per_step": cnt[i] / kp}
+               for i in range(ncat) if cnt[i]}
+        pk = peaks()
+        gemm_ms = fam.get("gemm_fwd", {}).get("ms_per_step", 0) + fam.get("gemm_bwd", {}).get("ms_per_step", 0)
+        gemm_launches = fam.get("gemm_fwd", {}).get("launches_per_step", 0) + fam.get("gemm_bwd", {}).get("launches_per_step", 0)
+        flops_step = FLOPS_PER_BLOCK_STEP * B_PER_GPU
+        ach = flops_step / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        # fp32 CUDA-core MLPs have no tensor peak; the TF32 tcgen05 peak is half the measured bf16 one
+        peak = pk["bf16_tflops_sustained"] / 2.0
+        roofline = {
+            "bound": "tensor", "kernel": "shared-MLP GEMMs (forward + dgrad, all layers)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+            "peak_source": f"{pk['source']} bf16 sustained / 2 (TF32 dense rate)", "traffic": None,
+            "launches_per_step": gemm_launches, "ms_per_step": gemm_ms, "mlp_mode": args.mlp,
+            "fps_ms_per_step": fam.get("fps", {}).get("ms_per_step"),
+        }
+        # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
+        if args.no_cpu:
+            cpu = None
+        else:
+            sps, cores, sample, _ = cpu_reference(3, 1)
+            cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.mlp == "fp32" else "tf32", "data": "synthetic",
+            "config": {"workload": "configs[1]: PointNet++ SSG sem_seg, norm-bounded targeted PGD (tar_NB_attack eps=0.5 "
+                                   "alpha=0.1 target=7, mask=z-band class 11), B=16x4096 per GPU, random-init weights, "
+                                   "synthetic S3DIS-shaped blocks",
+                       "blocks_per_gpu": B_PER_GPU, "points": N_POINTS, "mlp": args.mlp,
+                       "l2": "per-step working set (~1 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "block_steps_per_s": value * B_PER_GPU,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "wall_s": wall, "identical_to_resident_run": same_as_resident},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roofline,
+            "kernel_families_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in fam.items()},
+            "cpu_baseline": cpu,
+            "attack_metrics": summary,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--mlp", default=os.environ.get("PSG_MLP", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun for --gpus > 1")
+    run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,9 +145,12 @@ int psg_net_pgd_update(psg_net *net, float *adv, const float *ori, const uint8_t
  * have been built; labels int32 [B,N] (kind-1 loss), target < 0 for the non-targeted attack. */
 int psg_nb_attack(psg_net *net, float *adv, const float *ori, const uint8_t *mask, const int32_t *labels,
                   int target, int iters, int t0, float alpha, float eps, float scale, psg_stream_t stream);
-/* confusion matrix conf[label][pred] += 1 (int64 [ncls][ncls]), NB_nontarget_test_semseg.py:193-211 */
-int psg_confusion_matrix(const float *logp, const int32_t *labels, int64_t rows, int ncls, int64_t *conf,
-                         psg_stream_t stream);
+/* Per-class counters of NB_nontarget_test_semseg.py:187-211 / NB_target_test_semseg.py:187-190 as one
+ * histogram: conf is int64 [ncls*ncls + 4] and is ACCUMULATED into: conf[label*ncls + pred] += 1 with
+ * pred = first arg-max of logp [rows,ncls]; then rows seen, rows with pred == label, masked rows,
+ * masked rows with pred == target (mask optional).  This buffer is what the NCCL all-reduce sums. */
+int psg_confusion_matrix(const float *logp, const int32_t *labels, const uint8_t *mask, int target, int64_t rows,
+                         int ncls, int64_t *conf, psg_stream_t stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t psg_launch_count(void);
 /* per-kernel-family device timing of the engine (CUDA event pairs on the launching stream);

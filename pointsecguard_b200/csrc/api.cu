@@ -117,9 +117,9 @@ extern "C" int psg_segment_sum(const float *src_base, int src_wchunks, int src_c
                       ncols, mkview(dst_base, dst_wchunks, dst_c0), accumulate, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int psg_confusion_matrix(const float *logp, const int32_t *labels, int64_t rows, int ncls, int64_t *conf,
-                                    psg_stream_t stream)
+extern "C" int psg_confusion_matrix(const float *logp, const int32_t *labels, const uint8_t *mask, int target,
+                                    int64_t rows, int ncls, int64_t *conf, psg_stream_t stream)
 {
     if (!logp || !labels || !conf || rows <= 0) return PSG_EINVAL;
-    return psg_confusion(logp, labels, rows, ncls, (long long *)conf, (cudaStream_t)stream);
+    return psg_confusion(logp, labels, mask, target, rows, ncls, (long long *)conf, (cudaStream_t)stream);
 }

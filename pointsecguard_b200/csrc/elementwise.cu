@@ -124,12 +124,15 @@ __global__ void pgd_update_kernel(float *__restrict__ adv, const float *__restri
     }
 }
 
-// conf[label][pred] += 1 with pred = first arg-max of the log-probabilities
-__global__ void confusion_kernel(const float *__restrict__ logp, const int *__restrict__ labels, long long rows,
+// conf[label][pred] += 1 with pred = first arg-max of the log-probabilities, followed by four
+// scalars: rows seen, rows with pred == label, masked rows, masked rows with pred == target
+__global__ void confusion_kernel(const float *__restrict__ logp, const int *__restrict__ labels,
+                                 const unsigned char *__restrict__ mask, int target, long long rows,
                                  int ncls, unsigned long long *__restrict__ conf)
 {
-    __shared__ unsigned int h[kMaxCls * kMaxCls];
-    for (int i = threadIdx.x; i < ncls * ncls; i += blockDim.x) h[i] = 0;
+    __shared__ unsigned int h[kMaxCls * kMaxCls + 4];
+    const int nh = ncls * ncls + 4;
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) h[i] = 0;
     __syncthreads();
     for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < rows;
          row += (long long)gridDim.x * blockDim.x) {
@@ -138,9 +141,15 @@ __global__ void confusion_kernel(const float *__restrict__ logp, const int *__re
         for (int c = 1; c < ncls; ++c) if (v[c] > bv) { bv = v[c]; best = c; }
         const int y = labels[row];
         if (y >= 0 && y < ncls) atomicAdd(&h[y * ncls + best], 1u);
+        atomicAdd(&h[ncls * ncls], 1u);
+        if (best == y) atomicAdd(&h[ncls * ncls + 1], 1u);
+        if (mask && mask[row]) {
+            atomicAdd(&h[ncls * ncls + 2], 1u);
+            if (best == target) atomicAdd(&h[ncls * ncls + 3], 1u);
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < ncls * ncls; i += blockDim.x)
+    for (int i = threadIdx.x; i < nh; i += blockDim.x)
         if (h[i]) atomicAdd(conf + i, (unsigned long long)h[i]);
 }
 
@@ -185,11 +194,12 @@ int psg_pgd_update(float *adv, const float *ori, TView grad, TView feats0, const
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
-int psg_confusion(const float *logp, const int *labels, long long rows, int ncls, long long *conf, cudaStream_t st)
+int psg_confusion(const float *logp, const int *labels, const unsigned char *mask, int target, long long rows, int ncls,
+                  long long *conf, cudaStream_t st)
 {
     if (ncls > kMaxCls) return PSG_EUNSUPPORTED;
     const unsigned blocks = (unsigned)min((long long)592, (rows + 255) / 256);
-    confusion_kernel<<<blocks, 256, 0, st>>>(logp, labels, rows, ncls, (unsigned long long *)conf);
+    confusion_kernel<<<blocks, 256, 0, st>>>(logp, labels, mask, target, rows, ncls, (unsigned long long *)conf);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
