@@ -1,5 +1,166 @@
-// gemm_tc.cu -- tcgen05 / TMEM TF32 GEMM for the shared MLPs (placeholder until the kernel lands:
-// reports "unsupported" so that callers fail loudly instead of silently changing precision).
+// gemm_tc.cu -- tcgen05 / TMEM TF32 GEMM for the shared 1x1-conv MLPs (same interface and operand
+// layout as gemm_simt.cu):   Out[M, Nout] = epilogue( [A1 | A2][M, K] * W[Nout, K]^T )
+//
+// One CTA computes a 128 x BN output tile (BN <= 128).  Warp 0 (one lane) streams the operands
+// with 1-D bulk async copies: a 128-row activation tile of T-layout is a run of whole 2 KB chunk
+// planes, i.e. already the K-major no-swizzle UMMA canonical layout, and the packed weights
+// [K/4][Nw][4] are the same layout for the B operand.  Warp 1 allocates TMEM and (one lane) issues
+// tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8 per instruction) into a TMEM accumulator, handing
+// shared-memory stages back through tcgen05.commit -> mbarrier.  Warps 2-5 read the accumulator
+// with tcgen05.ld (thread = row), apply bias / ReLU / ReLU-mask and write T-layout rows as
+// coalesced 16-byte pieces.
 #include "psg_common.cuh"
 #include "psg_internal.h"
-int psg_gemm_tc(const PsgGemmArgs &, cudaStream_t) { return PSG_EUNSUPPORTED; }
+#include "psg_tc.cuh"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBlk = 8;                       // chunk planes (4 floats of K each) per stage
+constexpr int kBNMax = 128;
+constexpr int kABytes = kBlk * 2048;          // 16 KB
+constexpr int kBBytes = kBlk * kBNMax * 16;   // 16 KB
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024;
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_full[kStages], bar_empty[kStages], bar_acc;
+    __shared__ uint32_t tmem_slot;
+
+    // 1024-byte aligned operand staging area
+    const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = sbase, sB = sbase + kStages * kABytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row0 = (long long)blockIdx.x * 128;
+    const int n0 = blockIdx.y * kBNMax;
+    const int BN = min(kBNMax, g.nout_pad - n0);
+    const uint32_t ncols = tc::next_pow2_cols(BN);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1); }
+        tc::mbar_init(tc::smem_u32(&bar_acc), 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- producer ----
+            int it = 0, kglob = 0;
+            for (int srcI = 0; srcI < 2; ++srcI) {
+                const TView &src = srcI == 0 ? g.A1 : g.A2;
+                const int kch = srcI == 0 ? g.k1chunks : g.k2chunks;
+                for (int c = 0; c < kch; c += kBlk, ++it) {
+                    const int n = min(kBlk, kch - c);
+                    const int s = it % kStages;
+                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                    tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
+                    const uint32_t full = tc::smem_u32(&bar_full[s]);
+                    tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + n * BN * 16));
+                    tc::bulk_g2s(sA + s * kABytes, src.base + tv_off(src, row0, c), (uint32_t)(n * 2048), full);
+                    for (int j = 0; j < n; ++j)
+                        tc::bulk_g2s(sB + s * kBBytes + j * BN * 16, g.W + ((size_t)(kglob + c + j) * g.Nw + n0) * 4,
+                                     (uint32_t)(BN * 16), full);
+                }
+                kglob += kch;
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            const uint32_t idesc = tc::idesc_tf32(128, BN);
+            int it = 0;
+            uint32_t acc = 0;
+            for (int srcI = 0; srcI < 2; ++srcI) {
+                const int kch = srcI == 0 ? g.k1chunks : g.k2chunks;
+                for (int c = 0; c < kch; c += kBlk, ++it) {
+                    const int n = min(kBlk, kch - c);
+                    const int s = it % kStages;
+                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                    tc::mbar_wait(tc::smem_u32(&bar_full[s]), ph);
+                    tc::fence_after_sync();
+                    for (int j = 0; j < n; j += 2) {
+                        const uint64_t ad = tc::smem_desc(sA + s * kABytes + j * 2048, 2048, 128);
+                        const uint64_t bd = tc::smem_desc(sB + s * kBBytes + j * BN * 16, (uint32_t)(BN * 16), 128);
+                        tc::mma_tf32(tmem, ad, bd, idesc, acc);
+                        acc = 1;
+                    }
+                    tc::mma_commit(tc::smem_u32(&bar_empty[s]));
+                }
+            }
+            tc::mma_commit(tc::smem_u32(&bar_acc));
+        }
+    } else {
+        // ---- epilogue: warp q owns TMEM lanes [32q, 32q + 32) ----
+        const int q = warp & 3;
+        const long long row = row0 + q * 32 + lane;
+        tc::mbar_wait(tc::smem_u32(&bar_acc), 0);
+        tc::fence_after_sync();
+        for (int c16 = 0; c16 < BN; c16 += 16) {
+            float v[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c16, v);
+            const int col = n0 + c16;
+            if (EPI == PSG_EPI_BIAS_RELU || EPI == PSG_EPI_BIAS) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] += __ldg(g.bias + col + i);
+                    if (EPI == PSG_EPI_BIAS_RELU) v[i] = fmaxf(v[i], 0.f);
+                }
+            }
+            if (EPI == PSG_EPI_MASK) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 y = tv_ld(g.Mask, row, (col >> 2) + c);
+                    v[4 * c + 0] = y.x > 0.f ? v[4 * c + 0] : 0.f;
+                    v[4 * c + 1] = y.y > 0.f ? v[4 * c + 1] : 0.f;
+                    v[4 * c + 2] = y.z > 0.f ? v[4 * c + 2] : 0.f;
+                    v[4 * c + 3] = y.w > 0.f ? v[4 * c + 3] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                tv_st(g.Out, row, (col >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, ncols);
+}
+
+template <int EPI>
+int launch(const PsgGemmArgs &g, cudaStream_t st)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+            return PSG_ECUDA;
+        attr_done = true;
+    }
+    dim3 grid((unsigned)g.mtiles, (unsigned)((g.nout_pad + kBNMax - 1) / kBNMax));
+    gemm_tc_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(g);
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}
+
+}  // namespace
+
+int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st)
+{
+    if (g.k1chunks % 4 || g.k2chunks % 4 || g.k1chunks <= 0 || g.mtiles <= 0 || g.nout_pad % 16) return PSG_EINVAL;
+    if (g.Nw < g.nout_pad) return PSG_EINVAL;
+    switch (g.epi) {
+    case PSG_EPI_BIAS_RELU: return launch<PSG_EPI_BIAS_RELU>(g, st);
+    case PSG_EPI_BIAS: return launch<PSG_EPI_BIAS>(g, st);
+    case PSG_EPI_MASK: return launch<PSG_EPI_MASK>(g, st);
+    case PSG_EPI_NONE: return launch<PSG_EPI_NONE>(g, st);
+    }
+    return PSG_EINVAL;
+}
