@@ -145,6 +145,39 @@ int psg_net_pgd_update(psg_net *net, float *adv, const float *ori, const uint8_t
  * have been built; labels int32 [B,N] (kind-1 loss), target < 0 for the non-targeted attack. */
 int psg_nb_attack(psg_net *net, float *adv, const float *ori, const uint8_t *mask, const int32_t *labels,
                   int target, int iters, int t0, float alpha, float eps, float scale, psg_stream_t stream);
+/* ---- norm-unbounded attacks: NU_attack (nontarget.py:52-106), tar_NU_attack (target.py:62-133) ----
+ * All buffers are caller-owned device memory.  One psg_nu_step enqueues, with no host round trip:
+ * colours = (tanh(w)+1)/2 written into the model input and `adv`; forward t; C&W f and its gradient
+ * (:120-128); input-gradient backward; the k-smallest colour-distance smoothness term of block 0 and
+ * its gradient (:130-135); cost[step] = f + c*smooth + c*L2 and the accuracy test (:86-96) on the
+ * device; the Adam update of w (torch.optim.Adam, betas 0.9/0.999, eps 1e-8).  When the accuracy
+ * test fires, status[0] latches to 1 and status[1] = step; later steps leave w / adv untouched, so
+ * `adv` is the image the reference returns.  status[2] = hit count of the last evaluated step. */
+typedef struct {
+    float *w, *adam_m, *adam_v;   /* [B,3,N] tanh-space colours and Adam moments */
+    float *adv;                   /* [B,C,N] image of the last forward (the returned tensor) */
+    const float *base;            /* [B,C,N] image the colours are written into (original; all-channel
+                                     clamped copy after a target.py:127-132 "bingo", Q4) */
+    const float *images;          /* [B,C,N] original image (L2 and smoothness reference) */
+    const uint8_t *mask;          /* [B,N] points whose colours move, or null = all */
+    const int32_t *labels;        /* [B,N] */
+    float *cost;                  /* [>= number of steps] cost history (target.py:95) */
+    int32_t *status;              /* [4] */
+    float *scratch;               /* psg_nu_scratch_floats(B, N) floats */
+} psg_nu_buffers;
+size_t psg_nu_scratch_floats(int B, int N);
+/* w = atanh(2 colour - 1) (:57, :111-117), Adam moments and status zeroed */
+int psg_nu_init(psg_net *net, const psg_nu_buffers *buf, psg_stream_t stream);
+/* target < 0: f against the labels; else against `target`.  step_size = lr / (1 - 0.9^k) and
+ * bc2_sqrt = sqrt(1 - 0.999^k) for the k-th step since the optimiser was (re)created; reset_adam
+ * clears the moments first (target.py:123-125).  Accuracy test: hits / acc_denom  < thr
+ * (exit_above = 0) or > thr (exit_above = 1), hits counted over all or only the masked points. */
+int psg_nu_step(psg_net *net, const psg_nu_buffers *buf, int t, int step, int target, int neighbour, float c,
+                float kappa, float targeted_sign, float step_size, float bc2_sqrt, int reset_adam, double acc_denom,
+                double thr, int exit_above, int count_masked_only, psg_stream_t stream);
+/* x = clamp(x, lo, hi) elementwise (target.py:132 clamps all nine channels) */
+int psg_clamp(float *x, int64_t count, float lo, float hi, psg_stream_t stream);
+
 /* Per-class counters of NB_nontarget_test_semseg.py:187-211 / NB_target_test_semseg.py:187-190 as one
  * histogram: conf is int64 [ncls*ncls + 4] and is ACCUMULATED into: conf[label*ncls + pred] += 1 with
  * pred = first arg-max of logp [rows,ncls]; then rows seen, rows with pred == label, masked rows,

@@ -39,7 +39,13 @@ class NetDesc(C.Structure):
                 ("conv1", MlpDesc), ("conv2", MlpDesc), ("mlp_mode", C.c_int)]
 
 
-_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+class NuBuffers(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("adv", C.c_void_p),
+                ("base", C.c_void_p), ("images", C.c_void_p), ("mask", C.c_void_p), ("labels", C.c_void_p),
+                ("cost", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+_vp, _i, _i64, _f, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes); status-returning functions are wrapped with a check
 _PROTOS = {
@@ -76,6 +82,10 @@ _PROTOS = {
     "psg_net_backward": (_i, [_vp, _i, _vp, _vp]),
     "psg_net_pgd_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _vp]),
     "psg_nb_attack": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp]),
+    "psg_nu_scratch_floats": (_sz, [_i, _i]),
+    "psg_nu_init": (_i, [_vp, C.POINTER(NuBuffers), _vp]),
+    "psg_nu_step": (_i, [_vp, C.POINTER(NuBuffers), _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _d, _d, _i, _i, _vp]),
+    "psg_clamp": (_i, [_vp, _i64, _f, _f, _vp]),
     "psg_prof_enable": (_i, [_i]),
     "psg_prof_ncat": (_i, []),
     "psg_prof_name": (C.c_char_p, [_i]),

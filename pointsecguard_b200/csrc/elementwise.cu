@@ -76,7 +76,8 @@ __global__ void dz_ce_kernel(TView z, const int *__restrict__ labels, int target
 
 // C&W f = clamp(sign * (p_y - max_{c != y} p_c), min = -kappa), summed over points
 __global__ void dz_cw_kernel(TView z, const int *__restrict__ labels, int target, long long rows, int ncls,
-                             float kappa, float sgn, TView dz, float *__restrict__ loss_rows)
+                             float kappa, float sgn, TView dz, float *__restrict__ loss_rows,
+                             unsigned char *__restrict__ hit)
 {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
@@ -89,6 +90,11 @@ __global__ void dz_cw_kernel(TView z, const int *__restrict__ labels, int target
     const float val = sgn * (p[y] - other);
     const bool pass = val >= -kappa;
     if (loss_rows) loss_rows[row] = pass ? val : -kappa;
+    if (hit) {                                            // outputs.max(dim=2)[1] == y (first arg-max)
+        int best = 0;
+        for (int c = 1; c < ncls; ++c) if (v[c] > v[best]) best = c;
+        hit[row] = best == y ? 1 : 0;
+    }
     // g = df/dp ; dz_c = p_c * (g_c - sum_k g_k p_k)
     const float gy = pass ? sgn : 0.f, go = (pass && oc >= 0) ? -sgn : 0.f;
     const float dot = gy * p[y] + (oc >= 0 ? go * p[oc] : 0.f);
@@ -179,10 +185,10 @@ int psg_dz_ce(TView z, const int *labels, int target, long long rows, int ncls, 
     return PSG_OK;
 }
 int psg_dz_cw(TView z, const int *labels, int target, long long rows, int ncls, float kappa, float sign, TView dz,
-              float *loss_rows, cudaStream_t st)
+              float *loss_rows, unsigned char *hit, cudaStream_t st)
 {
     if (ncls > kMaxCls) return PSG_EUNSUPPORTED;
-    dz_cw_kernel<<<nb(rows, 256), 256, 0, st>>>(z, labels, target, rows, ncls, kappa, sign, dz, loss_rows);
+    dz_cw_kernel<<<nb(rows, 256), 256, 0, st>>>(z, labels, target, rows, ncls, kappa, sign, dz, loss_rows, hit);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

@@ -559,7 +559,7 @@ extern "C" int psg_net_loss_grad(psg_net *n, int kind, const float *dlogp, const
         return PSG_OK;
     case 2:
         if (!labels && target < 0) return PSG_EINVAL;
-        PSG_RUN(PF_LOSS, psg_dz_cw(z, labels, target, rows, n->ncls, kappa, scale, dz, loss_rows, st));
+        PSG_RUN(PF_LOSS, psg_dz_cw(z, labels, target, rows, n->ncls, kappa, scale, dz, loss_rows, nullptr, st));
         return PSG_OK;
     }
     return PSG_EINVAL;
@@ -669,6 +669,72 @@ extern "C" int psg_nb_attack(psg_net *n, float *adv, const float *ori, const uin
         PSG_TRY(psg_net_backward(n, t0 + i, nullptr, stream));
         PSG_TRY(psg_net_pgd_update(n, adv, ori, mask, 3, 3, a, eps, 0.f, 1.f, stream));
     }
+    return PSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// norm-unbounded attacks (nontarget.py:52-106, target.py:62-133): one step = one launch sequence
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NuScratch { float *f_rows, *l2_rows, *smooth_rows, *smooth_grad; unsigned char *hit; };
+inline NuScratch nu_carve(float *s, int B, int N)
+{
+    const size_t bn = (size_t)B * N;
+    NuScratch r;
+    r.f_rows = s; r.l2_rows = s + bn; r.smooth_rows = s + 2 * bn; r.smooth_grad = r.smooth_rows + N;
+    r.hit = reinterpret_cast<unsigned char *>(r.smooth_grad + 3 * (size_t)N);
+    return r;
+}
+}  // namespace
+
+extern "C" size_t psg_nu_scratch_floats(int B, int N)
+{
+    if (B <= 0 || N <= 0) return 0;
+    const size_t bn = (size_t)B * N;
+    return 2 * bn + 4 * (size_t)N + (bn + 3) / 4 + 16;
+}
+
+extern "C" int psg_nu_init(psg_net *n, const psg_nu_buffers *b, psg_stream_t stream)
+{
+    if (!n || !n->bound || !b || !b->w || !b->adam_m || !b->adam_v || !b->images || !b->status) return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(b->status, 0, 4 * sizeof(int32_t), st) != cudaSuccess) return PSG_ECUDA;
+    PSG_RUN(PF_PGD, psg_nu_init_k(b->images, n->B, n->in_channels, n->N, b->w, b->adam_m, b->adam_v, st));
+    return PSG_OK;
+}
+
+extern "C" int psg_nu_step(psg_net *n, const psg_nu_buffers *b, int t, int step, int target, int neighbour, float c,
+                           float kappa, float targeted_sign, float step_size, float bc2_sqrt, int reset_adam,
+                           double acc_denom, double thr, int exit_above, int count_masked_only, psg_stream_t stream)
+{
+    if (!n || !n->bound || !b || !b->w || !b->adv || !b->base || !b->images || !b->labels || !b->cost || !b->status ||
+        !b->scratch || step < 0 || acc_denom <= 0.0)
+        return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = n->B, N = n->N, C = n->in_channels;
+    const long long rows = (long long)B * N;
+    NuScratch s = nu_carve(b->scratch, B, N);
+    TView f0 = tv(n->feats[0], n->wfeat[0]), g0 = tv(n->dfeat[0], n->wfeat[0]);
+    PSG_RUN(PF_PGD, psg_nu_build_adv_k(b->w, b->base, b->images, b->mask, B, C, N, f0, b->adv, s.l2_rows, b->status, st));
+    PSG_TRY(psg_net_forward(n, t, nullptr, nullptr, stream));
+    // f(outputs, labels) of nontarget.py:120-128 / target.py:149-168 and its gradient; `hit` feeds
+    // the accuracy test of :86-87 / :96-105
+    PSG_RUN(PF_LOSS, psg_dz_cw(tv(n->Z, n->conv2->npad), b->labels, target, rows, n->ncls, kappa, targeted_sign,
+                               tv(n->dZ, n->conv2->npad), s.f_rows, s.hit, st));
+    PSG_TRY(psg_net_backward(n, t, nullptr, stream));
+    PSG_RUN(PF_LOSS, psg_nu_smooth_k(b->adv, b->images, C, N, neighbour, s.smooth_rows, s.smooth_grad, st));
+    PSG_RUN(PF_LOSS, psg_nu_reduce_k(s.f_rows, s.l2_rows, s.smooth_rows, s.hit, b->mask, rows, N, c, step, acc_denom, thr,
+                                     exit_above, count_masked_only, b->cost, b->status, st));
+    PSG_RUN(PF_PGD, psg_nu_adam_k(b->w, b->adam_m, b->adam_v, g0, b->adv, b->images, s.smooth_grad, b->mask, B, C, N, c,
+                                  step_size, bc2_sqrt, 0.9f, 0.999f, 1e-8f, reset_adam, b->status, st));
+    return PSG_OK;
+}
+
+extern "C" int psg_clamp(float *x, int64_t count, float lo, float hi, psg_stream_t stream)
+{
+    if (!x || count <= 0) return PSG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    PSG_RUN(PF_PGD, psg_clamp_k(x, count, lo, hi, st));
     return PSG_OK;
 }
 

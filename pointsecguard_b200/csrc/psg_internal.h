@@ -59,8 +59,21 @@ int psg_dz_from_dlogp(TView z, const float *dlogp, long long rows, int ncls, TVi
 int psg_dz_ce(TView z, const int *labels, int target, long long rows, int ncls, float scale, TView dz,
               cudaStream_t st);
 int psg_dz_cw(TView z, const int *labels, int target, long long rows, int ncls, float kappa, float sign, TView dz,
-              float *loss_rows, cudaStream_t st);
+              float *loss_rows, unsigned char *hit, cudaStream_t st);
 int psg_pgd_update(float *adv, const float *ori, TView grad, TView feats0, const unsigned char *mask, int B, int C,
                    int N, int c0, int nc, float alpha_signed, float eps, float lo, float hi, cudaStream_t st);
 int psg_confusion(const float *logp, const int *labels, const unsigned char *mask, int target, long long rows, int ncls,
                   long long *conf, cudaStream_t st);
+// nu.cu
+int psg_nu_init_k(const float *images, int B, int C, int N, float *w, float *m, float *v, cudaStream_t st);
+int psg_nu_build_adv_k(const float *w, const float *base, const float *images, const unsigned char *mask, int B, int C,
+                     int N, TView feats0, float *adv, float *l2_rows, const int *status, cudaStream_t st);
+int psg_nu_smooth_k(const float *adv0, const float *images0, int C, int N, int k, float *rows_out, float *grad_out,
+                  cudaStream_t st);
+int psg_nu_reduce_k(const float *f_rows, const float *l2_rows, const float *smooth_rows, const unsigned char *hit,
+                  const unsigned char *mask, long long rows, int nsmooth, float c, int step, double acc_denom, double thr,
+                  int exit_above, int count_masked_only, float *cost, int *status, cudaStream_t st);
+int psg_nu_adam_k(float *w, float *m, float *v, TView grad0, const float *adv, const float *images,
+                const float *smooth_grad, const unsigned char *mask, int B, int C, int N, float c, float step_size,
+                float bc2_sqrt, float beta1, float beta2, float eps, int reset, const int *status, cudaStream_t st);
+int psg_clamp_k(float *x, long long n, float lo, float hi, cudaStream_t st);

@@ -1,0 +1,150 @@
+"""Host side of the norm-unbounded colour attacks -- NU_attack (reference
+PointNet/attacks/torchattacks/attacks/nontarget.py:52-106) and tar_NU_attack (target.py:62-133).
+
+The per-step work (tanh-space colours -> forward -> C&W f -> input gradient -> smoothness term ->
+cost / accuracy test -> Adam) is one C call, ``psg_nu_step`` (csrc/net.cu, csrc/nu.cu), with no host
+round trip.  The host keeps only what the reference decides on the host:
+
+* the FPS start draws on the CPU generator, in the reference's order (pointnet_util.py:75);
+* the early exit: the device latches a ``done`` flag at the step whose accuracy test fires and
+  freezes the attack state; the host reads it once per *chunk* of steps and rewinds the CPU
+  generator to where the reference left it (the draws of the steps it never ran are un-done);
+* tar-NU's schedule (target.py:123-132): every 50 steps halve ``lr`` and re-create Adam; every 10
+  steps after step 10 compare the cost with the one 10 steps earlier and, if it did not drop, add
+  uniform noise to the masked colours (overwritten by tanh(w) at the next step) and clamp **all
+  nine channels** to [0,1] -- which silently changes xyz for the rest of the attack (Q4), so the
+  geometry is rebuilt from the clamped image.  The noise draw is made on the CPU generator and
+  discarded, which keeps later FPS start draws aligned with the CPU reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_MAX_PROBLEMS = 1024     # FPS problems (= forwards x blocks) whose geometry is resident at once
+
+
+def _draw_chunk(eng, T):
+    """FPS starts for T forwards + the generator state after each forward's draws."""
+    sizes = [eng.N] + eng.npoints[:3]
+    starts = torch.empty(4, T, eng.B, dtype=torch.int32)
+    states = []
+    for t in range(T):
+        for l in range(4):
+            starts[l, t] = torch.randint(0, sizes[l], (eng.B,), dtype=torch.long).to(torch.int32)
+        states.append(torch.get_rng_state())
+    return starts, states
+
+
+def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None):
+    """Shared driver.  ``masked_variant`` False -> NU_attack semantics (nontarget.py), True ->
+    tar_NU_attack semantics (target.py); default: masked iff a mask is given."""
+    eng = atk._engine(images)
+    dev = images.device
+    B, Cc, N = images.shape
+    tar_variant = (mask is not None) if masked_variant is None else masked_variant
+    if tar_variant and mask is None:
+        raise ValueError("tar_NU_attack needs a mask (target.py:53)")
+    img = images.detach().to(torch.float32).contiguous()            # `images` of the reference (never modified)
+    base = img                                                       # best_adv_images minus the colours
+    lab = atk._labels_i32(labels, dev)
+    msk = atk._mask_u8(mask, B, N, dev) if mask is not None else None
+    steps = int(atk.steps)
+    st = torch.cuda.current_stream().cuda_stream
+
+    w = torch.empty(B, 3, N, dtype=torch.float32, device=dev)
+    am, av = torch.empty_like(w), torch.empty_like(w)
+    adv = img.clone()
+    cost = torch.zeros(max(steps, 1), dtype=torch.float32, device=dev)
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    scratch = torch.empty(L.psg_nu_scratch_floats(B, N), dtype=torch.float32, device=dev)
+    buf = L.NuBuffers(w.data_ptr(), am.data_ptr(), av.data_ptr(), adv.data_ptr(), base.data_ptr(), img.data_ptr(),
+                      msk.data_ptr() if msk is not None else None, lab.data_ptr(), cost.data_ptr(), status.data_ptr(),
+                      scratch.data_ptr())
+
+    if tar_variant:
+        m_cpu = torch.as_tensor(np.asarray(mask)) if not torch.is_tensor(mask) else mask.cpu()
+        m_cpu = m_cpu.to(torch.bool)
+        # target.py:101-105: hits over the masked points / mask.sum() (the reference's mask is [N])
+        denom = max(float(m_cpu.sum().item()), 1.0)
+        thr, above = (1.0 / 13.0, 0) if target is None else (0.9, 1)
+        masked_only = 1
+    else:
+        denom, thr, above, masked_only = 4096.0, 1.0 / 13.0, 0, 0      # nontarget.py:87,95 (Q9)
+    tgt = -1 if target is None else int(target)
+    sign = float(atk._targeted)                                        # +1 unless set_attack_mode was called (Q3)
+
+    chunk_cap = max(1, _MAX_PROBLEMS // B)
+    eng.bind(B, N, min(chunk_cap, max(steps, 1)))
+    eng.set_input(img)
+    L.psg_nu_init(eng._net, C.byref(buf), st)
+
+    lr = float(atk.lr)
+    adam_k, reset = 0, 0
+    step = 0
+    while step < steps:
+        # a chunk ends where the host has to look at device results (tar-NU's every-10-steps test)
+        end = min(steps, step + chunk_cap)
+        if tar_variant:
+            end = min(end, max(20, (step + 9) // 10 * 10) + 1)
+        T = end - step
+        starts, states = _draw_chunk(eng, T)
+        eng.geometry(starts)
+        for i in range(T):
+            s = step + i
+            adam_k += 1
+            step_size = lr / (1.0 - 0.9 ** adam_k)
+            bc2 = math.sqrt(1.0 - 0.999 ** adam_k)
+            L.psg_nu_step(eng._net, C.byref(buf), i, s, tgt, int(neighbour), float(atk.c), float(atk.kappa), sign,
+                          step_size, bc2, reset, denom, thr, above, masked_only, st)
+            reset = 0
+            if tar_variant and s > 0 and s % 50 == 0:                 # target.py:123-125
+                lr = lr / 2
+                atk.lr = lr
+                adam_k, reset = 0, 1
+        last = end - 1
+        stat = status.cpu()                                           # the chunk's only host sync
+        if int(stat[0]):
+            torch.set_rng_state(states[int(stat[1]) - step])          # un-draw the steps the reference never ran
+            break
+        if tar_variant and last > 10 and last % 10 == 0:              # target.py:127-132
+            c2 = cost[[last, last - 10]].cpu()
+            if float(c2[0]) >= float(c2[1]):
+                noise = _bingo_noise(m_cpu, B)                        # CPU-generator draw, as the CPU reference makes it
+                if last == steps - 1:
+                    # the loop ends here: the reference returns the noised, all-channel-clamped image
+                    _apply_noise(adv, noise, m_cpu)
+                    L.psg_clamp(adv.data_ptr(), adv.numel(), 0.0, 1.0, st)
+                elif base is img:
+                    # the noise is overwritten by tanh(w) at the next step; what persists is the clamp
+                    # of all nine channels (Q4): xyz changes, so the geometry is rebuilt from it
+                    base = img.clone()
+                    L.psg_clamp(base.data_ptr(), base.numel(), 0.0, 1.0, st)
+                    buf.base = base.data_ptr()
+                    eng.set_input(base)
+        step = end
+    atk.model._generation += 1
+    return adv
+
+
+def _bingo_noise(m_cpu, B):
+    """torch.empty_like(best[:, 3:6][:, :, mask]).uniform_(0, 1) of target.py:131."""
+    if m_cpu.dim() == 1:
+        return torch.empty(B, 3, int(m_cpu.sum())).uniform_(0, 1)
+    return [torch.empty(3, int(m_cpu[b].sum())).uniform_(0, 1) for b in range(B)]
+
+
+def _apply_noise(adv, noise, m_cpu):
+    m = m_cpu.to(adv.device)
+    if m_cpu.dim() == 1:
+        col = adv[:, 3:6]
+        col[:, :, m] = col[:, :, m] + noise.to(adv.device)
+    else:
+        for b, nz in enumerate(noise):
+            col = adv[b, 3:6]
+            col[:, m[b]] = col[:, m[b]] + nz.to(adv.device)
