@@ -722,7 +722,11 @@ extern "C" int psg_nu_step(psg_net *n, const psg_nu_buffers *b, int t, int step,
     PSG_RUN(PF_LOSS, psg_dz_cw(tv(n->Z, n->conv2->npad), b->labels, target, rows, n->ncls, kappa, targeted_sign,
                                tv(n->dZ, n->conv2->npad), s.f_rows, s.hit, st));
     PSG_TRY(psg_net_backward(n, t, nullptr, stream));
-    PSG_RUN(PF_LOSS, psg_nu_smooth_k(b->adv, b->images, C, N, neighbour, s.smooth_rows, s.smooth_grad, st));
+    if (neighbour > 0) {
+        PSG_RUN(PF_LOSS, psg_nu_smooth_k(b->adv, b->images, C, N, neighbour, s.smooth_rows, s.smooth_grad, st));
+    } else if (cudaMemsetAsync(s.smooth_rows, 0, 4 * (size_t)N * sizeof(float), st) != cudaSuccess) {
+        return PSG_ECUDA;      // this rank does not own global block 0 (nontarget.py:131): no smoothness term
+    }
     PSG_RUN(PF_LOSS, psg_nu_reduce_k(s.f_rows, s.l2_rows, s.smooth_rows, s.hit, b->mask, rows, N, c, step, acc_denom, thr,
                                      exit_above, count_masked_only, b->cost, b->status, st));
     PSG_RUN(PF_PGD, psg_nu_adam_k(b->w, b->adam_m, b->adam_v, g0, b->adv, b->images, s.smooth_grad, b->mask, B, C, N, c,

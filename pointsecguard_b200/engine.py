@@ -82,6 +82,7 @@ class Engine:
         self.B = self.N = self.T = 0
         self._ws = None
         self.mlp_mode = mlp_mode
+        self.shard = None           # distributed.Shard when the bound batch is a slice of a global batch
 
     def _fill(self, m: L.MlpDesc, w: np.ndarray, b: np.ndarray):
         w = np.ascontiguousarray(w, dtype=np.float32)
@@ -122,12 +123,18 @@ class Engine:
         """FPS start indices for T forwards, drawn on the global CPU generator in the reference's
         call order (per forward: level 1..4, each ``torch.randint(0, N_level, (B,))``,
         pointnet_util.py:75).  Returns int32 [4, T, B] (CPU)."""
+        from .distributed import Shard, draw_starts
         sizes = [self.N] + self.npoints[:3]
-        out = torch.empty(4, T, self.B, dtype=torch.int32)
-        for t in range(T):
-            for l in range(4):
-                out[l, t] = torch.randint(0, sizes[l], (self.B,), dtype=torch.long).to(torch.int32)
-        return out
+        shard = self.shard if self.shard is not None else Shard(self.B, 0, self.B)
+        if shard.size != self.B:
+            raise ValueError(f"shard of {shard.size} blocks does not match the bound batch of {self.B}")
+        return draw_starts(sizes, T, shard)
+
+    def set_shard(self, shard):
+        """Declare the bound batch to be ``shard`` of a global batch (multi-GPU runs): the FPS start
+        draws are then made for the whole global batch and sliced, so every rank consumes the CPU
+        generator like the single-GPU run does."""
+        self.shard = shard
 
     def set_input(self, x: torch.Tensor):
         if x.dim() != 3 or x.shape[0] != self.B or x.shape[1] != self.in_channels or x.shape[2] != self.N:

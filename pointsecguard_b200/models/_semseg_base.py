@@ -50,6 +50,15 @@ class SemSegBase(nn.Module):
         self._engine = None
         self._engine_key = None
         self._generation = 0
+        self._shard = None
+
+    def set_shard(self, shard):
+        """Multi-GPU runs: declare that the batches this replica sees are ``shard``
+        (pointsecguard_b200.distributed.Shard) of a global batch; FPS start draws are then made for
+        the global batch and sliced.  ``None`` restores single-process behaviour."""
+        self._shard = shard
+        if self._engine is not None:
+            self._engine.set_shard(shard)
 
     # ---- engine management ----------------------------------------------------------------
     def _param_key(self, device):
@@ -66,6 +75,7 @@ class SemSegBase(nn.Module):
         if self._engine is None or key != self._engine_key:
             self._engine = Engine(self.describe(), device, self.mlp_mode)
             self._engine_key = key
+            self._engine.set_shard(self._shard)
         return self._engine
 
     def set_mlp_mode(self, mode: int):

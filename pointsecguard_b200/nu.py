@@ -25,20 +25,18 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import distributed as D
 
 _MAX_PROBLEMS = 1024     # FPS problems (= forwards x blocks) whose geometry is resident at once
 
 
 def _draw_chunk(eng, T):
     """FPS starts for T forwards + the generator state after each forward's draws."""
-    sizes = [eng.N] + eng.npoints[:3]
-    starts = torch.empty(4, T, eng.B, dtype=torch.int32)
-    states = []
+    starts, states = [], []
     for t in range(T):
-        for l in range(4):
-            starts[l, t] = torch.randint(0, sizes[l], (eng.B,), dtype=torch.long).to(torch.int32)
+        starts.append(eng.draw_starts(1))
         states.append(torch.get_rng_state())
-    return starts, states
+    return torch.cat(starts, dim=1), states
 
 
 def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None):
@@ -80,6 +78,20 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
     sign = float(atk._targeted)                                        # +1 unless set_attack_mode was called (Q3)
 
     chunk_cap = max(1, _MAX_PROBLEMS // B)
+    # Sharded over ranks (distributed.py): the accuracy test and the cost are sums over the GLOBAL
+    # batch, so every step ends with one tiny all-reduce and the host decides, as the reference's
+    # per-step .item() does; the smoothness term belongs to the rank that owns global block 0.
+    sharded = eng.shard is not None and D.world_size() > 1
+    host_cost = {}
+    thr_dev = thr
+    if sharded:
+        chunk_cap = 1
+        thr_dev = 1e30 if above else -1.0                              # the device latch never fires
+        if not eng.shard.owns_block0:
+            neighbour = 0
+        if tar_variant and m_cpu.dim() == 2:
+            dn = torch.tensor([denom], dtype=torch.float64, device=dev)
+            denom = max(float(D.all_reduce_sum_(dn).item()), 1.0)
     eng.bind(B, N, min(chunk_cap, max(steps, 1)))
     eng.set_input(img)
     L.psg_nu_init(eng._net, C.byref(buf), st)
@@ -101,21 +113,29 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
             step_size = lr / (1.0 - 0.9 ** adam_k)
             bc2 = math.sqrt(1.0 - 0.999 ** adam_k)
             L.psg_nu_step(eng._net, C.byref(buf), i, s, tgt, int(neighbour), float(atk.c), float(atk.kappa), sign,
-                          step_size, bc2, reset, denom, thr, above, masked_only, st)
+                          step_size, bc2, reset, denom, thr_dev, above, masked_only, st)
             reset = 0
             if tar_variant and s > 0 and s % 50 == 0:                 # target.py:123-125
                 lr = lr / 2
                 atk.lr = lr
                 adam_k, reset = 0, 1
         last = end - 1
-        stat = status.cpu()                                           # the chunk's only host sync
-        if int(stat[0]):
-            torch.set_rng_state(states[int(stat[1]) - step])          # un-draw the steps the reference never ran
-            break
+        if sharded:
+            red = torch.stack([status[2].double(), cost[last].double()])
+            hits, gcost = D.all_reduce_sum_(red).cpu().tolist()       # the step's only exchange (2 numbers)
+            host_cost[last] = gcost
+            acc = hits / denom
+            if (acc > thr) if above else (acc < thr):
+                break
+        else:
+            stat = status.cpu()                                       # the chunk's only host sync
+            if int(stat[0]):
+                torch.set_rng_state(states[int(stat[1]) - step])      # un-draw the steps the reference never ran
+                break
         if tar_variant and last > 10 and last % 10 == 0:              # target.py:127-132
-            c2 = cost[[last, last - 10]].cpu()
+            c2 = [host_cost[last], host_cost[last - 10]] if sharded else cost[[last, last - 10]].cpu().tolist()
             if float(c2[0]) >= float(c2[1]):
-                noise = _bingo_noise(m_cpu, B)                        # CPU-generator draw, as the CPU reference makes it
+                noise = _bingo_noise(m_cpu, B, eng.shard if sharded else None)   # CPU-generator draw, like the CPU reference's
                 if last == steps - 1:
                     # the loop ends here: the reference returns the noised, all-channel-clamped image
                     _apply_noise(adv, noise, m_cpu)
@@ -132,10 +152,12 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
     return adv
 
 
-def _bingo_noise(m_cpu, B):
-    """torch.empty_like(best[:, 3:6][:, :, mask]).uniform_(0, 1) of target.py:131."""
+def _bingo_noise(m_cpu, B, shard=None):
+    """torch.empty_like(best[:, 3:6][:, :, mask]).uniform_(0, 1) of target.py:131 (under sharding:
+    drawn for the global batch and sliced, so every rank consumes the generator identically)."""
     if m_cpu.dim() == 1:
-        return torch.empty(B, 3, int(m_cpu.sum())).uniform_(0, 1)
+        full = torch.empty(shard.global_batch if shard else B, 3, int(m_cpu.sum())).uniform_(0, 1)
+        return shard.slice(full) if shard else full
     return [torch.empty(3, int(m_cpu[b].sum())).uniform_(0, 1) for b in range(B)]
 
 

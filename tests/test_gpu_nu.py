@@ -65,13 +65,14 @@ def test_tar_nu_attack_vs_reference_golden(golden_dir):
 
 
 def test_nu_early_exit_returns_input_and_rewinds_rng():
-    """With random labels the accuracy test of nontarget.py:95 fires at step 0 (Q7): the input comes
+    """With labels the model never predicts the accuracy test of nontarget.py:95 fires at step 0 (Q7): the input comes
     back unchanged, and the CPU generator is left where the reference leaves it (after ONE forward's
     four start draws), not after the draws of the steps that never ran."""
     from pointsecguard_b200 import torchattacks
     m = _model()
     x = syn.make_blocks(1, 4096, 3).cuda()
-    lab = np.random.default_rng(0).integers(0, 13, (1, 4096)).astype(np.float64)
+    torch.manual_seed(5)
+    lab = ((m(x)[0].argmax(2) + 1) % 13).cpu().numpy().astype(np.float64)
     torch.manual_seed(0)
     adv = torchattacks.NU_attack(m, c=0.1, kappa=0, steps=30, lr=0.01)(x, lab)
     after = torch.randint(0, 1 << 30, (1,)).item()
