@@ -207,6 +207,8 @@ struct Branch {
     float *G, *Y[3];
     unsigned char *arg;
     int *ball;             // [T*B][S][K]
+    bool fused;            // tcgen05 mode runs the branch as one kernel per direction (sa_fused.cu)
+    unsigned *m0, *m1;     // ReLU bits of layers 0 / 1 (fused path)
     int *csr_off, *csr_perm;   // [T*B][R+1], [T*B][S*K]
 };
 
@@ -369,6 +371,12 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
                 if ((size_t)Br.mlp[j]->npad > wmax) wmax = Br.mlp[j]->npad;
             }
             Br.arg = bp.take<unsigned char>((size_t)B * S * Br.mlp[Br.nl - 1]->npad);
+            Br.fused = Br.nl == 3 && psg_sa_fusable(Br.K, Br.gpad, Br.mlp[0]->npad, Br.mlp[1]->npad, Br.mlp[2]->npad);
+            Br.m0 = Br.m1 = nullptr;
+            if (Br.fused) {
+                Br.m0 = bp.take<unsigned>(psg_sa_mask_words(rows, Br.mlp[0]->npad));
+                Br.m1 = bp.take<unsigned>(psg_sa_mask_words(rows, Br.mlp[1]->npad));
+            }
             size_t s = (size_t)round_up_ll(rows, 128) * wmax;
             if (s > scratch) scratch = s;
         }
@@ -487,6 +495,28 @@ extern "C" int psg_net_geometry(psg_net *n, const int32_t *starts, int T, psg_st
 
 static inline TView tv(float *p, int width, int col0 = 0) { return TView{p, width / 4, col0 / 4}; }
 
+static PsgSaFused sa_fused_desc(psg_net *n, int l, int b, int t)
+{
+    SaLevel &L = n->sa[l - 1];
+    Branch &Br = L.br[b];
+    const int B = n->B, S = L.S, R = n->npts[l - 1];
+    PsgSaFused f;
+    f.K = Br.K;
+    f.feats = tv(n->feats[l - 1], n->wfeat[l - 1]); f.D = n->cfeat[l - 1];
+    f.xyz = lvl_xyz(n, l - 1, t); f.cloud_stride = (long long)R * 3; f.nclouds = B; f.Nsrc = R;
+    f.new_xyz = lvl_xyz(n, l, t); f.idx = Br.ball + (size_t)t * B * S * Br.K;
+    f.rows = (long long)B * S * Br.K; f.S = S;
+    f.gpad = Br.gpad;
+    for (int j = 0; j < 3; ++j) {
+        f.n[j] = Br.mlp[j]->npad;
+        f.wf[j] = Br.mlp[j]->wf; f.nwf[j] = Br.mlp[j]->nwf; f.bias[j] = Br.mlp[j]->bias;
+        f.wb[j] = Br.mlp[j]->wb; f.nwb[j] = Br.mlp[j]->nwb;
+    }
+    f.m0 = Br.m0; f.m1 = Br.m1;
+    f.out = tv(n->feats[l], n->wfeat[l], Br.col0); f.arg = Br.arg;
+    return f;
+}
+
 extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points, psg_stream_t stream)
 {
     if (!n || !n->bound || t < 0 || t >= n->T) return PSG_EINVAL;
@@ -499,6 +529,11 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
         for (int b = 0; b < L.nbr; ++b) {
             Branch &Br = L.br[b];
             const long long rows = (long long)B * S * Br.K;
+            if (mode == 1 && Br.fused) {
+                PsgSaFused f = sa_fused_desc(n, l, b, t);
+                PSG_RUN(PF_GEMM_FWD, psg_sa_fused_fwd(f, st));
+                continue;
+            }
             PSG_RUN(PF_GROUP, psg_group(tv(n->feats[l - 1], n->wfeat[l - 1]), D, lvl_xyz(n, l - 1, t), (long long)R * 3, B, R,
                               lvl_xyz(n, l, t), Br.ball + (size_t)t * B * S * Br.K, B, S, Br.K, tv(Br.G, Br.gpad), Br.gpad,
                               st));
@@ -631,6 +666,16 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             Branch &Br = L.br[b];
             const long long rows = (long long)B * S * Br.K;
             const int cw = Br.mlp[Br.nl - 1]->npad;
+            if (n->mode == 1 && Br.fused) {
+                PsgSaFused f = sa_fused_desc(n, l, b, t);
+                const int gcols = round_up(D, 16);       // feature columns only: xyz gets no gradient on this path
+                PSG_RUN(PF_GEMM_BWD, psg_sa_fused_bwd(f, tv(n->dfeat[l], n->wfeat[l], Br.col0), tv(n->S[0], Br.gpad), gcols, st));
+                const size_t go = (size_t)t * B;
+                const int M = S * Br.K;
+                PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[0], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,
+                                   B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, st));
+                continue;
+            }
             TView dy = tv(n->S[0], cw);
             PSG_RUN(PF_MAXPOOL_BWD, psg_maxpool_bwd(tv(n->dfeat[l], n->wfeat[l], Br.col0), tv(n->feats[l], n->wfeat[l], Br.col0), Br.arg,
                                     (long long)B * S, Br.K, cw, dy, st));

@@ -53,6 +53,21 @@ int psg_index_points_rm(const float *pts, const long long *idx, int B, int N, in
 // gemm_simt.cu / gemm_tc.cu
 int psg_gemm_simt(const PsgGemmArgs &g, cudaStream_t st);
 int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st);
+// sa_fused.cu: one set-abstraction branch (gather -> 3 layers -> neighbourhood max) per kernel
+struct PsgSaFused {
+    int K;
+    TView feats; int D; const float *xyz; long long cloud_stride; int nclouds; int Nsrc;
+    const float *new_xyz; const int *idx; long long rows; int S;
+    int gpad; int n[3];
+    const float *wf[3]; int nwf[3]; const float *bias[3];
+    const float *wb[3]; int nwb[3];
+    unsigned *m0, *m1;             // ReLU bits of layers 0 / 1, psg_sa_mask_words(rows, n) words each
+    TView out; unsigned char *arg; // pooled rows [groups][n2 slice of the level's features], arg-max [groups][n2]
+};
+bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2);
+size_t psg_sa_mask_words(long long rows, int n);
+int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st);
+int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st);
 // elementwise.cu
 int psg_head_logsoftmax(TView z, long long rows, int ncls, float *logp, cudaStream_t st);
 int psg_dz_from_dlogp(TView z, const float *dlogp, long long rows, int ncls, TView dz, cudaStream_t st);

@@ -1,0 +1,452 @@
+// sa_fused.cu -- set-abstraction level as ONE kernel per direction (tcgen05 TF32 mode).
+//
+// Reference: PointNet/models/pointnet_util.py:126-137 / :245-255 (gather neighbours, centre xyz,
+// concat), :200-205 / :256-262 (three 1x1 conv + BN + ReLU layers, max over the K neighbours) and
+// the autograd of the same.
+//
+// Forward, per 128-row tile (= 128/K neighbourhoods), persistent CTAs:
+//   workers (4 warps, thread = tile row = TMEM lane) gather the grouped rows straight into shared
+//   memory in the UMMA K-major no-swizzle operand layout; one MMA thread issues
+//   tcgen05.mma.kind::tf32 against the folded weights, which stay resident in shared memory for the
+//   CTA's lifetime; the workers read the accumulator back with tcgen05.ld, apply bias + ReLU and
+//   write the next layer's A operand into shared memory; the last epilogue takes the max over each
+//   neighbourhood with warp REDUX (a warp holds exactly 32/K neighbourhoods) and stores only the
+//   pooled row and its arg-max.  The grouped tensor and the three activation tensors of the
+//   unfused path (1.2 KB per row in SA1) never exist in HBM.
+//
+// Backward needs no activation VALUES (dgrad only, no wgrad): the forward keeps one ReLU bit per
+// activation (8 B per row in SA1).  Per tile: scatter dOut to the arg-max rows -> dY2 in shared
+// memory -> three dgrad GEMMs with the bit masks applied in the epilogues -> dG rows to HBM, which
+// the deterministic segmented sum (gather.cu) then reduces by source point.
+#include "psg_common.cuh"
+#include "psg_internal.h"
+#include "psg_tc.cuh"
+
+namespace {
+
+constexpr int kWorkers = 128;
+constexpr int kThreads = 160;      // 4 worker warps + 1 MMA warp
+
+__device__ __forceinline__ float4 *plane_ptr(unsigned char *buf, int chunk, int row)
+{
+    return reinterpret_cast<float4 *>(buf) + (size_t)chunk * 128 + row;
+}
+
+// packed global weights [planes][nw][4] -> shared [planes][n][4]
+__device__ __forceinline__ void load_weights(unsigned char *dst, const float *src, int planes, int n, int nw)
+{
+    float4 *d = reinterpret_cast<float4 *>(dst);
+    const float4 *s = reinterpret_cast<const float4 *>(src);
+    for (int e = threadIdx.x; e < planes * n; e += blockDim.x) {
+        const int j = e / n, r = e - j * n;
+        d[e] = __ldg(s + (size_t)j * nw + r);
+    }
+}
+
+// D[128 x n] (+)= A[128 x 4*planes] * B[n x 4*planes]^T, both operands in shared memory
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t sA, uint32_t sB, int planes, int n)
+{
+    const uint32_t idesc = tc::idesc_tf32(128, n);
+    uint32_t acc = 0;
+    for (int j = 0; j < planes; j += 2) {
+        const uint64_t ad = tc::smem_desc(sA + j * 2048, 2048, 128);
+        const uint64_t bd = tc::smem_desc(sB + j * n * 16, (uint32_t)(n * 16), 128);
+        tc::mma_tf32(tmem, ad, bd, idesc, acc);
+        acc = 1;
+    }
+}
+
+struct SaFwdArgs {
+    TView feats; int D; const float *xyz; long long cloud_stride; int nclouds; int Nsrc;
+    const float *new_xyz; const int *idx; long long rows; int S;
+    int gpad, n0, n1, n2;
+    const float *w0, *w1, *w2; int nw0, nw1, nw2;
+    const float *b0, *b1, *b2;
+    unsigned *m0, *m1;
+    TView out; unsigned char *arg;
+    int ntiles;
+};
+
+// accumulator -> bias + ReLU -> next A operand in shared memory (+ one ReLU bit per element)
+__device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n, const float *__restrict__ bias,
+                                                      unsigned char *dst, unsigned *mask_tile, int row)
+{
+    unsigned bits = 0;
+    for (int c16 = 0; c16 < n; c16 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_lane + (uint32_t)c16, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            v[i] = fmaxf(v[i] + __ldg(bias + c16 + i), 0.f);
+            bits |= (v[i] > 0.f ? 1u : 0u) << ((c16 & 16) + i);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            *plane_ptr(dst, (c16 >> 2) + c, row) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        if ((c16 & 16) || c16 + 16 >= n) {
+            mask_tile[(size_t)(c16 >> 5) * 128 + row] = bits;
+            bits = 0;
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) sa_fwd_kernel(SaFwdArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_in, bar_acc;
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t s0 = tc::smem_u32(smem_raw);
+    const uint32_t sbase = (s0 + 1023u) & ~1023u;
+    unsigned char *base = smem_raw + (sbase - s0);
+    const int szW0 = a.gpad * a.n0 * 4, szW1 = a.n0 * a.n1 * 4, szW2 = a.n1 * a.n2 * 4;
+    const int szA = max(a.gpad, a.n1) * 512;
+    unsigned char *pW0 = base, *pW1 = pW0 + szW0, *pW2 = pW1 + szW1;
+    unsigned char *pA = pW2 + ((szW2 + 1023) & ~1023), *pY0 = pA + ((szA + 1023) & ~1023);
+    const uint32_t sW0 = sbase, sW1 = sW0 + szW0, sW2 = sW1 + szW1;
+    const uint32_t sA = sW2 + ((szW2 + 1023) & ~1023), sY0 = sA + ((szA + 1023) & ~1023);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nmax = max(a.n0, max(a.n1, a.n2));
+    const uint32_t ncols = tc::next_pow2_cols(nmax);
+
+    load_weights(pW0, a.w0, a.gpad / 4, a.n0, a.nw0);
+    load_weights(pW1, a.w1, a.n0 / 4, a.n1, a.nw1);
+    load_weights(pW2, a.w2, a.n1 / 4, a.n2, a.nw2);
+    if (threadIdx.x == 0) {
+        tc::mbar_init(tc::smem_u32(&bar_in), kWorkers);
+        tc::mbar_init(tc::smem_u32(&bar_acc), 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t b_in = tc::smem_u32(&bar_in), b_acc = tc::smem_u32(&bar_acc);
+
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
+                issue_layer(tmem, sA, sW0, a.gpad / 4, a.n0);
+                tc::mma_commit(b_acc);
+                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
+                issue_layer(tmem, sY0, sW1, a.n0 / 4, a.n1);
+                tc::mma_commit(b_acc);
+                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
+                issue_layer(tmem, sA, sW2, a.n1 / 4, a.n2);
+                tc::mma_commit(b_acc);
+            }
+        }
+    } else {
+        const int r = threadIdx.x;                       // tile row = TMEM lane
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const int k = r % K;
+        const unsigned gmask = (K == 32) ? 0xffffffffu : (0xffffu << (16 * ((lane / 16))));
+        const int w0words = (a.n0 + 31) / 32, w1words = (a.n1 + 31) / 32;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const long long row = (long long)tile * 128 + r;
+            const bool valid = row < a.rows;
+            // ---- gather: [ feats[src] (D) | xyz[src] - centre (3) | 0 ] -> A operand ----
+            {
+                const long long rr = valid ? row : 0;
+                const long long ps = rr / K;
+                const int p = (int)(ps / a.S);
+                const int src = a.idx[rr];
+                const int cloud = p % a.nclouds;
+                const long long srow = (long long)cloud * a.Nsrc + src;
+                const int D = a.D;
+                const int nfull = D >> 2;                 // chunks that are features only
+#pragma unroll 4
+                for (int c = 0; c < nfull; ++c) {
+                    float4 v = valid ? tv_ld(a.feats, srow, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *plane_ptr(pA, c, r) = v;
+                }
+                const float *sp = a.xyz + (long long)cloud * a.cloud_stride + (long long)src * 3;
+                const float *cp = a.new_xyz + ps * 3;
+                const float dx = __fsub_rn(sp[0], cp[0]), dy = __fsub_rn(sp[1], cp[1]), dz = __fsub_rn(sp[2], cp[2]);
+                for (int c = nfull; c < a.gpad / 4; ++c) {
+                    float f[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (4 * c < D) { float4 q = tv_ld(a.feats, srow, c); f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w; }
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ch = 4 * c + j;
+                        o[j] = ch < D ? f[j] : (ch == D ? dx : (ch == D + 1 ? dy : (ch == D + 2 ? dz : 0.f)));
+                        if (!valid) o[j] = 0.f;
+                    }
+                    *plane_ptr(pA, c, r) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(b_in);
+            // ---- layer 0 epilogue -> Y0 ----
+            tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            epilogue_relu_to_smem(tl, a.n0, a.b0, pY0, a.m0 + (size_t)tile * w0words * 128, r);
+            tc::fence_before_sync();
+            tc::fence_async_smem();
+            tc::mbar_arrive(b_in);
+            // ---- layer 1 epilogue -> Y1 (reuses the gather buffer) ----
+            tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            epilogue_relu_to_smem(tl, a.n1, a.b1, pA, a.m1 + (size_t)tile * w1words * 128, r);
+            tc::fence_before_sync();
+            tc::fence_async_smem();
+            tc::mbar_arrive(b_in);
+            // ---- layer 2 epilogue: bias + ReLU + max over the K rows of each neighbourhood ----
+            tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            const long long g = row / K;
+            for (int c16 = 0; c16 < a.n2; c16 += 16) {
+                float v[16];
+                tc::tmem_ld16(tl + (uint32_t)c16, v);
+                unsigned am[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const unsigned b = __float_as_uint(fmaxf(v[i] + __ldg(a.b2 + c16 + i), 0.f));
+                    const unsigned mx = __reduce_max_sync(gmask, b);     // post-ReLU values order like their bits
+                    am[i] = __reduce_min_sync(gmask, b == mx ? (unsigned)k : 64u);   // first arg-max
+                    v[i] = __uint_as_float(mx);
+                }
+                if (k == 0 && valid) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        tv_st(a.out, g, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                    uint4 pk;
+                    pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+                    pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+                    pk.z = am[8] | (am[9] << 8) | (am[10] << 16) | (am[11] << 24);
+                    pk.w = am[12] | (am[13] << 8) | (am[14] << 16) | (am[15] << 24);
+                    *reinterpret_cast<uint4 *>(a.arg + g * a.n2 + c16) = pk;
+                }
+            }
+            tc::fence_before_sync();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, ncols);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct SaBwdArgs {
+    TView dout, outv; const unsigned char *arg;
+    const unsigned *m0, *m1;
+    const float *wb0, *wb1, *wb2; int nwb0, nwb1, nwb2;   // dgrad weights [cout/4][nwb][4], rows = cin
+    TView dG; int gcols;
+    long long rows;
+    int gpad, n0, n1, n2;
+    int ntiles;
+};
+
+// accumulator -> ReLU-bit mask -> next A operand in shared memory
+__device__ __forceinline__ void epilogue_mask_to_smem(uint32_t tmem_lane, int n, const unsigned *mask_tile,
+                                                      unsigned char *dst, int row)
+{
+    unsigned bits = 0;
+    for (int c16 = 0; c16 < n; c16 += 16) {
+        if ((c16 & 16) == 0) bits = mask_tile[(size_t)(c16 >> 5) * 128 + row];
+        float v[16];
+        tc::tmem_ld16(tmem_lane + (uint32_t)c16, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (!((bits >> ((c16 & 16) + i)) & 1u)) v[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            *plane_ptr(dst, (c16 >> 2) + c, row) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) sa_bwd_kernel(SaBwdArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_in, bar_acc;
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t s0 = tc::smem_u32(smem_raw);
+    const uint32_t sbase = (s0 + 1023u) & ~1023u;
+    unsigned char *base = smem_raw + (sbase - s0);
+    // dgrad weights of layer l: planes = cout_l / 4, rows = cin_l
+    const int szW2 = a.n2 * a.n1 * 4, szW1 = a.n1 * a.n0 * 4, szW0 = a.n0 * a.gpad * 4;
+    const int szD2 = max(a.n2, a.n0) * 512;              // dY2, later dY0
+    unsigned char *pW2 = base, *pW1 = pW2 + szW2, *pW0 = pW1 + szW1;
+    unsigned char *pD2 = pW0 + ((szW0 + 1023) & ~1023), *pD1 = pD2 + ((szD2 + 1023) & ~1023);
+    const uint32_t sW2 = sbase, sW1 = sW2 + szW2, sW0 = sW1 + szW1;
+    const uint32_t sD2 = sW0 + ((szW0 + 1023) & ~1023), sD1 = sD2 + ((szD2 + 1023) & ~1023);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nmax = max(a.n0, max(a.n1, a.gpad));
+    const uint32_t ncols = tc::next_pow2_cols(nmax);
+
+    load_weights(pW2, a.wb2, a.n2 / 4, a.n1, a.nwb2);
+    load_weights(pW1, a.wb1, a.n1 / 4, a.n0, a.nwb1);
+    load_weights(pW0, a.wb0, a.n0 / 4, a.gpad, a.nwb0);
+    if (threadIdx.x == 0) {
+        tc::mbar_init(tc::smem_u32(&bar_in), kWorkers);
+        tc::mbar_init(tc::smem_u32(&bar_acc), 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t b_in = tc::smem_u32(&bar_in), b_acc = tc::smem_u32(&bar_acc);
+
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
+                issue_layer(tmem, sD2, sW2, a.n2 / 4, a.n1);       // dY1 = dY2 W2
+                tc::mma_commit(b_acc);
+                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
+                issue_layer(tmem, sD1, sW1, a.n1 / 4, a.n0);       // dY0 = dY1 W1
+                tc::mma_commit(b_acc);
+                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
+                issue_layer(tmem, sD2, sW0, a.n0 / 4, a.gpad);     // dG  = dY0 W0
+                tc::mma_commit(b_acc);
+            }
+        }
+    } else {
+        const int r = threadIdx.x;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const int k = r % K;
+        const int w0words = (a.n0 + 31) / 32, w1words = (a.n1 + 31) / 32;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const long long row = (long long)tile * 128 + r;
+            const bool valid = row < a.rows;
+            const long long g = (valid ? row : 0) / K;
+            // ---- dY2[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0 ----
+            for (int c = 0; c < a.n2 / 4; ++c) {
+                const float4 d = tv_ld(a.dout, g, c);
+                const float4 o = tv_ld(a.outv, g, c);
+                const uchar4 am = *reinterpret_cast<const uchar4 *>(a.arg + g * a.n2 + 4 * c);
+                float4 q;
+                q.x = (valid && am.x == k && o.x > 0.f) ? d.x : 0.f;
+                q.y = (valid && am.y == k && o.y > 0.f) ? d.y : 0.f;
+                q.z = (valid && am.z == k && o.z > 0.f) ? d.z : 0.f;
+                q.w = (valid && am.w == k && o.w > 0.f) ? d.w : 0.f;
+                *plane_ptr(pD2, c, r) = q;
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(b_in);
+            tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            epilogue_mask_to_smem(tl, a.n1, a.m1 + (size_t)tile * w1words * 128, pD1, r);
+            tc::fence_before_sync();
+            tc::fence_async_smem();
+            tc::mbar_arrive(b_in);
+            tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            epilogue_mask_to_smem(tl, a.n0, a.m0 + (size_t)tile * w0words * 128, pD2, r);
+            tc::fence_before_sync();
+            tc::fence_async_smem();
+            tc::mbar_arrive(b_in);
+            tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            for (int c16 = 0; c16 < a.gcols; c16 += 16) {
+                float v[16];
+                tc::tmem_ld16(tl + (uint32_t)c16, v);
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        tv_st(a.dG, row, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                }
+            }
+            tc::fence_before_sync();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, ncols);
+}
+
+int g_num_sms = 0;
+
+template <class Kern>
+int grid_for(Kern kern, size_t smem, int ntiles, int *grid)
+{
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return PSG_ECUDA;
+    }
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) return PSG_ECUDA;
+    if (occ > 4) occ = 4;                               // 128 TMEM columns per CTA, 512 per SM
+    *grid = min(ntiles, g_num_sms * occ);
+    return PSG_OK;
+}
+
+inline size_t r1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
+
+}  // namespace
+
+bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2)
+{
+    if (K != 16 && K != 32) return false;
+    if (gpad % 16 || n0 % 16 || n1 % 16 || n2 % 16) return false;
+    if (gpad > 128 || n0 > 128 || n1 > 128 || n2 > 128) return false;
+    const size_t fwd = (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4) +
+                       r1k((size_t)(gpad > n1 ? gpad : n1) * 512) + (size_t)n0 * 512 + 2048;
+    const size_t bwd = (size_t)n2 * n1 * 4 + (size_t)n1 * n0 * 4 + r1k((size_t)n0 * gpad * 4) +
+                       r1k((size_t)(n2 > n0 ? n2 : n0) * 512) + (size_t)n1 * 512 + 2048;
+    return fwd <= 220 * 1024 && bwd <= 220 * 1024;
+}
+
+size_t psg_sa_mask_words(long long rows, int n)
+{
+    return (size_t)((rows + 127) / 128) * ((n + 31) / 32) * 128;
+}
+
+int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
+{
+    SaFwdArgs a;
+    a.feats = f.feats; a.D = f.D; a.xyz = f.xyz; a.cloud_stride = f.cloud_stride; a.nclouds = f.nclouds; a.Nsrc = f.Nsrc;
+    a.new_xyz = f.new_xyz; a.idx = f.idx; a.rows = f.rows; a.S = f.S;
+    a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
+    a.w0 = f.wf[0]; a.w1 = f.wf[1]; a.w2 = f.wf[2]; a.nw0 = f.nwf[0]; a.nw1 = f.nwf[1]; a.nw2 = f.nwf[2];
+    a.b0 = f.bias[0]; a.b1 = f.bias[1]; a.b2 = f.bias[2];
+    a.m0 = f.m0; a.m1 = f.m1; a.out = f.out; a.arg = f.arg;
+    a.ntiles = (int)((f.rows + 127) / 128);
+    const size_t smem = (size_t)a.gpad * a.n0 * 4 + (size_t)a.n0 * a.n1 * 4 + r1k((size_t)a.n1 * a.n2 * 4) +
+                        r1k((size_t)max(a.gpad, a.n1) * 512) + (size_t)a.n0 * 512 + 1024;
+    int grid = 0, rc;
+    if (f.K == 32) {
+        if ((rc = grid_for(sa_fwd_kernel<32>, smem, a.ntiles, &grid)) != PSG_OK) return rc;
+        sa_fwd_kernel<32><<<grid, kThreads, smem, st>>>(a);
+    } else if (f.K == 16) {
+        if ((rc = grid_for(sa_fwd_kernel<16>, smem, a.ntiles, &grid)) != PSG_OK) return rc;
+        sa_fwd_kernel<16><<<grid, kThreads, smem, st>>>(a);
+    } else return PSG_EUNSUPPORTED;
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}
+
+int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st)
+{
+    SaBwdArgs a;
+    a.dout = dout; a.outv = f.out; a.arg = f.arg; a.m0 = f.m0; a.m1 = f.m1;
+    a.wb0 = f.wb[0]; a.wb1 = f.wb[1]; a.wb2 = f.wb[2]; a.nwb0 = f.nwb[0]; a.nwb1 = f.nwb[1]; a.nwb2 = f.nwb[2];
+    a.dG = dG; a.gcols = gcols; a.rows = f.rows;
+    a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
+    a.ntiles = (int)((f.rows + 127) / 128);
+    const size_t smem = (size_t)a.n2 * a.n1 * 4 + (size_t)a.n1 * a.n0 * 4 + r1k((size_t)a.n0 * a.gpad * 4) +
+                        r1k((size_t)max(a.n2, a.n0) * 512) + (size_t)a.n1 * 512 + 1024;
+    int grid = 0, rc;
+    if (f.K == 32) {
+        if ((rc = grid_for(sa_bwd_kernel<32>, smem, a.ntiles, &grid)) != PSG_OK) return rc;
+        sa_bwd_kernel<32><<<grid, kThreads, smem, st>>>(a);
+    } else if (f.K == 16) {
+        if ((rc = grid_for(sa_bwd_kernel<16>, smem, a.ntiles, &grid)) != PSG_OK) return rc;
+        sa_bwd_kernel<16><<<grid, kThreads, smem, st>>>(a);
+    } else return PSG_EUNSUPPORTED;
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}
