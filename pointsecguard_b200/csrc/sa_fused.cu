@@ -25,7 +25,6 @@
 namespace {
 
 constexpr int kWorkers = 128;
-constexpr int kThreads = 160;      // 4 worker warps + 1 MMA warp
 
 __device__ __forceinline__ float4 *plane_ptr(unsigned char *buf, int chunk, int row)
 {
@@ -90,66 +89,86 @@ __device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n,
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kThreads) sa_fwd_kernel(SaFwdArgs a)
+template <int K, int NG>
+__global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bar_in, bar_acc;
+    __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG];
     __shared__ uint32_t tmem_slot;
 
     const uint32_t s0 = tc::smem_u32(smem_raw);
     const uint32_t sbase = (s0 + 1023u) & ~1023u;
     unsigned char *base = smem_raw + (sbase - s0);
-    const int szW0 = a.gpad * a.n0 * 4, szW1 = a.n0 * a.n1 * 4, szW2 = a.n1 * a.n2 * 4;
-    const int szA = max(a.gpad, a.n1) * 512;
-    unsigned char *pW0 = base, *pW1 = pW0 + szW0, *pW2 = pW1 + szW1;
-    unsigned char *pA = pW2 + ((szW2 + 1023) & ~1023), *pY0 = pA + ((szA + 1023) & ~1023);
-    const uint32_t sW0 = sbase, sW1 = sW0 + szW0, sW2 = sW1 + szW1;
-    const uint32_t sA = sW2 + ((szW2 + 1023) & ~1023), sY0 = sA + ((szA + 1023) & ~1023);
+    const int szW0 = a.gpad * a.n0 * 4, szW1 = a.n0 * a.n1 * 4, szW2 = (a.n1 * a.n2 * 4 + 1023) & ~1023;
+    const int szA = max(a.gpad, a.n1) * 512, szG = szA + a.n0 * 512;   // per group: [A / Y1 | Y0]
+    unsigned char *pW0 = base, *pW1 = pW0 + szW0, *pW2 = pW1 + szW1, *pG = pW2 + szW2;
+    const uint32_t sW0 = sbase, sW1 = sW0 + szW0, sW2 = sW1 + szW1, sG = sW2 + szW2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nmax = max(a.n0, max(a.n1, a.n2));
-    const uint32_t ncols = tc::next_pow2_cols(nmax);
+    const uint32_t gcols = tc::next_pow2_cols(nmax);       // TMEM columns per group
+    const uint32_t ncols = gcols * NG;
 
     load_weights(pW0, a.w0, a.gpad / 4, a.n0, a.nw0);
     load_weights(pW1, a.w1, a.n0 / 4, a.n1, a.nw1);
     load_weights(pW2, a.w2, a.n1 / 4, a.n2, a.nw2);
     if (threadIdx.x == 0) {
-        tc::mbar_init(tc::smem_u32(&bar_in), kWorkers);
-        tc::mbar_init(tc::smem_u32(&bar_acc), 1);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            tc::mbar_init(tc::smem_u32(&bar_in[g]), kWorkers);
+            tc::mbar_init(tc::smem_u32(&bar_acc[g]), 1);
+        }
         tc::fence_mbar_init();
     }
-    if (warp == 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
+    if (warp == NG * 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const uint32_t b_in = tc::smem_u32(&bar_in), b_acc = tc::smem_u32(&bar_acc);
+    const int tstride = gridDim.x * NG;
 
-    if (warp == 4) {
+    if (warp == NG * 4) {
         if (lane == 0) {
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
-                issue_layer(tmem, sA, sW0, a.gpad / 4, a.n0);
-                tc::mma_commit(b_acc);
-                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
-                issue_layer(tmem, sY0, sW1, a.n0 / 4, a.n1);
-                tc::mma_commit(b_acc);
-                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
-                issue_layer(tmem, sA, sW2, a.n1 / 4, a.n2);
-                tc::mma_commit(b_acc);
+            // ---- MMA issuer: serves whichever group has its next A operand ready ----
+            int tile[NG], layer[NG]; uint32_t ph[NG]; bool act[NG];
+            int nact = 0;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                tile[g] = blockIdx.x * NG + g; layer[g] = 0; ph[g] = 0;
+                act[g] = tile[g] < a.ntiles; nact += act[g] ? 1 : 0;
+            }
+            while (nact) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (!act[g] || !tc::mbar_try_wait(tc::smem_u32(&bar_in[g]), ph[g])) continue;
+                    ph[g] ^= 1u;
+                    tc::fence_after_sync();
+                    const uint32_t sA = sG + g * szG, sY0 = sA + szA, tm = tmem + g * gcols;
+                    if (layer[g] == 0) issue_layer(tm, sA, sW0, a.gpad / 4, a.n0);
+                    else if (layer[g] == 1) issue_layer(tm, sY0, sW1, a.n0 / 4, a.n1);
+                    else issue_layer(tm, sA, sW2, a.n1 / 4, a.n2);
+                    tc::mma_commit(tc::smem_u32(&bar_acc[g]));
+                    if (++layer[g] == 3) {
+                        layer[g] = 0; tile[g] += tstride;
+                        if (tile[g] >= a.ntiles) { act[g] = false; --nact; }
+                    }
+                }
             }
         }
     } else {
-        const int r = threadIdx.x;                       // tile row = TMEM lane
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const int grp = warp >> 2, wq = warp & 3;
+        const int r = threadIdx.x & 127;                 // tile row = TMEM lane
+        unsigned char *pA = pG + (size_t)grp * szG, *pY0 = pA + szA;
+        const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
+        const uint32_t tl = tmem + grp * gcols + ((uint32_t)(wq * 32) << 16);
         const int k = r % K;
         const unsigned gmask = (K == 32) ? 0xffffffffu : (0xffffu << (16 * ((lane / 16))));
         const int w0words = (a.n0 + 31) / 32, w1words = (a.n1 + 31) / 32;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        int tile = blockIdx.x * NG + grp;
+        int src_next = (tile < a.ntiles && (long long)tile * 128 + r < a.rows) ? a.idx[(long long)tile * 128 + r] : 0;
+        for (; tile < a.ntiles; tile += tstride) {
             const long long row = (long long)tile * 128 + r;
             const bool valid = row < a.rows;
             // ---- gather: [ feats[src] (D) | xyz[src] - centre (3) | 0 ] -> A operand ----
@@ -157,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) sa_fwd_kernel(SaFwdArgs a)
                 const long long rr = valid ? row : 0;
                 const long long ps = rr / K;
                 const int p = (int)(ps / a.S);
-                const int src = a.idx[rr];
+                const int src = src_next;
                 const int cloud = p % a.nclouds;
                 const long long srow = (long long)cloud * a.Nsrc + src;
                 const int D = a.D;
@@ -182,6 +201,9 @@ __global__ void __launch_bounds__(kThreads) sa_fwd_kernel(SaFwdArgs a)
                     }
                     *plane_ptr(pA, c, r) = make_float4(o[0], o[1], o[2], o[3]);
                 }
+                // prefetch the next tile's neighbour index: takes one L2 round trip off its gather
+                const long long nrow = row + (long long)tstride * 128;
+                src_next = (nrow < a.rows) ? a.idx[nrow] : 0;
             }
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
@@ -228,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) sa_fwd_kernel(SaFwdArgs a)
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem, ncols);
+    if (warp == NG * 4) tc::tmem_dealloc(tmem, ncols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -260,70 +282,89 @@ __device__ __forceinline__ void epilogue_mask_to_smem(uint32_t tmem_lane, int n,
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kThreads) sa_bwd_kernel(SaBwdArgs a)
+template <int K, int NG>
+__global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bar_in, bar_acc;
+    __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG];
     __shared__ uint32_t tmem_slot;
 
     const uint32_t s0 = tc::smem_u32(smem_raw);
     const uint32_t sbase = (s0 + 1023u) & ~1023u;
     unsigned char *base = smem_raw + (sbase - s0);
     // dgrad weights of layer l: planes = cout_l / 4, rows = cin_l
-    const int szW2 = a.n2 * a.n1 * 4, szW1 = a.n1 * a.n0 * 4, szW0 = a.n0 * a.gpad * 4;
-    const int szD2 = max(a.n2, a.n0) * 512;              // dY2, later dY0
-    unsigned char *pW2 = base, *pW1 = pW2 + szW2, *pW0 = pW1 + szW1;
-    unsigned char *pD2 = pW0 + ((szW0 + 1023) & ~1023), *pD1 = pD2 + ((szD2 + 1023) & ~1023);
-    const uint32_t sW2 = sbase, sW1 = sW2 + szW2, sW0 = sW1 + szW1;
-    const uint32_t sD2 = sW0 + ((szW0 + 1023) & ~1023), sD1 = sD2 + ((szD2 + 1023) & ~1023);
+    const int szW2 = a.n2 * a.n1 * 4, szW1 = a.n1 * a.n0 * 4, szW0 = (a.n0 * a.gpad * 4 + 1023) & ~1023;
+    // per group one buffer: dY2 [n2 cols]; then dY1 overwrites its first n1 columns and dY0 the next n0
+    const int szG = max(a.n2, a.n1 + a.n0) * 512;
+    unsigned char *pW2 = base, *pW1 = pW2 + szW2, *pW0 = pW1 + szW1, *pG = pW0 + szW0;
+    const uint32_t sW2 = sbase, sW1 = sW2 + szW2, sW0 = sW1 + szW1, sG = sW0 + szW0;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nmax = max(a.n0, max(a.n1, a.gpad));
-    const uint32_t ncols = tc::next_pow2_cols(nmax);
+    const uint32_t gcols = tc::next_pow2_cols(nmax);
+    const uint32_t ncols = gcols * NG;
 
     load_weights(pW2, a.wb2, a.n2 / 4, a.n1, a.nwb2);
     load_weights(pW1, a.wb1, a.n1 / 4, a.n0, a.nwb1);
     load_weights(pW0, a.wb0, a.n0 / 4, a.gpad, a.nwb0);
     if (threadIdx.x == 0) {
-        tc::mbar_init(tc::smem_u32(&bar_in), kWorkers);
-        tc::mbar_init(tc::smem_u32(&bar_acc), 1);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            tc::mbar_init(tc::smem_u32(&bar_in[g]), kWorkers);
+            tc::mbar_init(tc::smem_u32(&bar_acc[g]), 1);
+        }
         tc::fence_mbar_init();
     }
-    if (warp == 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
+    if (warp == NG * 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const uint32_t b_in = tc::smem_u32(&bar_in), b_acc = tc::smem_u32(&bar_acc);
+    const int tstride = gridDim.x * NG;
 
-    if (warp == 4) {
+    if (warp == NG * 4) {
         if (lane == 0) {
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
-                issue_layer(tmem, sD2, sW2, a.n2 / 4, a.n1);       // dY1 = dY2 W2
-                tc::mma_commit(b_acc);
-                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
-                issue_layer(tmem, sD1, sW1, a.n1 / 4, a.n0);       // dY0 = dY1 W1
-                tc::mma_commit(b_acc);
-                tc::mbar_wait(b_in, ph); ph ^= 1u; tc::fence_after_sync();
-                issue_layer(tmem, sD2, sW0, a.n0 / 4, a.gpad);     // dG  = dY0 W0
-                tc::mma_commit(b_acc);
+            int tile[NG], layer[NG]; uint32_t ph[NG]; bool act[NG];
+            int nact = 0;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                tile[g] = blockIdx.x * NG + g; layer[g] = 0; ph[g] = 0;
+                act[g] = tile[g] < a.ntiles; nact += act[g] ? 1 : 0;
+            }
+            while (nact) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (!act[g] || !tc::mbar_try_wait(tc::smem_u32(&bar_in[g]), ph[g])) continue;
+                    ph[g] ^= 1u;
+                    tc::fence_after_sync();
+                    const uint32_t sD2 = sG + g * szG, sD1 = sD2, sD0 = sD2 + a.n1 * 512, tm = tmem + g * gcols;
+                    if (layer[g] == 0) issue_layer(tm, sD2, sW2, a.n2 / 4, a.n1);        // dY1 = dY2 W2
+                    else if (layer[g] == 1) issue_layer(tm, sD1, sW1, a.n1 / 4, a.n0);   // dY0 = dY1 W1
+                    else issue_layer(tm, sD0, sW0, a.n0 / 4, a.gpad);                   // dG  = dY0 W0
+                    tc::mma_commit(tc::smem_u32(&bar_acc[g]));
+                    if (++layer[g] == 3) {
+                        layer[g] = 0; tile[g] += tstride;
+                        if (tile[g] >= a.ntiles) { act[g] = false; --nact; }
+                    }
+                }
             }
         }
     } else {
-        const int r = threadIdx.x;
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const int grp = warp >> 2, wq = warp & 3;
+        const int r = threadIdx.x & 127;
+        unsigned char *pD2 = pG + (size_t)grp * szG, *pD1 = pD2, *pD0 = pD2 + (size_t)a.n1 * 512;
+        const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
+        const uint32_t tl = tmem + grp * gcols + ((uint32_t)(wq * 32) << 16);
         const int k = r % K;
         const int w0words = (a.n0 + 31) / 32, w1words = (a.n1 + 31) / 32;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x * NG + grp; tile < a.ntiles; tile += tstride) {
             const long long row = (long long)tile * 128 + r;
             const bool valid = row < a.rows;
             const long long g = (valid ? row : 0) / K;
             // ---- dY2[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0 ----
+#pragma unroll 4
             for (int c = 0; c < a.n2 / 4; ++c) {
                 const float4 d = tv_ld(a.dout, g, c);
                 const float4 o = tv_ld(a.outv, g, c);
@@ -343,7 +384,7 @@ __global__ void __launch_bounds__(kThreads) sa_bwd_kernel(SaBwdArgs a)
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
-            epilogue_mask_to_smem(tl, a.n0, a.m0 + (size_t)tile * w0words * 128, pD2, r);
+            epilogue_mask_to_smem(tl, a.n0, a.m0 + (size_t)tile * w0words * 128, pD0, r);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
@@ -362,13 +403,36 @@ __global__ void __launch_bounds__(kThreads) sa_bwd_kernel(SaBwdArgs a)
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem, ncols);
+    if (warp == NG * 4) tc::tmem_dealloc(tmem, ncols);
 }
 
 int g_num_sms = 0;
+constexpr size_t kSmemBudget = 226 * 1024;     // per SM, minus what the runtime reserves per CTA
+constexpr size_t kSmemPerCtaMax = 224 * 1024;
+
+inline size_t r1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
+inline size_t fwd_smem(int gpad, int n0, int n1, int n2, int ng)
+{
+    return (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4) +
+           (size_t)ng * ((size_t)(gpad > n1 ? gpad : n1) + n0) * 512 + 1024;
+}
+inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng)
+{
+    return (size_t)n2 * n1 * 4 + (size_t)n1 * n0 * 4 + r1k((size_t)n0 * gpad * 4) +
+           (size_t)ng * (size_t)(n2 > n1 + n0 ? n2 : n1 + n0) * 512 + 1024;
+}
+inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
+
+// CTAs per SM: shared memory (dynamic + 1 KB static + 1 KB reserved) and TMEM columns (512 per SM)
+inline int ctas_per_sm(size_t smem, int tmem_cols)
+{
+    int occ = (int)(kSmemBudget / (smem + 2048));
+    occ = occ < 512 / tmem_cols ? occ : 512 / tmem_cols;
+    return occ < 1 ? 1 : (occ > 8 ? 8 : occ);
+}
 
 template <class Kern>
-int grid_for(Kern kern, size_t smem, int ntiles, int *grid)
+int launch_cfg(Kern kern, size_t smem, int ntiles, int ng, int tmem_cols, int *grid)
 {
     if (g_num_sms == 0) {
         int dev = 0;
@@ -377,14 +441,11 @@ int grid_for(Kern kern, size_t smem, int ntiles, int *grid)
             return PSG_ECUDA;
     }
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) return PSG_ECUDA;
-    if (occ > 4) occ = 4;                               // 128 TMEM columns per CTA, 512 per SM
-    *grid = min(ntiles, g_num_sms * occ);
+    const int want = (ntiles + ng - 1) / ng;
+    const int cap = g_num_sms * ctas_per_sm(smem, tmem_cols);
+    *grid = want < cap ? want : cap;
     return PSG_OK;
 }
-
-inline size_t r1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
 }  // namespace
 
@@ -393,17 +454,20 @@ bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2)
     if (K != 16 && K != 32) return false;
     if (gpad % 16 || n0 % 16 || n1 % 16 || n2 % 16) return false;
     if (gpad > 128 || n0 > 128 || n1 > 128 || n2 > 128) return false;
-    const size_t fwd = (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4) +
-                       r1k((size_t)(gpad > n1 ? gpad : n1) * 512) + (size_t)n0 * 512 + 2048;
-    const size_t bwd = (size_t)n2 * n1 * 4 + (size_t)n1 * n0 * 4 + r1k((size_t)n0 * gpad * 4) +
-                       r1k((size_t)(n2 > n0 ? n2 : n0) * 512) + (size_t)n1 * 512 + 2048;
-    return fwd <= 220 * 1024 && bwd <= 220 * 1024;
+    return fwd_smem(gpad, n0, n1, n2, 1) <= kSmemPerCtaMax && bwd_smem(gpad, n0, n1, n2, 1) <= kSmemPerCtaMax;
 }
 
 size_t psg_sa_mask_words(long long rows, int n)
 {
     return (size_t)((rows + 127) / 128) * ((n + 31) / 32) * 128;
 }
+
+#define SA_LAUNCH(KERN, KK, NGG, ARGS, SMEM, COLS)                                         \
+    do {                                                                                   \
+        int grid__ = 0, rc__;                                                              \
+        if ((rc__ = launch_cfg(KERN<KK, NGG>, SMEM, ARGS.ntiles, NGG, COLS, &grid__)) != PSG_OK) return rc__; \
+        KERN<KK, NGG><<<grid__, NGG * 128 + 32, SMEM, st>>>(ARGS);                         \
+    } while (0)
 
 int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
 {
@@ -415,16 +479,15 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     a.b0 = f.bias[0]; a.b1 = f.bias[1]; a.b2 = f.bias[2];
     a.m0 = f.m0; a.m1 = f.m1; a.out = f.out; a.arg = f.arg;
     a.ntiles = (int)((f.rows + 127) / 128);
-    const size_t smem = (size_t)a.gpad * a.n0 * 4 + (size_t)a.n0 * a.n1 * 4 + r1k((size_t)a.n1 * a.n2 * 4) +
-                        r1k((size_t)max(a.gpad, a.n1) * 512) + (size_t)a.n0 * 512 + 1024;
-    int grid = 0, rc;
-    if (f.K == 32) {
-        if ((rc = grid_for(sa_fwd_kernel<32>, smem, a.ntiles, &grid)) != PSG_OK) return rc;
-        sa_fwd_kernel<32><<<grid, kThreads, smem, st>>>(a);
-    } else if (f.K == 16) {
-        if ((rc = grid_for(sa_fwd_kernel<16>, smem, a.ntiles, &grid)) != PSG_OK) return rc;
-        sa_fwd_kernel<16><<<grid, kThreads, smem, st>>>(a);
-    } else return PSG_EUNSUPPORTED;
+    const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.n2 ? a.n0 : a.n2) : (a.n1 > a.n2 ? a.n1 : a.n2));
+    // two tiles in flight per CTA (they share the resident weights) when shared memory allows
+    const int ng = fwd_smem(a.gpad, a.n0, a.n1, a.n2, 2) <= kSmemPerCtaMax ? 2 : 1;
+    const size_t smem = fwd_smem(a.gpad, a.n0, a.n1, a.n2, ng);
+    if (f.K == 32 && ng == 2) SA_LAUNCH(sa_fwd_kernel, 32, 2, a, smem, gc * 2);
+    else if (f.K == 32) SA_LAUNCH(sa_fwd_kernel, 32, 1, a, smem, gc);
+    else if (f.K == 16 && ng == 2) SA_LAUNCH(sa_fwd_kernel, 16, 2, a, smem, gc * 2);
+    else if (f.K == 16) SA_LAUNCH(sa_fwd_kernel, 16, 1, a, smem, gc);
+    else return PSG_EUNSUPPORTED;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
@@ -437,16 +500,14 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaS
     a.dG = dG; a.gcols = gcols; a.rows = f.rows;
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
-    const size_t smem = (size_t)a.n2 * a.n1 * 4 + (size_t)a.n1 * a.n0 * 4 + r1k((size_t)a.n0 * a.gpad * 4) +
-                        r1k((size_t)max(a.n2, a.n0) * 512) + (size_t)a.n1 * 512 + 1024;
-    int grid = 0, rc;
-    if (f.K == 32) {
-        if ((rc = grid_for(sa_bwd_kernel<32>, smem, a.ntiles, &grid)) != PSG_OK) return rc;
-        sa_bwd_kernel<32><<<grid, kThreads, smem, st>>>(a);
-    } else if (f.K == 16) {
-        if ((rc = grid_for(sa_bwd_kernel<16>, smem, a.ntiles, &grid)) != PSG_OK) return rc;
-        sa_bwd_kernel<16><<<grid, kThreads, smem, st>>>(a);
-    } else return PSG_EUNSUPPORTED;
+    const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.gpad ? a.n0 : a.gpad) : (a.n1 > a.gpad ? a.n1 : a.gpad));
+    const int ng = bwd_smem(a.gpad, a.n0, a.n1, a.n2, 2) <= kSmemPerCtaMax ? 2 : 1;
+    const size_t smem = bwd_smem(a.gpad, a.n0, a.n1, a.n2, ng);
+    if (f.K == 32 && ng == 2) SA_LAUNCH(sa_bwd_kernel, 32, 2, a, smem, gc * 2);
+    else if (f.K == 32) SA_LAUNCH(sa_bwd_kernel, 32, 1, a, smem, gc);
+    else if (f.K == 16 && ng == 2) SA_LAUNCH(sa_bwd_kernel, 16, 2, a, smem, gc * 2);
+    else if (f.K == 16) SA_LAUNCH(sa_bwd_kernel, 16, 1, a, smem, gc);
+    else return PSG_EUNSUPPORTED;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
