@@ -4,6 +4,7 @@
 // update + projection), NB_nontarget_test_semseg.py:187-211 (per-class counters).
 #include "psg_common.cuh"
 #include "psg_internal.h"
+#include "psg_loss.cuh"
 
 namespace {
 
@@ -24,16 +25,9 @@ __device__ __forceinline__ void store_row(const TView &z, long long row, const f
 #pragma unroll
     for (int c = 0; c < kMaxCls / 4; ++c) tv_st(z, row, c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
 }
-// p = softmax(v[0..ncls)), returns log-sum-exp pieces
 __device__ __forceinline__ void softmax_row(const float *v, int ncls, float *p, float &mx, float &lse)
 {
-    mx = v[0];
-    for (int c = 1; c < ncls; ++c) mx = fmaxf(mx, v[c]);
-    float s = 0.f;
-    for (int c = 0; c < ncls; ++c) { p[c] = expf(v[c] - mx); s += p[c]; }
-    lse = logf(s);
-    const float inv = 1.0f / s;
-    for (int c = 0; c < ncls; ++c) p[c] *= inv;
+    psg_softmax_row(v, ncls, p, mx, lse);
 }
 
 __global__ void head_logsoftmax_kernel(TView z, long long rows, int ncls, float *__restrict__ logp)
@@ -51,57 +45,35 @@ __global__ void dz_from_dlogp_kernel(TView z, const float *__restrict__ dlogp, l
 {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
-    float v[kMaxCls], p[kMaxCls], o[kMaxCls], mx, lse;
+    float v[kMaxCls], o[kMaxCls];
     load_row(z, row, ncls, v);
-    softmax_row(v, ncls, p, mx, lse);
-    float s = 0.f;
-    for (int c = 0; c < ncls; ++c) s += dlogp[row * ncls + c];
-    for (int c = 0; c < kMaxCls; ++c) o[c] = c < ncls ? dlogp[row * ncls + c] - p[c] * s : 0.f;
+    psg_dz_generic(v, ncls, dlogp + row * ncls, o);
     store_row(dz, row, o);
 }
 
-// cross-entropy on the log-probabilities (log_softmax is idempotent): dz = (softmax - onehot) * scale
 __global__ void dz_ce_kernel(TView z, const int *__restrict__ labels, int target, long long rows, int ncls,
                              float scale, TView dz)
 {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
-    float v[kMaxCls], p[kMaxCls], o[kMaxCls], mx, lse;
+    float v[kMaxCls], o[kMaxCls];
     load_row(z, row, ncls, v);
-    softmax_row(v, ncls, p, mx, lse);
-    const int y = target >= 0 ? target : labels[row];
-    for (int c = 0; c < kMaxCls; ++c) o[c] = c < ncls ? (p[c] - (c == y ? 1.f : 0.f)) * scale : 0.f;
+    psg_dz_ce_row(v, ncls, target >= 0 ? target : labels[row], scale, o);
     store_row(dz, row, o);
 }
 
-// C&W f = clamp(sign * (p_y - max_{c != y} p_c), min = -kappa), summed over points
 __global__ void dz_cw_kernel(TView z, const int *__restrict__ labels, int target, long long rows, int ncls,
                              float kappa, float sgn, TView dz, float *__restrict__ loss_rows,
                              unsigned char *__restrict__ hit)
 {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
-    float v[kMaxCls], p[kMaxCls], o[kMaxCls], mx, lse;
+    float v[kMaxCls], o[kMaxCls];
     load_row(z, row, ncls, v);
-    softmax_row(v, ncls, p, mx, lse);
-    const int y = target >= 0 ? target : labels[row];
-    int oc = -1; float other = 0.f;                       // (1 - onehot) * p has a 0 at the label
-    for (int c = 0; c < ncls; ++c) if (c != y && p[c] > other) { other = p[c]; oc = c; }
-    const float val = sgn * (p[y] - other);
-    const bool pass = val >= -kappa;
-    if (loss_rows) loss_rows[row] = pass ? val : -kappa;
-    if (hit) {                                            // outputs.max(dim=2)[1] == y (first arg-max)
-        int best = 0;
-        for (int c = 1; c < ncls; ++c) if (v[c] > v[best]) best = c;
-        hit[row] = best == y ? 1 : 0;
-    }
-    // g = df/dp ; dz_c = p_c * (g_c - sum_k g_k p_k)
-    const float gy = pass ? sgn : 0.f, go = (pass && oc >= 0) ? -sgn : 0.f;
-    const float dot = gy * p[y] + (oc >= 0 ? go * p[oc] : 0.f);
-    for (int c = 0; c < kMaxCls; ++c) {
-        float gc = c == y ? gy : (c == oc ? go : 0.f);
-        o[c] = c < ncls ? p[c] * (gc - dot) : 0.f;
-    }
+    int h;
+    const float f = psg_dz_cw_row(v, ncls, target >= 0 ? target : labels[row], kappa, sgn, o, h);
+    if (loss_rows) loss_rows[row] = f;
+    if (hit) hit[row] = (unsigned char)h;
     store_row(dz, row, o);
 }
 

@@ -249,6 +249,12 @@ struct psg_net {
     float *S[2]; size_t scratch_floats;
     bool bound;
     int last_t;
+    // tcgen05 mode: fp1 + head run as one forward+backward kernel (chain_fused.cu); the loss is then
+    // evaluated inside psg_net_backward from this deferred specification
+    bool head_fused;
+    bool z_valid;          // logits of the last forward are materialised in Z
+    struct { int kind, target; const float *dlogp; const int *labels; float scale, kappa; float *loss_rows;
+             unsigned char *hit; bool set; } loss;
 };
 
 static psg_mlp *make_layer(const psg_mlp_desc &d) { return psg_mlp_create(d.w_host, d.b_host, d.cin, d.cout); }
@@ -315,6 +321,18 @@ extern "C" psg_net *psg_net_create(const psg_net_desc *d)
              d->conv1.cout % 16 == 0;
     }
     if (!ok) { psg_net_destroy(n); return nullptr; }
+    {
+        const FpLevel &F = n->fp[0];
+        bool hf = F.C1 == 0 && F.C2 % 16 == 0 && F.C2 <= 128 && F.nl + 1 <= 4 && n->conv2->npad == 16 &&
+                  n->conv2->nwf <= 128 && n->conv2->nwb == n->conv1->npad;
+        int kprev = F.C2;
+        for (int j = 0; j < F.nl && hf; ++j) {
+            hf = F.mlp[j]->npad <= 128 && F.mlp[j]->nwf == F.mlp[j]->npad && F.mlp[j]->nwb == kprev;
+            kprev = F.mlp[j]->npad;
+        }
+        hf = hf && n->conv1->npad <= 128 && n->conv1->nwf == n->conv1->npad && n->conv1->nwb == kprev;
+        n->head_fused = hf;
+    }
     return n;
 }
 
@@ -517,6 +535,26 @@ static PsgSaFused sa_fused_desc(psg_net *n, int l, int b, int t)
     return f;
 }
 
+// fp1 (+ conv1 as one more hidden layer) + conv2 head, interpolating from `coarse` (fp2's output)
+static PsgChain head_chain_desc(psg_net *n, int t, TView coarse)
+{
+    FpLevel &F = n->fp[0];
+    const int B = n->B, Nf = n->npts[0], Nc = n->npts[1];
+    PsgChain c;
+    memset(&c, 0, sizeof(c));
+    c.src = coarse; c.S = Nc; c.Nf = Nf; c.kin = F.C2; c.rows = (long long)B * Nf;
+    c.nn_idx = F.nn_idx + (size_t)t * B * Nf * 3; c.nn_w = F.nn_w + (size_t)t * B * Nf * 3;
+    c.nlayers = F.nl + 1;
+    for (int j = 0; j <= F.nl; ++j) {
+        const psg_mlp *m = j < F.nl ? F.mlp[j] : n->conv1;
+        c.n[j] = m->npad; c.wf[j] = m->wf; c.nwf[j] = m->nwf; c.bias[j] = m->bias; c.wb[j] = m->wb; c.nwb[j] = m->nwb;
+    }
+    c.head_wf = n->conv2->wf; c.head_nwf = n->conv2->nwf; c.head_bias = n->conv2->bias;
+    c.head_wb = n->conv2->wb; c.head_nwb = n->conv2->nwb;
+    c.ncls = n->ncls; c.target = -1;
+    return c;
+}
+
 extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points, psg_stream_t stream)
 {
     if (!n || !n->bound || t < 0 || t >= n->T) return PSG_EINVAL;
@@ -550,10 +588,24 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
     // feature propagation, coarse to fine
     float *up = n->feats[4];
     int upw = n->wfeat[4];
+    const bool fuse_head = mode == 1 && n->head_fused;
+    n->z_valid = false;
+    n->loss.set = false;
     for (int f = 3; f >= 0; --f) {
         FpLevel &F = n->fp[f];
         const int Nf = n->npts[f], Nc = n->npts[f + 1];
         const long long rows = (long long)B * Nf;
+        if (f == 0 && fuse_head) {
+            // fp1 + head as one kernel; when nobody asked for the log-probabilities the whole chain is
+            // deferred to psg_net_backward, which runs it forward AND backward in one pass
+            if (logp) {
+                PsgChain c = head_chain_desc(n, t, tv(up, upw));
+                c.backward = 0; c.zout = tv(n->Z, n->conv2->npad);
+                PSG_RUN(PF_GEMM_FWD, psg_chain_fused(c, st));
+                n->z_valid = true;
+            }
+            break;
+        }
         PSG_RUN(PF_INTERP, psg_interp(tv(up, upw), Nc, F.nn_idx + (size_t)t * B * Nf * 3, F.nn_w + (size_t)t * B * Nf * 3, B, Nf,
                            F.C2 / 4, tv(F.I, F.C2), st));
         TView a1 = F.C1 ? tv(n->feats[f], n->wfeat[f]) : tv(F.I, F.C2);
@@ -567,37 +619,43 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
         up = F.Y[F.nl - 1]; upw = F.mlp[F.nl - 1]->npad;
     }
     const long long rows0 = (long long)B * n->N;
-    PSG_RUN(PF_GEMM_FWD, mlp_fwd(n->conv1, tv(up, upw), upw / 4, none, 0, rows0, tv(n->H, n->conv1->npad), 1, mode, st));
-    PSG_RUN(PF_GEMM_FWD, mlp_fwd(n->conv2, tv(n->H, n->conv1->npad), n->conv1->npad / 4, none, 0, rows0, tv(n->Z, n->conv2->npad), 0,
-                    mode, st));
+    if (!fuse_head) {
+        PSG_RUN(PF_GEMM_FWD, mlp_fwd(n->conv1, tv(up, upw), upw / 4, none, 0, rows0, tv(n->H, n->conv1->npad), 1, mode, st));
+        PSG_RUN(PF_GEMM_FWD, mlp_fwd(n->conv2, tv(n->H, n->conv1->npad), n->conv1->npad / 4, none, 0, rows0,
+                                     tv(n->Z, n->conv2->npad), 0, mode, st));
+        n->z_valid = true;
+    }
     if (logp) PSG_RUN(PF_HEAD, psg_head_logsoftmax(tv(n->Z, n->conv2->npad), rows0, n->ncls, logp, st));
     if (l4_points) PSG_RUN(PF_PACK, psg_unpack_cf(tv(n->feats[4], n->wfeat[4]), B, n->cfeat[4], n->npts[4], l4_points, 0, st));
     n->last_t = t;
     return PSG_OK;
 }
 
+static int set_loss(psg_net *n, int kind, const float *dlogp, const int32_t *labels, int target, float scale, float kappa,
+                    float *loss_rows, unsigned char *hit, cudaStream_t st)
+{
+    if (kind == 0 && !dlogp) return PSG_EINVAL;
+    if (kind != 0 && !labels && target < 0) return PSG_EINVAL;
+    if (kind < 0 || kind > 2) return PSG_EINVAL;
+    if (n->mode == 1 && n->head_fused) {
+        // evaluated inside the fused fp1 + head kernel launched by psg_net_backward
+        n->loss.kind = kind; n->loss.dlogp = dlogp; n->loss.labels = labels; n->loss.target = target;
+        n->loss.scale = scale; n->loss.kappa = kappa; n->loss.loss_rows = loss_rows; n->loss.hit = hit; n->loss.set = true;
+        return PSG_OK;
+    }
+    const long long rows = (long long)n->B * n->N;
+    TView z = tv(n->Z, n->conv2->npad), dz = tv(n->dZ, n->conv2->npad);
+    if (kind == 0) PSG_RUN(PF_LOSS, psg_dz_from_dlogp(z, dlogp, rows, n->ncls, dz, st));
+    else if (kind == 1) PSG_RUN(PF_LOSS, psg_dz_ce(z, labels, target, rows, n->ncls, scale, dz, st));
+    else PSG_RUN(PF_LOSS, psg_dz_cw(z, labels, target, rows, n->ncls, kappa, scale, dz, loss_rows, hit, st));
+    return PSG_OK;
+}
+
 extern "C" int psg_net_loss_grad(psg_net *n, int kind, const float *dlogp, const int32_t *labels, int target, float scale,
                                  float kappa, float *loss_rows, psg_stream_t stream)
 {
-    if (!n || !n->bound) return PSG_EINVAL;
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long rows = (long long)n->B * n->N;
-    TView z = tv(n->Z, n->conv2->npad), dz = tv(n->dZ, n->conv2->npad);
-    switch (kind) {
-    case 0:
-        if (!dlogp) return PSG_EINVAL;
-        PSG_RUN(PF_LOSS, psg_dz_from_dlogp(z, dlogp, rows, n->ncls, dz, st));
-        return PSG_OK;
-    case 1:
-        if (!labels && target < 0) return PSG_EINVAL;
-        PSG_RUN(PF_LOSS, psg_dz_ce(z, labels, target, rows, n->ncls, scale, dz, st));
-        return PSG_OK;
-    case 2:
-        if (!labels && target < 0) return PSG_EINVAL;
-        PSG_RUN(PF_LOSS, psg_dz_cw(z, labels, target, rows, n->ncls, kappa, scale, dz, loss_rows, nullptr, st));
-        return PSG_OK;
-    }
-    return PSG_EINVAL;
+    if (!n || !n->bound || n->last_t < 0) return PSG_EINVAL;
+    return set_loss(n, kind, dlogp, labels, target, scale, kappa, loss_rows, nullptr, (cudaStream_t)stream);
 }
 
 // Backward through a chain of folded layers.  `top` is the gradient w.r.t. the pre-activation of
@@ -639,6 +697,16 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
         for (int j = 0; j < F.nl; ++j) { mlps[nl] = F.mlp[j]; Ys[nl] = F.Y[j]; ++nl; }
         if (f == 0) { mlps[nl] = n->conv1; Ys[nl] = n->H; ++nl; mlps[nl] = n->conv2; Ys[nl] = n->Z; ++nl; }
         int cat_buf = 0;
+        if (f == 0 && n->mode == 1 && n->head_fused) {
+            if (!n->loss.set) return PSG_EINVAL;
+            FpLevel &C = n->fp[1];
+            PsgChain c = head_chain_desc(n, t, tv(C.Y[C.nl - 1], C.mlp[C.nl - 1]->npad));
+            c.backward = 1; c.loss_kind = n->loss.kind; c.target = n->loss.target; c.labels = n->loss.labels;
+            c.scale = n->loss.scale; c.kappa = n->loss.kappa; c.dlogp = n->loss.dlogp;
+            c.loss_rows = n->loss.loss_rows; c.hit = n->loss.hit;
+            c.dI = tv(n->S[0], F.C2);
+            PSG_RUN(PF_GEMM_BWD, psg_chain_fused(c, st));
+        } else
         PSG_TRY(chain_bwd(n, mlps, Ys, nl, rows, top, top_buf, &cat_buf, st));
         const int catw = F.C1 + F.C2;
         if (F.C1) PSG_RUN(PF_COPY, psg_copy_cols(tv(n->S[cat_buf], catw), tv(n->dfeat[f], n->wfeat[f]), rows, F.C1, 0, st));
@@ -764,8 +832,7 @@ extern "C" int psg_nu_step(psg_net *n, const psg_nu_buffers *b, int t, int step,
     PSG_TRY(psg_net_forward(n, t, nullptr, nullptr, stream));
     // f(outputs, labels) of nontarget.py:120-128 / target.py:149-168 and its gradient; `hit` feeds
     // the accuracy test of :86-87 / :96-105
-    PSG_RUN(PF_LOSS, psg_dz_cw(tv(n->Z, n->conv2->npad), b->labels, target, rows, n->ncls, kappa, targeted_sign,
-                               tv(n->dZ, n->conv2->npad), s.f_rows, s.hit, st));
+    PSG_TRY(set_loss(n, 2, nullptr, b->labels, target, targeted_sign, kappa, s.f_rows, s.hit, st));
     PSG_TRY(psg_net_backward(n, t, nullptr, stream));
     if (neighbour > 0) {
         PSG_RUN(PF_LOSS, psg_nu_smooth_k(b->adv, b->images, C, N, neighbour, s.smooth_rows, s.smooth_grad, st));

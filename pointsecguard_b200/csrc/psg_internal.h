@@ -68,6 +68,19 @@ bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2);
 size_t psg_sa_mask_words(long long rows, int n);
 int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st);
 int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st);
+// chain_fused.cu: finest FP level + head, forward [+ loss gradient + backward] in one kernel
+#define PSG_CHAIN_MAX_OPS 10
+struct PsgChain {
+    TView src; int S; const int *nn_idx; const float *nn_w; int Nf; int kin; long long rows;
+    int nlayers;                       // hidden layers (conv + folded BN + ReLU), <= 4
+    int n[4]; const float *wf[4]; int nwf[4]; const float *bias[4]; const float *wb[4]; int nwb[4];
+    const float *head_wf; int head_nwf; const float *head_bias; const float *head_wb; int head_nwb;
+    int backward;                      // 0: logits -> zout; 1: loss gradient + dgrad chain -> dI
+    int ncls, loss_kind, target; const int *labels; float scale, kappa; const float *dlogp;
+    float *loss_rows; unsigned char *hit;
+    TView zout, dI;
+};
+int psg_chain_fused(const PsgChain &c, cudaStream_t st);
 // elementwise.cu
 int psg_head_logsoftmax(TView z, long long rows, int ncls, float *logp, cudaStream_t st);
 int psg_dz_from_dlogp(TView z, const float *dlogp, long long rows, int ncls, TView dz, cudaStream_t st);

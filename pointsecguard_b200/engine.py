@@ -161,6 +161,7 @@ class Engine:
 
     def loss_grad_generic(self, dlogp: torch.Tensor):
         dlogp = dlogp.contiguous()
+        self._dlogp_keep = dlogp      # read by the kernels psg_net_backward launches (deferred loss, tcgen05 mode)
         L.psg_net_loss_grad(self._net, 0, dlogp.data_ptr(), None, -1, 1.0, 0.0, None, self._stream())
 
     def loss_grad_ce(self, labels: torch.Tensor | None, target: int, scale: float):
