@@ -81,8 +81,10 @@ int psg_group_max_backward(const float *dout_base, int dout_wchunks, int dout_c0
 int psg_interpolate(const float *feats_base, int feats_wchunks, int S, const int32_t *idx, const float *w,
                     int64_t P, int N, int ncols, float *out_base, int out_wchunks, int out_c0, psg_stream_t stream);
 size_t psg_csr_workspace(int64_t P, int M, int R);
-int psg_csr_build_by_source(const int32_t *keys, int64_t P, int M, int R, int32_t *offsets, int32_t *perm,
-                            void *workspace, psg_stream_t stream);
+/* pad_group = nsample when `keys` are ball-query rows: slots that repeat the row's first hit
+ * (pointnet_util.py:104-106 padding) carry exactly-zero gradient rows and are left out; 0 otherwise */
+int psg_csr_build_by_source(const int32_t *keys, int64_t P, int M, int R, int pad_group, int32_t *offsets,
+                            int32_t *perm, void *workspace, psg_stream_t stream);
 int psg_segment_sum(const float *src_base, int src_wchunks, int src_c0, int64_t src_rows_per_problem, int div,
                     const float *weights, const int32_t *offsets, const int32_t *perm, int M, int R, int64_t P,
                     int ncols, float *dst_base, int dst_wchunks, int dst_c0, int accumulate, psg_stream_t stream);

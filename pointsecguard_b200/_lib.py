@@ -64,7 +64,7 @@ _PROTOS = {
     "psg_group_max_backward": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i64, _i, _i, _vp, _i, _vp]),
     "psg_interpolate": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _i, _i, _vp]),
     "psg_csr_workspace": (_sz, [_i64, _i, _i]),
-    "psg_csr_build_by_source": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp]),
+    "psg_csr_build_by_source": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "psg_segment_sum": (_i, [_vp, _i, _i, _i64, _i, _vp, _vp, _vp, _i, _i, _i64, _i, _vp, _i, _i, _i, _vp]),
     "psg_mlp_create": (_vp, [_vp, _vp, _i, _i]),
     "psg_mlp_destroy": (None, [_vp]),

@@ -100,11 +100,11 @@ extern "C" int psg_interpolate(const float *feats_base, int feats_wchunks, int S
 
 extern "C" size_t psg_csr_workspace(int64_t P, int M, int R) { return psg_csr_scratch_bytes(P, M, R); }
 
-extern "C" int psg_csr_build_by_source(const int32_t *keys, int64_t P, int M, int R, int32_t *offsets, int32_t *perm,
-                                       void *workspace, psg_stream_t stream)
+extern "C" int psg_csr_build_by_source(const int32_t *keys, int64_t P, int M, int R, int pad_group, int32_t *offsets,
+                                       int32_t *perm, void *workspace, psg_stream_t stream)
 {
-    if (!keys || !offsets || !perm || !workspace || P <= 0 || M <= 0 || R <= 0) return PSG_EINVAL;
-    return psg_csr_build(keys, P, M, R, offsets, perm, workspace, (cudaStream_t)stream);
+    if (!keys || !offsets || !perm || !workspace || P <= 0 || M <= 0 || R <= 0 || pad_group < 0) return PSG_EINVAL;
+    return psg_csr_build(keys, P, M, R, pad_group, offsets, perm, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int psg_segment_sum(const float *src_base, int src_wchunks, int src_c0, int64_t src_rows_per_problem, int div,

@@ -26,7 +26,13 @@ __device__ __forceinline__ void warp_argmax(unsigned &bits, int &idx)
 
 // MODE 0: coordinates in registers (+ shared copy for the centroid broadcast), N <= THREADS*PPT
 // MODE 1: coordinates only in shared memory (N <= 16384), min-distance in registers
-template <int THREADS, int PPT, int MODE>
+// EXACT:  N == THREADS*PPT, no bounds checks in the round loop (the common 4096 / 1024 / 256 / 64 case)
+//
+// The round loop is issue-bound (every round touches every point), so it is written to minimise
+// instructions: min-distance update is one FMNMX, the per-thread arg-max keeps (value, slot) with a
+// strict '>' (slots ascend with the point index, so the first maximum wins as torch.max does), and
+// the point index is formed once per round.
+template <int THREADS, int PPT, int MODE, bool EXACT>
 __global__ void __launch_bounds__(THREADS)
 fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, int N, int npoint,
            const int *__restrict__ start, int *__restrict__ out_idx, float *__restrict__ out_xyz)
@@ -47,8 +53,9 @@ fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, i
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
         int i = k * THREADS + t;
-        mind[k] = 1e10f;
-        if (i < N) {
+        // slots past the end of the cloud keep -1 (below every real distance): never selected
+        mind[k] = (EXACT || i < N) ? 1e10f : -1.f;
+        if (EXACT || i < N) {
             float x = cloud[3 * i], y = cloud[3 * i + 1], z = cloud[3 * i + 2];
             sx[i] = x; sy[i] = y; sz[i] = z;
             if (MODE == 0) { px[k] = x; py[k] = y; pz[k] = z; }
@@ -57,28 +64,29 @@ fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, i
     int far = start[p];
     __syncthreads();
 
+    int *oi = out_idx + (long long)p * npoint;
+    float *ox = out_xyz ? out_xyz + (long long)p * npoint * 3 : nullptr;
     int buf = 0;
     for (int it = 0; it < npoint; ++it) {
         const float cx = sx[far], cy = sy[far], cz = sz[far];
         if (t == 0) {
-            out_idx[(long long)p * npoint + it] = far;
-            if (out_xyz) {
-                float *o = out_xyz + ((long long)p * npoint + it) * 3;
-                o[0] = cx; o[1] = cy; o[2] = cz;
-            }
+            oi[it] = far;
+            if (ox) { ox[3 * it] = cx; ox[3 * it + 1] = cy; ox[3 * it + 2] = cz; }
         }
-        unsigned best = 0u; int besti = kIntMax;
+        float bestv = -2.f; int bestk = 0;
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
-            int i = k * THREADS + t;
-            if (i < N) {
-                float d = (MODE == 0) ? psg_fpsdist(px[k], py[k], pz[k], cx, cy, cz)
-                                      : psg_fpsdist(sx[i], sy[i], sz[i], cx, cy, cz);
-                if (d < mind[k]) mind[k] = d;
-                unsigned b = __float_as_uint(mind[k]);
-                if (b > best || besti == kIntMax) { best = b; besti = i; }   // i ascends with k
+            const int i = k * THREADS + t;
+            if (EXACT || i < N) {
+                const float d = (MODE == 0) ? psg_fpsdist(px[k], py[k], pz[k], cx, cy, cz)
+                                            : psg_fpsdist(sx[i], sy[i], sz[i], cx, cy, cz);
+                mind[k] = fminf(mind[k], d);          // d is never NaN for finite inputs
             }
+            if (mind[k] > bestv) { bestv = mind[k]; bestk = k; }
         }
+        // distances are >= 0 (or the -1 sentinel, mapped to 0 bits below) so their bit patterns order like unsigned ints
+        unsigned best = bestv < 0.f ? 0u : __float_as_uint(bestv);
+        int besti = bestv < 0.f ? kIntMax : bestk * THREADS + t;
         warp_argmax(best, besti);
         if (NW > 1) {
             if (lane == 0) { red_v[buf * 32 + warp] = best; red_i[buf * 32 + warp] = besti; }
@@ -142,7 +150,7 @@ int launch_fps(const float *xyz, long long cloud_stride, int nclouds, int P, int
                const int *start, int *out_idx, float *out_xyz, cudaStream_t st)
 {
     size_t smem = (size_t)3 * N * sizeof(float) + 128 * sizeof(int);
-    auto kern = fps_kernel<THREADS, PPT, MODE>;
+    auto kern = (N == THREADS * PPT) ? fps_kernel<THREADS, PPT, MODE, true> : fps_kernel<THREADS, PPT, MODE, false>;
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return PSG_ECUDA;
@@ -168,6 +176,10 @@ int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P,
     if (N <= 256) return launch_fps<256, 1, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 1024) return launch_fps<512, 2, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 2048) return launch_fps<512, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    // many problems in flight (attack geometry batches): fewer, fatter threads -- the per-round warp
+    // overhead (REDUX, barrier, exchange) is amortised over 16 points and 4 CTAs share an SM
+    if (N <= 4096 && N > 2048 && P >= 256)
+        return launch_fps<256, 16, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 4096) return launch_fps<1024, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 16384) return launch_fps<1024, 16, 1>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (ws_bytes < psg_fps_workspace_bytes(P, N) || !ws) return PSG_EWORKSPACE;

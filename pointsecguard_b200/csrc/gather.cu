@@ -131,30 +131,31 @@ __global__ void __launch_bounds__(256)
 maxpool_kernel(TView in, long long groups, int C, TView out, unsigned char *__restrict__ arg)
 {
     constexpr int GPW = 32 / K;
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nch = C / 4;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (group set, chunk)
     const int lane = threadIdx.x & 31;
-    const long long g0 = wid * GPW;
+    const long long gs = wid / nch;
+    const int c = (int)(wid % nch);
+    const long long g0 = gs * GPW;
     if (g0 >= groups) return;
     const int sub = lane / K, k = lane % K;
     const long long g = g0 + sub;
     const unsigned mask = (K == 32) ? 0xffffffffu : (0xffffu << (16 * sub));
     const bool valid = g < groups;
     const long long row = (valid ? g : g0) * K + k;
-    for (int c = 0; c < C / 4; ++c) {
-        float4 v = tv_ld(in, row, c);
-        unsigned b[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
-        float m[4]; int a[4];
+    float4 v = tv_ld(in, row, c);
+    unsigned b[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+    float m[4]; int a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            unsigned mx = __reduce_max_sync(mask, b[j]);
-            int cand = (b[j] == mx) ? k : 64;
-            a[j] = __reduce_min_sync(mask, cand);
-            m[j] = __uint_as_float(mx);
-        }
-        if (k == 0 && valid) {
-            tv_st(out, g, c, make_float4(m[0], m[1], m[2], m[3]));
-            *reinterpret_cast<uchar4 *>(arg + g * C + 4 * c) = make_uchar4(a[0], a[1], a[2], a[3]);
-        }
+    for (int j = 0; j < 4; ++j) {
+        unsigned mx = __reduce_max_sync(mask, b[j]);
+        int cand = (b[j] == mx) ? k : 64;
+        a[j] = __reduce_min_sync(mask, cand);
+        m[j] = __uint_as_float(mx);
+    }
+    if (k == 0 && valid) {
+        tv_st(out, g, c, make_float4(m[0], m[1], m[2], m[3]));
+        *reinterpret_cast<uchar4 *>(arg + g * C + 4 * c) = make_uchar4(a[0], a[1], a[2], a[3]);
     }
 }
 
@@ -206,13 +207,23 @@ __global__ void interp_kernel(TView feats, int S, const int *__restrict__ idx, c
 }
 
 // ---- CSR by source (built once per geometry) ------------------------------------------------------
-__global__ void csr_count_kernel(const int *__restrict__ keys, long long total, int M, int R, int *__restrict__ cnt)
+// `grp` > 0: keys are ball-query rows of grp slots; a slot k > 0 holding the group's first hit is
+// padding (pointnet_util.py:104-106).  Padded rows are exact copies of the first row, the max-pool
+// routes the gradient to the first of equal rows, so their gradient rows are exactly zero: they are
+// left out of the CSR (6x fewer entries at SA1 densities, and no 200-entry buckets).
+__device__ __forceinline__ bool csr_is_pad(const int *__restrict__ keys, long long t, int slot, int key, int grp)
+{
+    if (grp <= 0) return false;
+    const int k = slot % grp;
+    return k > 0 && key == keys[t - k];
+}
+__global__ void csr_count_kernel(const int *__restrict__ keys, long long total, int M, int R, int grp, int *__restrict__ cnt)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const long long p = t / M;
     const int key = keys[t];
-    if (key >= 0 && key < R) atomicAdd(cnt + p * (R + 1) + key, 1);
+    if (key >= 0 && key < R && !csr_is_pad(keys, t, (int)(t % M), key, grp)) atomicAdd(cnt + p * (R + 1) + key, 1);
 }
 // exclusive scan of cnt[p][0..R) in place -> offsets[p][0..R]; one CTA per problem
 __global__ void __launch_bounds__(1024) csr_scan_kernel(int *__restrict__ cnt, int R)
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int *__restrict__ cnt, i
     }
     if (threadIdx.x == 0) row[R] = carry_s;
 }
-__global__ void csr_fill_kernel(const int *__restrict__ keys, long long total, int M, int R,
+__global__ void csr_fill_kernel(const int *__restrict__ keys, long long total, int M, int R, int grp,
                                 const int *__restrict__ offs, int *__restrict__ cursor, int *__restrict__ tmp)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,12 +266,12 @@ __global__ void csr_fill_kernel(const int *__restrict__ keys, long long total, i
     const long long p = t / M;
     const int slot = (int)(t % M);
     const int key = keys[t];
-    if (key < 0 || key >= R) return;
+    if (key < 0 || key >= R || csr_is_pad(keys, t, slot, key, grp)) return;
     const int pos = atomicAdd(cursor + p * (R + 1) + key, 1);
     tmp[p * M + offs[p * (R + 1) + key] + pos] = slot;
 }
 // order every bucket by slot id: rank = number of bucket members with a smaller slot
-__global__ void csr_rank_kernel(const int *__restrict__ keys, long long total, int M, int R,
+__global__ void csr_rank_kernel(const int *__restrict__ keys, long long total, int M, int R, int grp,
                                 const int *__restrict__ offs, const int *__restrict__ tmp, int *__restrict__ perm)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,7 +279,7 @@ __global__ void csr_rank_kernel(const int *__restrict__ keys, long long total, i
     const long long p = t / M;
     const int slot = (int)(t % M);
     const int key = keys[t];
-    if (key < 0 || key >= R) return;
+    if (key < 0 || key >= R || csr_is_pad(keys, t, slot, key, grp)) return;
     const int lo = offs[p * (R + 1) + key], hi = offs[p * (R + 1) + key + 1];
     const int *b = tmp + p * M;
     int rank = 0;
@@ -278,36 +289,51 @@ __global__ void csr_rank_kernel(const int *__restrict__ keys, long long total, i
 
 // ---- ordered segmented sum (backward of group / interp) ---------------------------------------
 // dst[p*R + r][c] (+)= sum over bucket entries e (ascending slot) of scale_e * src[p*rows_per_p + slot_e/div][c]
-// One warp per destination row; lanes stride over chunks.
+// LPR lanes per destination row (narrow rows share a warp); the entry loop issues four independent
+// loads at a time and adds them in bucket order, so the result is bit-reproducible.
+template <int LPR>
 __global__ void __launch_bounds__(256)
 segsum_kernel(TView src, long long src_rows_per_p, int div, const float *__restrict__ wgt,
               const int *__restrict__ offs, const int *__restrict__ perm, int M, int R, long long P,
               int nch, int tail_cols, TView dst, int accumulate, TView rmask)
 {
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long wid = gid / LPR;                 // destination row
+    const int lane = (int)(gid % LPR);
     if (wid >= P * R) return;
     const long long p = wid / R;
     const int r = (int)(wid % R);
     const int lo = offs[p * (R + 1) + r], hi = offs[p * (R + 1) + r + 1];
     const int *pm = perm + p * M;
     const float *ww = wgt ? wgt + p * M : nullptr;
-    for (int c = lane; c < nch; c += 32) {
+    const long long sbase = p * src_rows_per_p;
+    for (int c = lane; c < nch; c += LPR) {
         float4 acc = accumulate ? tv_ld(dst, wid, c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = lo; e < hi; ++e) {
-            const int slot = pm[e];
-            float4 v = tv_ld(src, p * src_rows_per_p + slot / div, c);
-            if (c == nch - 1 && tail_cols) {      // keep only the first tail_cols of the last chunk
-                if (tail_cols < 2) v.y = 0.f;
-                if (tail_cols < 3) v.z = 0.f;
-                v.w = 0.f;
+        const bool tail = (c == nch - 1 && tail_cols);
+        for (int e = lo; e < hi; e += 4) {
+            int slot[4]; float4 v[4]; float sc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) slot[u] = e + u < hi ? pm[e + u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = slot[u] >= 0 ? tv_ld(src, sbase + slot[u] / div, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                sc[u] = (ww && slot[u] >= 0) ? ww[slot[u]] : 1.f;
             }
-            if (ww) {
-                const float s = ww[slot];
-                acc.x = fmaf(v.x, s, acc.x); acc.y = fmaf(v.y, s, acc.y);
-                acc.z = fmaf(v.z, s, acc.z); acc.w = fmaf(v.w, s, acc.w);
-            } else {
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (slot[u] < 0) continue;
+                float4 q = v[u];
+                if (tail) {                      // keep only the first tail_cols of the last chunk
+                    if (tail_cols < 2) q.y = 0.f;
+                    if (tail_cols < 3) q.z = 0.f;
+                    q.w = 0.f;
+                }
+                if (ww) {
+                    acc.x = fmaf(q.x, sc[u], acc.x); acc.y = fmaf(q.y, sc[u], acc.y);
+                    acc.z = fmaf(q.z, sc[u], acc.z); acc.w = fmaf(q.w, sc[u], acc.w);
+                } else {
+                    acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+                }
             }
         }
         if (rmask.base) {                          // gradient w.r.t. the pre-activation of a ReLU layer
@@ -384,8 +410,8 @@ int psg_group(TView feats, int D, const float *xyz, long long cloud_stride, int 
 }
 int psg_maxpool(TView in, long long groups, int K, int C, TView out, unsigned char *arg, cudaStream_t st)
 {
-    if (K == 32) maxpool_kernel<32><<<nblocks(groups * 32, 256), 256, 0, st>>>(in, groups, C, out, arg);
-    else if (K == 16) maxpool_kernel<16><<<nblocks((groups + 1) / 2 * 32, 256), 256, 0, st>>>(in, groups, C, out, arg);
+    if (K == 32) maxpool_kernel<32><<<nblocks(groups * 32 * (C / 4), 256), 256, 0, st>>>(in, groups, C, out, arg);
+    else if (K == 16) maxpool_kernel<16><<<nblocks((groups + 1) / 2 * 32 * (C / 4), 256), 256, 0, st>>>(in, groups, C, out, arg);
     else return PSG_EUNSUPPORTED;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
@@ -410,7 +436,7 @@ int psg_interp(TView feats, int S, const int *idx, const float *w, long long P, 
 }
 // offs [P][R+1], perm [P][M]; scratch: cursor [P][R+1] ints + tmp [P][M] ints
 size_t psg_csr_scratch_bytes(long long P, int M, int R) { return (size_t)P * ((size_t)(R + 1) + M) * sizeof(int); }
-int psg_csr_build(const int *keys, long long P, int M, int R, int *offs, int *perm, void *scratch,
+int psg_csr_build(const int *keys, long long P, int M, int R, int grp, int *offs, int *perm, void *scratch,
                   cudaStream_t st)
 {
     int *cursor = (int *)scratch;
@@ -418,10 +444,10 @@ int psg_csr_build(const int *keys, long long P, int M, int R, int *offs, int *pe
     const long long total = P * M;
     if (cudaMemsetAsync(offs, 0, (size_t)P * (R + 1) * sizeof(int), st) != cudaSuccess) return PSG_ECUDA;
     if (cudaMemsetAsync(cursor, 0, (size_t)P * (R + 1) * sizeof(int), st) != cudaSuccess) return PSG_ECUDA;
-    csr_count_kernel<<<nblocks(total, 256), 256, 0, st>>>(keys, total, M, R, offs);
+    csr_count_kernel<<<nblocks(total, 256), 256, 0, st>>>(keys, total, M, R, grp, offs);
     csr_scan_kernel<<<(unsigned)P, 1024, 0, st>>>(offs, R);
-    csr_fill_kernel<<<nblocks(total, 256), 256, 0, st>>>(keys, total, M, R, offs, cursor, tmp);
-    csr_rank_kernel<<<nblocks(total, 256), 256, 0, st>>>(keys, total, M, R, offs, tmp, perm);
+    csr_fill_kernel<<<nblocks(total, 256), 256, 0, st>>>(keys, total, M, R, grp, offs, cursor, tmp);
+    csr_rank_kernel<<<nblocks(total, 256), 256, 0, st>>>(keys, total, M, R, grp, offs, tmp, perm);
     PSG_LAUNCH_CHECK();
     g_psg_launch_count += 3;
     return PSG_OK;
@@ -431,8 +457,18 @@ int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, c
 {
     TView rm = relu_mask ? *relu_mask : TView{nullptr, 0, 0};
     const int nch = (ncols + 3) / 4;
-    segsum_kernel<<<nblocks(P * R * 32, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P,
-                                                           nch, ncols & 3, dst, accumulate, rm);
+    if (nch <= 4)
+        segsum_kernel<4><<<nblocks(P * R * 4, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
+                                                                  ncols & 3, dst, accumulate, rm);
+    else if (nch <= 8)
+        segsum_kernel<8><<<nblocks(P * R * 8, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
+                                                                  ncols & 3, dst, accumulate, rm);
+    else if (nch <= 16)
+        segsum_kernel<16><<<nblocks(P * R * 16, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
+                                                                    ncols & 3, dst, accumulate, rm);
+    else
+        segsum_kernel<32><<<nblocks(P * R * 32, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
+                                                                    ncols & 3, dst, accumulate, rm);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

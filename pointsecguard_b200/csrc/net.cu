@@ -498,7 +498,7 @@ extern "C" int psg_net_geometry(psg_net *n, const int32_t *starts, int T, psg_st
         PSG_RUN(PF_BALL, psg_ball_query_launch(cloud, stride, nclouds, P, R, n->xyz[l], S, L.nbr, L.radius, ns, L.br[0].ball,
                                       L.nbr > 1 ? L.br[1].ball : nullptr, st));
         for (int b = 0; b < L.nbr; ++b)
-            PSG_RUN(PF_CSR, psg_csr_build(L.br[b].ball, P, S * L.br[b].K, R, L.br[b].csr_off, L.br[b].csr_perm, n->csr_ws, st));
+            PSG_RUN(PF_CSR, psg_csr_build(L.br[b].ball, P, S * L.br[b].K, R, L.br[b].K, L.br[b].csr_off, L.br[b].csr_perm, n->csr_ws, st));
     }
     for (int f = 0; f < 4; ++f) {
         FpLevel &F = n->fp[f];
@@ -506,7 +506,7 @@ extern "C" int psg_net_geometry(psg_net *n, const int32_t *starts, int T, psg_st
         const float *fine = f == 0 ? n->xyz0 : n->xyz[f];
         PSG_RUN(PF_NN3, psg_three_nn_launch(fine, (long long)Nf * 3, f == 0 ? B : P, P, Nf, n->xyz[f + 1], Nc, F.nn_idx, F.nn_w,
                                     nullptr, st));
-        PSG_RUN(PF_CSR, psg_csr_build(F.nn_idx, P, Nf * 3, Nc, F.csr_off, F.csr_perm, n->csr_ws, st));
+        PSG_RUN(PF_CSR, psg_csr_build(F.nn_idx, P, Nf * 3, Nc, 0, F.csr_off, F.csr_perm, n->csr_ws, st));
     }
     return PSG_OK;
 }

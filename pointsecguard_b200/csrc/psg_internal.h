@@ -44,7 +44,7 @@ int psg_maxpool_bwd(TView dout, TView outv, const unsigned char *arg, long long 
 int psg_interp(TView feats, int S, const int *idx, const float *w, long long P, int N, int nch, TView out,
                cudaStream_t st);
 size_t psg_csr_scratch_bytes(long long P, int M, int R);
-int psg_csr_build(const int *keys, long long P, int M, int R, int *offs, int *perm, void *scratch, cudaStream_t st);
+int psg_csr_build(const int *keys, long long P, int M, int R, int grp, int *offs, int *perm, void *scratch, cudaStream_t st);
 int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, const int *offs, const int *perm,
                int M, int R, long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, cudaStream_t st);
 int psg_copy_cols(TView src, TView dst, long long rows, int ncols, int accumulate, cudaStream_t st);

@@ -99,11 +99,12 @@ def _chain_backward(chain, ys, dy, rows, device, mode):
     return cur
 
 
-def _csr(keys_i32, P, M, R, device):
+def _csr(keys_i32, P, M, R, device, pad_group=0):
     offs = torch.empty(P * (R + 1), dtype=torch.int32, device=device)
     perm = torch.empty(P * M, dtype=torch.int32, device=device)
     ws = torch.empty(max(L.psg_csr_workspace(P, M, R), 16), dtype=torch.uint8, device=device)
-    L.psg_csr_build_by_source(keys_i32.data_ptr(), P, M, R, offs.data_ptr(), perm.data_ptr(), ws.data_ptr(), _stream())
+    L.psg_csr_build_by_source(keys_i32.data_ptr(), P, M, R, pad_group, offs.data_ptr(), perm.data_ptr(), ws.data_ptr(),
+                              _stream())
     return offs, perm
 
 
@@ -160,7 +161,7 @@ class _SetAbstractionFn(torch.autograd.Function):
             L.psg_group_max_backward(dT.ptr, dT.wchunks, col // 4, out.ptr, out.wchunks, col // 4, arg.data_ptr(), B * S, K,
                                      cw, dy.ptr, dy.wchunks, _stream())
             dG = _chain_backward(chain, ys, dy, rows, dev, mode)
-            offs, perm = _csr(idx, B, S * K, N, dev)
+            offs, perm = _csr(idx, B, S * K, N, dev, pad_group=K)
             L.psg_segment_sum(dG.ptr, dG.wchunks, 0, S * K, 1, None, offs.data_ptr(), perm.data_ptr(), S * K, N, B, D,
                               dfeats.ptr, dfeats.wchunks, 0, 1 if bi > 0 else 0, _stream())
         return dfeats.to_channels_first(B, N, D), None, None, None, None, None
