@@ -1,22 +1,23 @@
-// chain_fused.cu -- the finest feature-propagation level and the classification head as ONE kernel:
-//   3-NN inverse-distance interpolation -> fp1 MLP (3 x 128) -> conv1+bn1+ReLU -> conv2 -> logits
-//   [-> loss gradient -> conv2^T -> conv1^T -> fp1^T x 3 -> gradient w.r.t. the interpolated rows]
+// chain_fused.cu -- "tile programs": chains of row-local layers executed per 128-row tile entirely
+// on-chip (tcgen05 TF32, TMEM accumulator, activations in one shared-memory A-operand buffer that
+// every layer overwrites in place), with the weights streamed through a TMA ring.
 //
-// Reference: PointNet/models/pointnet_util.py:305-319 (interpolate + MLP), pointnet2_sem_seg.py:34-39
-// (fp1, conv1, bn1, drop1 (identity in eval), conv2, log_softmax), the attack costs of
-// nontarget.py:34,120-128 / target.py:38,149-168, and autograd of all of it.
+// One kernel, driven by a small op list built on the host, covers
+//   * fp1 + head forward [+ loss gradient + backward]       (psg_chain_fused)
+//   * wide set-abstraction levels, forward and backward     (psg_sa_stream_fwd / _bwd)
+//   * feature-propagation levels, forward and backward      (psg_fp_stream_fwd / _bwd)
+// i.e. every place where the reference runs conv1x1 + BN + ReLU chains whose weights do not fit
+// in shared memory next to the activations (the narrow SA levels keep their weights resident:
+// sa_fused.cu).
 //
-// Every one of these layers is row-local (row = point), so a 128-row tile runs the whole forward
-// AND the whole backward on-chip: activations ping through one shared-memory A-operand buffer
-// (UMMA K-major, no swizzle) and a TMEM accumulator, the ReLU masks the backward needs are bits in
-// shared memory, the loss gradient is computed in registers from the 13 logits of the thread's own
-// row.  HBM sees only the interpolation gather (L2-resident coarse features) and the 128-column
-// gradient rows handed to the interpolation backward.  Ten GEMMs per tile and no activation traffic,
-// against 10 separate GEMM launches + 1.1 KB/row of activation round trips in the unfused path.
+// Reference: PointNet/models/pointnet_util.py:126-137,200-205 (group + MLP + max), :305-319
+// (interpolate + concat + MLP), pointnet2_sem_seg.py:34-39 (fp1, conv1, bn1, conv2, log_softmax), the
+// attack costs of nontarget.py:34,120-128 / target.py:38,149-168, and autograd of all of it.
 //
-// The 9 weight matrices (580 KB) do not fit in shared memory: a producer thread streams them
-// through a ring of 32 KB stages with 1-D bulk copies (TMA), and each stage is consumed by BOTH tiles
-// in flight before it is released, halving the L2 -> SM weight traffic.
+// Roles per CTA: NG x 4 worker warps (thread = tile row = TMEM lane; they fill the A operand --
+// gather / interpolate / scatter / load -- and run the epilogues), one MMA-issuing thread, one
+// weight-producer thread.  A weight stage is consumed by all NG tiles in flight before it is
+// released, so the L2 -> SM weight traffic is shared between them.
 #include "psg_common.cuh"
 #include "psg_internal.h"
 #include "psg_loss.cuh"
@@ -24,34 +25,53 @@
 
 namespace {
 
-constexpr int NG = 2;                       // tiles in flight per CTA
 constexpr int kWorkers = 128;
-constexpr int kThreads = NG * 128 + 64;     // workers + MMA warp + weight-producer warp
-constexpr int kStageBytes = 32 * 1024;
 constexpr int kStages = 2;
 constexpr int kMaskSlots = 4;
-constexpr int kABytes = 128 * 512;          // A operand: up to 128 columns
+constexpr int kMaxOps = PSG_CHAIN_MAX_OPS;
 
-enum { EPI_RELU_SAVE = 0, EPI_HEAD = 1, EPI_MASK = 2, EPI_STORE = 3 };
+enum { PRE_NONE = 0, PRE_GROUP, PRE_FP, PRE_LOAD, PRE_SCATTER };
+enum { EPI_NONE = 0, EPI_RELU, EPI_MASK, EPI_HEAD, EPI_STORE, EPI_MAXPOOL };
 
-struct ChainOp {
-    const float *w;        // packed [planes][n][4], contiguous
+struct TileOp {
+    const float *w;            // packed weights [plane][wstride rows][4]
+    int wstride, wrow0, wplane0;
+    int n, planes;             // MMA N; K / 4
+    int aplane0;               // first A-buffer plane read
+    int accumulate;            // continue the previous op's accumulator
+    int pps;                   // planes per weight stage (even)
+    int pre, pre_a;            // A refill before this op (PRE_SCATTER: first column)
+    int epi, relu;
     const float *bias;
-    int planes, n, nstages, epi, slot;
+    int slot;                  // shared-memory mask slot or -1
+    unsigned *mglobal;         // global ReLU bits of this op's output [tile][words][128] or null
+    TView out;                 // EPI_STORE / EPI_MAXPOOL destination (column offset folded into c0)
+    unsigned char *arg; int argC, arg0;   // EPI_MAXPOOL
 };
 
-struct ChainArgs {
-    ChainOp ops[PSG_CHAIN_MAX_OPS];
+struct TileSrc {
+    // PRE_GROUP
+    TView feats; int D, gpad; const float *xyz; long long cloud_stride; int nclouds, Nsrc;
+    const float *new_xyz; const int *idx; int S, K;
+    // PRE_FP: skip rows (row-local) into planes [0, lcols/4), interpolation into planes [iplane0, ...)
+    // PRE_LOAD: lsrc rows only
+    TView lsrc; int lcols;
+    TView isrc; int iS, iNf, icols, iplane0; const int *nn_idx; const float *nn_w;
+    // PRE_SCATTER
+    TView dout, outv; const unsigned char *sarg; int sargC;
+};
+
+struct TileArgs {
+    TileOp ops[kMaxOps];
     int nops;
-    // source: 3-NN interpolation of `src` rows
-    TView src; int S; const int *nn_idx; const float *nn_w; int Nf; int kin;
+    TileSrc src;
     long long rows; int ntiles;
-    // head / loss
-    int backward;          // 0: stop at the logits (stored to zout); 1: loss gradient + backward chain
-    int ncls, loss_kind, target;
+    int abytes, stage_bytes, tcols;      // A buffer bytes per tile, weight stage bytes, TMEM columns per tile
+    // head / loss (EPI_HEAD)
+    int backward, ncls, loss_kind, target;
     const int *labels; float scale, kappa; const float *dlogp;
     float *loss_rows; unsigned char *hit;
-    TView zout, dI;
+    TView zout;
 };
 
 __device__ __forceinline__ float4 *plane_ptr(unsigned char *buf, int chunk, int row)
@@ -59,7 +79,87 @@ __device__ __forceinline__ float4 *plane_ptr(unsigned char *buf, int chunk, int 
     return reinterpret_cast<float4 *>(buf) + (size_t)chunk * 128 + row;
 }
 
-__global__ void __launch_bounds__(kThreads) chain_kernel(const __grid_constant__ ChainArgs a)
+// ---- A-operand producers (worker thread r owns tile row r) ----------------------------------------
+__device__ __forceinline__ void pre_group(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r)
+{
+    const long long rr = valid ? row : 0;
+    const long long ps = rr / s.K;
+    const int p = (int)(ps / s.S);
+    const int src = s.idx[rr];
+    const int cloud = p % s.nclouds;
+    const long long srow = (long long)cloud * s.Nsrc + src;
+    const int D = s.D, nfull = D >> 2;
+#pragma unroll 4
+    for (int c = 0; c < nfull; ++c)
+        *plane_ptr(pA, c, r) = valid ? tv_ld(s.feats, srow, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *sp = s.xyz + (long long)cloud * s.cloud_stride + (long long)src * 3;
+    const float *cp = s.new_xyz + ps * 3;
+    const float dx = __fsub_rn(sp[0], cp[0]), dy = __fsub_rn(sp[1], cp[1]), dz = __fsub_rn(sp[2], cp[2]);
+    for (int c = nfull; c < s.gpad / 4; ++c) {
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * c < D) { float4 q = tv_ld(s.feats, srow, c); f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w; }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ch = 4 * c + j;
+            o[j] = ch < D ? f[j] : (ch == D ? dx : (ch == D + 1 ? dy : (ch == D + 2 ? dz : 0.f)));
+            if (!valid) o[j] = 0.f;
+        }
+        *plane_ptr(pA, c, r) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__device__ __forceinline__ void pre_load(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r)
+{
+#pragma unroll 4
+    for (int c = 0; c < s.lcols / 4; ++c)
+        *plane_ptr(pA, c, r) = valid ? tv_ld(s.lsrc, row, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// (f[i0] w0 + f[i1] w1) + f[i2] w2, products rounded separately as torch does (pointnet_util.py:308)
+__device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r)
+{
+    const long long rr = valid ? row : 0;
+    const long long p = rr / s.iNf;
+    const int *ii = s.nn_idx + rr * 3;
+    const float *ww = s.nn_w + rr * 3;
+    const long long r0 = p * s.iS + ii[0], r1 = p * s.iS + ii[1], r2 = p * s.iS + ii[2];
+    const float w0 = valid ? ww[0] : 0.f, w1 = valid ? ww[1] : 0.f, w2 = valid ? ww[2] : 0.f;
+#pragma unroll 4
+    for (int c = 0; c < s.icols / 4; ++c) {
+        const float4 x = tv_ld(s.isrc, r0, c), y = tv_ld(s.isrc, r1, c), z = tv_ld(s.isrc, r2, c);
+        float4 q;
+        q.x = __fadd_rn(__fadd_rn(__fmul_rn(x.x, w0), __fmul_rn(y.x, w1)), __fmul_rn(z.x, w2));
+        q.y = __fadd_rn(__fadd_rn(__fmul_rn(x.y, w0), __fmul_rn(y.y, w1)), __fmul_rn(z.y, w2));
+        q.z = __fadd_rn(__fadd_rn(__fmul_rn(x.z, w0), __fmul_rn(y.z, w1)), __fmul_rn(z.z, w2));
+        q.w = __fadd_rn(__fadd_rn(__fmul_rn(x.w, w0), __fmul_rn(y.w, w1)), __fmul_rn(z.w, w2));
+        *plane_ptr(pA, s.iplane0 + c, r) = q;
+    }
+}
+
+// dY[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0 for columns [col0, col0 + 4*planes)
+__device__ __forceinline__ void pre_scatter(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r, int col0,
+                                            int planes)
+{
+    const long long g = (valid ? row : 0) / s.K;
+    const int k = r % s.K;
+    const int c0 = col0 >> 2;
+#pragma unroll 4
+    for (int c = 0; c < planes; ++c) {
+        const float4 d = tv_ld(s.dout, g, c0 + c);
+        const float4 o = tv_ld(s.outv, g, c0 + c);
+        const uchar4 am = *reinterpret_cast<const uchar4 *>(s.sarg + g * s.sargC + col0 + 4 * c);
+        float4 q;
+        q.x = (valid && am.x == k && o.x > 0.f) ? d.x : 0.f;
+        q.y = (valid && am.y == k && o.y > 0.f) ? d.y : 0.f;
+        q.z = (valid && am.z == k && o.z > 0.f) ? d.z : 0.f;
+        q.w = (valid && am.w == k && o.w > 0.f) ? d.w : 0.f;
+        *plane_ptr(pA, c, r) = q;
+    }
+}
+
+template <int NG>
+__global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_constant__ TileArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG], bar_full[kStages], bar_empty[kStages];
@@ -68,18 +168,19 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const __grid_constant__
     const uint32_t s0 = tc::smem_u32(smem_raw);
     const uint32_t sbase = (s0 + 1023u) & ~1023u;
     unsigned char *base = smem_raw + (sbase - s0);
-    // [A g0][A g1][W stage 0][W stage 1][mask bits g0][mask bits g1]
-    const uint32_t sA0 = sbase, sW = sbase + NG * kABytes;
+    // [A tile 0 .. NG-1][W stage 0][W stage 1][mask bits tile 0 .. NG-1]
+    const uint32_t sA0 = sbase, sW = sbase + NG * a.abytes;
     unsigned char *pA0 = base;
-    unsigned *pMask = reinterpret_cast<unsigned *>(base + NG * kABytes + kStages * kStageBytes);
+    unsigned *pMask = reinterpret_cast<unsigned *>(base + (size_t)NG * a.abytes + (size_t)kStages * a.stage_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ncols = (uint32_t)(a.tcols * NG);
     if (threadIdx.x == 0) {
         for (int g = 0; g < NG; ++g) { tc::mbar_init(tc::smem_u32(&bar_in[g]), kWorkers); tc::mbar_init(tc::smem_u32(&bar_acc[g]), 1); }
         for (int s = 0; s < kStages; ++s) { tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1); }
         tc::fence_mbar_init();
     }
-    if (warp == NG * 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), NG * 128);
+    if (warp == NG * 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -92,16 +193,22 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const __grid_constant__
             int it = 0;
             for (int tile0 = blockIdx.x * NG; tile0 < a.ntiles; tile0 += tstride) {
                 for (int o = 0; o < a.nops; ++o) {
-                    const ChainOp &op = a.ops[o];
-                    const uint32_t bytes = (uint32_t)(op.planes / op.nstages) * op.n * 16;
-                    for (int s = 0; s < op.nstages; ++s, ++it) {
+                    const TileOp &op = a.ops[o];
+                    for (int pl = 0; pl < op.planes; pl += op.pps, ++it) {
+                        const int np = min(op.pps, op.planes - pl);
                         const int slot = it % kStages;
                         const uint32_t ph = (uint32_t)(it / kStages) & 1u;
                         tc::mbar_wait(tc::smem_u32(&bar_empty[slot]), ph ^ 1u);
                         const uint32_t full = tc::smem_u32(&bar_full[slot]);
-                        tc::mbar_expect_tx(full, bytes);
-                        tc::bulk_g2s(sW + slot * kStageBytes, reinterpret_cast<const unsigned char *>(op.w) + (size_t)s * bytes,
-                                     bytes, full);
+                        const uint32_t dst = sW + slot * a.stage_bytes;
+                        tc::mbar_expect_tx(full, (uint32_t)np * op.n * 16);
+                        const float4 *wsrc = reinterpret_cast<const float4 *>(op.w) + (size_t)(op.wplane0 + pl) * op.wstride + op.wrow0;
+                        if (op.wstride == op.n) {
+                            tc::bulk_g2s(dst, wsrc, (uint32_t)np * op.n * 16, full);
+                        } else {
+                            for (int j = 0; j < np; ++j)
+                                tc::bulk_g2s(dst + j * op.n * 16, wsrc + (size_t)j * op.wstride, (uint32_t)op.n * 16, full);
+                        }
                     }
                 }
             }
@@ -110,73 +217,67 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const __grid_constant__
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             int it = 0;
-            uint32_t ph_in[NG] = {0u, 0u};
+            uint32_t ph_in[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) ph_in[g] = 0u;
             for (int tile0 = blockIdx.x * NG; tile0 < a.ntiles; tile0 += tstride) {
                 for (int o = 0; o < a.nops; ++o) {
-                    const ChainOp &op = a.ops[o];
-                    const int pps = op.planes / op.nstages;
+                    const TileOp &op = a.ops[o];
                     const uint32_t idesc = tc::idesc_tf32(128, op.n);
-                    for (int s = 0; s < op.nstages; ++s, ++it) {
+                    for (int pl = 0; pl < op.planes; pl += op.pps, ++it) {
+                        const int np = min(op.pps, op.planes - pl);
                         const int slot = it % kStages;
+                        const bool last = pl + op.pps >= op.planes;
                         tc::mbar_wait(tc::smem_u32(&bar_full[slot]), (uint32_t)(it / kStages) & 1u);
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
                             if (tile0 + g >= a.ntiles) continue;
-                            if (s == 0) { tc::mbar_wait(tc::smem_u32(&bar_in[g]), ph_in[g]); ph_in[g] ^= 1u; }
+                            if (pl == 0) { tc::mbar_wait(tc::smem_u32(&bar_in[g]), ph_in[g]); ph_in[g] ^= 1u; }
                             tc::fence_after_sync();
-                            const uint32_t sA = sA0 + g * kABytes + (uint32_t)(s * pps) * 2048u;
-                            const uint32_t sB = sW + slot * kStageBytes;
-                            for (int j = 0; j < pps; j += 2) {
+                            const uint32_t sA = sA0 + g * a.abytes + (uint32_t)(op.aplane0 + pl) * 2048u;
+                            const uint32_t sB = sW + slot * a.stage_bytes;
+                            for (int j = 0; j < np; j += 2) {
                                 const uint64_t ad = tc::smem_desc(sA + j * 2048, 2048, 128);
                                 const uint64_t bd = tc::smem_desc(sB + j * op.n * 16, (uint32_t)(op.n * 16), 128);
-                                tc::mma_tf32(tmem + g * 128, ad, bd, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                                tc::mma_tf32(tmem + g * a.tcols, ad, bd, idesc, (op.accumulate || pl > 0 || j > 0) ? 1u : 0u);
                             }
-                            if (s == op.nstages - 1) tc::mma_commit(tc::smem_u32(&bar_acc[g]));
+                            if (last) tc::mma_commit(tc::smem_u32(&bar_acc[g]));
                         }
-                        tc::mma_commit(tc::smem_u32(&bar_empty[slot]));     // stage free once both tiles consumed it
+                        tc::mma_commit(tc::smem_u32(&bar_empty[slot]));     // stage free once every tile consumed it
                     }
                 }
             }
         }
     } else {
-        // ---------------- workers: thread = tile row = TMEM lane ----------------
+        // ---------------- workers ----------------
         const int grp = warp >> 2, wq = warp & 3;
         const int r = threadIdx.x & 127;
-        unsigned char *pA = pA0 + (size_t)grp * kABytes;
-        unsigned *mbits = pMask + (size_t)grp * kMaskSlots * 4 * 128;
+        unsigned char *pA = pA0 + (size_t)grp * a.abytes;
+        unsigned *mbits = pMask + (size_t)grp * kMaskSlots * 8 * 128;
         const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
-        const uint32_t tl = tmem + grp * 128 + ((uint32_t)(wq * 32) << 16);
+        const uint32_t tl = tmem + grp * a.tcols + ((uint32_t)(wq * 32) << 16);
+        const int K = a.src.K > 0 ? a.src.K : 32;
+        const int k = r % K;
+        const unsigned gmask = (K == 32) ? 0xffffffffu : (0xffffu << (16 * (lane / 16)));
         uint32_t ph = 0;
         for (int tile = blockIdx.x * NG + grp; tile < a.ntiles; tile += tstride) {
             const long long row = (long long)tile * 128 + r;
             const bool valid = row < a.rows;
-            // ---- interpolation: (f[i0] w0 + f[i1] w1) + f[i2] w2, products rounded separately ----
-            {
-                const long long rr = valid ? row : 0;
-                const long long p = rr / a.Nf;
-                const int *ii = a.nn_idx + rr * 3;
-                const float *ww = a.nn_w + rr * 3;
-                const long long r0 = p * a.S + ii[0], r1 = p * a.S + ii[1], r2 = p * a.S + ii[2];
-                const float w0 = valid ? ww[0] : 0.f, w1 = valid ? ww[1] : 0.f, w2 = valid ? ww[2] : 0.f;
-#pragma unroll 4
-                for (int c = 0; c < a.kin / 4; ++c) {
-                    const float4 x = tv_ld(a.src, r0, c), y = tv_ld(a.src, r1, c), z = tv_ld(a.src, r2, c);
-                    float4 q;
-                    q.x = __fadd_rn(__fadd_rn(__fmul_rn(x.x, w0), __fmul_rn(y.x, w1)), __fmul_rn(z.x, w2));
-                    q.y = __fadd_rn(__fadd_rn(__fmul_rn(x.y, w0), __fmul_rn(y.y, w1)), __fmul_rn(z.y, w2));
-                    q.z = __fadd_rn(__fadd_rn(__fmul_rn(x.z, w0), __fmul_rn(y.z, w1)), __fmul_rn(z.z, w2));
-                    q.w = __fadd_rn(__fadd_rn(__fmul_rn(x.w, w0), __fmul_rn(y.w, w1)), __fmul_rn(z.w, w2));
-                    *plane_ptr(pA, c, r) = q;
-                }
-            }
-            tc::fence_async_smem();
-            tc::mbar_arrive(b_in);
             for (int o = 0; o < a.nops; ++o) {
-                const ChainOp &op = a.ops[o];
+                const TileOp &op = a.ops[o];
+                // ---- refill the A operand, hand it to the MMA thread ----
+                if (op.pre == PRE_GROUP) pre_group(a.src, pA, row, valid, r);
+                else if (op.pre == PRE_FP) { if (a.src.lcols) pre_load(a.src, pA, row, valid, r); pre_interp(a.src, pA, row, valid, r); }
+                else if (op.pre == PRE_LOAD) pre_load(a.src, pA, row, valid, r);
+                else if (op.pre == PRE_SCATTER) pre_scatter(a.src, pA, row, valid, r, op.pre_a, op.planes);
+                tc::fence_before_sync();
+                tc::fence_async_smem();
+                tc::mbar_arrive(b_in);
+                // ---- epilogue ----
                 tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
-                if (op.epi == EPI_RELU_SAVE) {
+                const int words = (op.n + 31) / 32;
+                if (op.epi == EPI_RELU) {
                     unsigned bits = 0;
-                    unsigned *mslot = mbits + (size_t)op.slot * 4 * 128;
                     for (int c16 = 0; c16 < op.n; c16 += 16) {
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c16, v);
@@ -188,13 +289,18 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const __grid_constant__
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             *plane_ptr(pA, (c16 >> 2) + c, r) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                        if ((c16 & 16) || c16 + 16 >= op.n) { mslot[(c16 >> 5) * 128 + r] = bits; bits = 0; }
+                        if ((c16 & 16) || c16 + 16 >= op.n) {
+                            if (op.slot >= 0) mbits[((size_t)op.slot * 8 + (c16 >> 5)) * 128 + r] = bits;
+                            if (op.mglobal) op.mglobal[((size_t)tile * words + (c16 >> 5)) * 128 + r] = bits;
+                            bits = 0;
+                        }
                     }
                 } else if (op.epi == EPI_MASK) {
                     unsigned bits = 0;
-                    const unsigned *mslot = mbits + (size_t)op.slot * 4 * 128;
                     for (int c16 = 0; c16 < op.n; c16 += 16) {
-                        if ((c16 & 16) == 0) bits = mslot[(c16 >> 5) * 128 + r];
+                        if ((c16 & 16) == 0)
+                            bits = op.mglobal ? op.mglobal[((size_t)tile * words + (c16 >> 5)) * 128 + r]
+                                              : mbits[((size_t)op.slot * 8 + (c16 >> 5)) * 128 + r];
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c16, v);
 #pragma unroll
@@ -203,6 +309,53 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const __grid_constant__
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             *plane_ptr(pA, (c16 >> 2) + c, r) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    }
+                } else if (op.epi == EPI_STORE) {
+                    unsigned bits = 0;
+                    for (int c16 = 0; c16 < op.n; c16 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(tl + (uint32_t)c16, v);
+                        if (op.relu) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                v[i] = fmaxf(v[i] + __ldg(op.bias + c16 + i), 0.f);
+                                bits |= (v[i] > 0.f ? 1u : 0u) << ((c16 & 16) + i);
+                            }
+                        }
+                        if (valid) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                tv_st(op.out, row, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                        }
+                        if (op.mglobal && ((c16 & 16) || c16 + 16 >= op.n)) {
+                            op.mglobal[((size_t)tile * words + (c16 >> 5)) * 128 + r] = bits;
+                            bits = 0;
+                        }
+                    }
+                } else if (op.epi == EPI_MAXPOOL) {
+                    const long long g = row / K;
+                    for (int c16 = 0; c16 < op.n; c16 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(tl + (uint32_t)c16, v);
+                        unsigned am[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const unsigned b = __float_as_uint(fmaxf(v[i] + __ldg(op.bias + c16 + i), 0.f));
+                            const unsigned mx = __reduce_max_sync(gmask, b);
+                            am[i] = __reduce_min_sync(gmask, b == mx ? (unsigned)k : 64u);
+                            v[i] = __uint_as_float(mx);
+                        }
+                        if (k == 0 && valid) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                tv_st(op.out, g, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                            uint4 pk;
+                            pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+                            pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+                            pk.z = am[8] | (am[9] << 8) | (am[10] << 16) | (am[11] << 24);
+                            pk.w = am[12] | (am[13] << 8) | (am[14] << 16) | (am[15] << 24);
+                            *reinterpret_cast<uint4 *>(op.arg + g * op.argC + op.arg0 + c16) = pk;
+                        }
                     }
                 } else if (op.epi == EPI_HEAD) {
                     float v[16], dz[16];
@@ -234,92 +387,232 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const __grid_constant__
                             *plane_ptr(pA, c, r) = q;
                         }
                     }
-                } else {   // EPI_STORE
-                    for (int c16 = 0; c16 < op.n; c16 += 16) {
-                        float v[16];
-                        tc::tmem_ld16(tl + (uint32_t)c16, v);
-                        if (valid) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                tv_st(a.dI, row, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
-                        }
-                    }
                 }
-                tc::fence_before_sync();
-                if (o + 1 < a.nops) {
-                    tc::fence_async_smem();
-                    tc::mbar_arrive(b_in);
-                }
+                // EPI_NONE: the accumulator is continued by the next op
             }
+            tc::fence_before_sync();
         }
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == NG * 4) tc::tmem_dealloc(tmem, NG * 128);
+    if (warp == NG * 4) tc::tmem_dealloc(tmem, ncols);
 }
 
 int g_sms = 0;
+constexpr size_t kSmemMax = 225 * 1024;
 
-}  // namespace
+inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
-// One description of a chain: forward layers (folded conv + bias + ReLU), head layer (bias only),
-// and -- when `backward` -- the same layers' dgrad weights in reverse.
-int psg_chain_fused(const PsgChain &c, cudaStream_t st)
+struct Builder {
+    TileArgs a;
+    int amax_cols = 0;    // widest A operand (columns)
+    int nmax = 0;         // widest accumulator
+    bool ok = true;
+    Builder() { memset(&a, 0, sizeof(a)); }
+    TileOp *add(const float *w, int wstride, int wrow0, int wplane0, int n, int planes, int aplane0)
+    {
+        if (a.nops >= kMaxOps || n % 16 || n < 16 || n > 256 || planes % 2 || planes < 2) { ok = false; return &a.ops[0]; }
+        TileOp &o = a.ops[a.nops++];
+        memset(&o, 0, sizeof(o));
+        o.w = w; o.wstride = wstride; o.wrow0 = wrow0; o.wplane0 = wplane0; o.n = n; o.planes = planes; o.aplane0 = aplane0;
+        o.slot = -1;
+        if ((aplane0 + planes) * 4 > amax_cols) amax_cols = (aplane0 + planes) * 4;
+        if (n > nmax) nmax = n;
+        return &o;
+    }
+    void want_a(int cols) { if (cols > amax_cols) amax_cols = cols; }
+};
+
+// choose NG / stage size to fit shared memory, fill the derived fields, launch
+int launch_program(Builder &b, long long rows, cudaStream_t st)
 {
-    if (c.nlayers < 1 || c.nlayers > 4 || c.kin % 16 || c.kin > 128 || c.ncls > kPsgMaxCls) return PSG_EUNSUPPORTED;
-    ChainArgs a;
-    int no = 0;
-    int kprev = c.kin;
-    for (int j = 0; j < c.nlayers; ++j) {          // hidden layers: bias + ReLU, bits saved in slot j
-        if (c.n[j] % 16 || c.n[j] > 128 || c.nwf[j] != c.n[j]) return PSG_EUNSUPPORTED;
-        ChainOp &o = a.ops[no++];
-        o.w = c.wf[j]; o.bias = c.bias[j]; o.planes = kprev / 4; o.n = c.n[j];
-        o.nstages = (o.planes * o.n * 16 + kStageBytes - 1) / kStageBytes; o.epi = EPI_RELU_SAVE; o.slot = j;
-        if (o.planes % (2 * o.nstages)) return PSG_EUNSUPPORTED;
-        kprev = c.n[j];
+    if (!b.ok || b.a.nops < 1) return PSG_EUNSUPPORTED;
+    TileArgs &a = b.a;
+    a.rows = rows; a.ntiles = (int)((rows + 127) / 128);
+    a.abytes = b.amax_cols * 512;
+    a.tcols = (int)pow2cols(b.nmax);
+    auto need = [&](int ng, int stg) {
+        return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * kMaskSlots * 8 * 128 * 4 + 1024;
+    };
+    // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
+    int ng = (a.ntiles >= 2 * 148 && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
+    int stage = need(ng, 32 * 1024) <= kSmemMax ? 32 * 1024 : 16 * 1024;
+    if (need(ng, stage) > kSmemMax || a.tcols * ng > 512) return PSG_EUNSUPPORTED;
+    a.stage_bytes = stage;
+    for (int o = 0; o < a.nops; ++o) {
+        TileOp &op = a.ops[o];
+        int pps = stage / (op.n * 16);
+        pps &= ~1;
+        if (pps < 2) return PSG_EUNSUPPORTED;
+        op.pps = pps < op.planes ? pps : op.planes;
     }
-    {                                               // head: N = packed width (zero-padded columns)
-        if (c.head_nwf > 128 || c.head_nwf % 16) return PSG_EUNSUPPORTED;
-        ChainOp &o = a.ops[no++];
-        o.w = c.head_wf; o.bias = c.head_bias; o.planes = kprev / 4; o.n = c.head_nwf;
-        o.nstages = (o.planes * o.n * 16 + kStageBytes - 1) / kStageBytes; o.epi = EPI_HEAD; o.slot = 0;
-        if (o.planes % (2 * o.nstages)) return PSG_EUNSUPPORTED;
-    }
-    if (c.backward) {
-        {                                           // d hidden_last = dz * W_head, masked by the last hidden layer's bits
-            if (c.head_nwb != kprev) return PSG_EUNSUPPORTED;
-            ChainOp &o = a.ops[no++];
-            o.w = c.head_wb; o.bias = nullptr; o.planes = 16 / 4; o.n = kprev; o.nstages = 1; o.epi = EPI_MASK;
-            o.slot = c.nlayers - 1;
-        }
-        for (int j = c.nlayers - 1; j >= 0; --j) {
-            const int nin = j > 0 ? c.n[j - 1] : c.kin;
-            if (c.nwb[j] != nin) return PSG_EUNSUPPORTED;
-            ChainOp &o = a.ops[no++];
-            o.w = c.wb[j]; o.bias = nullptr; o.planes = c.n[j] / 4; o.n = nin;
-            o.nstages = (o.planes * o.n * 16 + kStageBytes - 1) / kStageBytes;
-            if (o.planes % (2 * o.nstages)) return PSG_EUNSUPPORTED;
-            o.epi = j > 0 ? EPI_MASK : EPI_STORE; o.slot = j - 1;
-        }
-    }
-    a.nops = no;
-    a.src = c.src; a.S = c.S; a.nn_idx = c.nn_idx; a.nn_w = c.nn_w; a.Nf = c.Nf; a.kin = c.kin;
-    a.rows = c.rows; a.ntiles = (int)((c.rows + 127) / 128);
-    a.backward = c.backward; a.ncls = c.ncls; a.loss_kind = c.loss_kind; a.target = c.target; a.labels = c.labels;
-    a.scale = c.scale; a.kappa = c.kappa; a.dlogp = c.dlogp; a.loss_rows = c.loss_rows; a.hit = c.hit;
-    a.zout = c.zout; a.dI = c.dI;
-    const size_t smem = (size_t)NG * kABytes + (size_t)kStages * kStageBytes + (size_t)NG * kMaskSlots * 4 * 128 * 4 + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
+    const size_t smem = (size_t)ng * a.abytes + (size_t)kStages * stage + (size_t)ng * kMaskSlots * 8 * 128 * 4 + 1024;
+    if (g_sms == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
             return PSG_ECUDA;
-        attr_done = true;
+        if (cudaFuncSetAttribute(tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess ||
+            cudaFuncSetAttribute(tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
+            return PSG_ECUDA;
     }
-    const int want = (a.ntiles + NG - 1) / NG;
+    const int want = (a.ntiles + ng - 1) / ng;
     const int grid = want < g_sms ? want : g_sms;
-    chain_kernel<<<grid, kThreads, smem, st>>>(a);
+    if (ng == 2) tile_kernel<2><<<grid, 2 * 128 + 64, smem, st>>>(a);
+    else tile_kernel<1><<<grid, 128 + 64, smem, st>>>(a);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
+}
+
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// fp1 + head (forward [+ loss + backward])
+// -------------------------------------------------------------------------------------------------
+int psg_chain_fused(const PsgChain &c, cudaStream_t st)
+{
+    if (c.nlayers < 1 || c.nlayers > kMaskSlots || c.kin % 16 || c.kin > 256 || c.ncls > kPsgMaxCls) return PSG_EUNSUPPORTED;
+    Builder b;
+    int kprev = c.kin;
+    for (int j = 0; j < c.nlayers; ++j) {          // hidden layers: bias + ReLU, bits kept in shared-memory slot j
+        if (c.n[j] > 256) return PSG_EUNSUPPORTED;
+        TileOp *o = b.add(c.wf[j], c.nwf[j], 0, 0, c.n[j], kprev / 4, 0);
+        o->epi = EPI_RELU; o->bias = c.bias[j]; o->slot = j;
+        if (j == 0) o->pre = PRE_FP;
+        kprev = c.n[j];
+    }
+    {                                               // head: N = 16 logits columns (zero-padded classes)
+        TileOp *o = b.add(c.head_wf, c.head_nwf, 0, 0, 16, kprev / 4, 0);
+        o->epi = EPI_HEAD; o->bias = c.head_bias;
+    }
+    if (c.backward) {
+        {                                           // d hidden_last = dz W_head, masked by the last hidden layer's bits
+            TileOp *o = b.add(c.head_wb, c.head_nwb, 0, 0, kprev, 16 / 4, 0);
+            o->epi = EPI_MASK; o->slot = c.nlayers - 1;
+        }
+        for (int j = c.nlayers - 1; j >= 0; --j) {
+            const int nin = j > 0 ? c.n[j - 1] : c.kin;
+            TileOp *o = b.add(c.wb[j], c.nwb[j], 0, 0, nin, c.n[j] / 4, 0);
+            if (j > 0) { o->epi = EPI_MASK; o->slot = j - 1; }
+            else { o->epi = EPI_STORE; o->out = c.dI; }
+        }
+    }
+    TileArgs &a = b.a;
+    a.src.isrc = c.src; a.src.iS = c.S; a.src.iNf = c.Nf; a.src.icols = c.kin; a.src.iplane0 = 0;
+    a.src.nn_idx = c.nn_idx; a.src.nn_w = c.nn_w; a.src.lcols = 0;
+    a.backward = c.backward; a.ncls = c.ncls; a.loss_kind = c.loss_kind; a.target = c.target; a.labels = c.labels;
+    a.scale = c.scale; a.kappa = c.kappa; a.dlogp = c.dlogp; a.loss_rows = c.loss_rows; a.hit = c.hit;
+    a.zout = c.zout;
+    return launch_program(b, c.rows, st);
+}
+
+// -------------------------------------------------------------------------------------------------
+// wide set-abstraction level (weights streamed)
+// -------------------------------------------------------------------------------------------------
+bool psg_sa_streamable(int K, int gpad, int n0, int n1, int n2)
+{
+    if (K != 16 && K != 32) return false;
+    if (gpad % 16 || n0 % 32 || n1 % 32 || n2 % 16) return false;     // hidden widths: whole mask words
+    if (gpad > 288 || n0 > 256 || n1 > 256 || n2 > 512) return false;
+    return true;
+}
+
+int psg_sa_stream_fwd(const PsgSaFused &f, cudaStream_t st)
+{
+    Builder b;
+    TileOp *o = b.add(f.wf[0], f.nwf[0], 0, 0, f.n[0], f.gpad / 4, 0);
+    o->pre = PRE_GROUP; o->epi = EPI_RELU; o->bias = f.bias[0]; o->mglobal = f.m0;
+    o = b.add(f.wf[1], f.nwf[1], 0, 0, f.n[1], f.n[0] / 4, 0);
+    o->epi = EPI_RELU; o->bias = f.bias[1]; o->mglobal = f.m1;
+    for (int c0 = 0; c0 < f.n[2]; c0 += 256) {
+        const int n = f.n[2] - c0 < 256 ? f.n[2] - c0 : 256;
+        o = b.add(f.wf[2], f.nwf[2], c0, 0, n, f.n[1] / 4, 0);
+        o->epi = EPI_MAXPOOL; o->bias = f.bias[2] + c0;
+        o->out = f.out; o->out.c0 += c0 / 4;
+        o->arg = f.arg; o->argC = f.n[2]; o->arg0 = c0;
+    }
+    TileSrc &s = b.a.src;
+    s.feats = f.feats; s.D = f.D; s.gpad = f.gpad; s.xyz = f.xyz; s.cloud_stride = f.cloud_stride; s.nclouds = f.nclouds;
+    s.Nsrc = f.Nsrc; s.new_xyz = f.new_xyz; s.idx = f.idx; s.S = f.S; s.K = f.K;
+    return launch_program(b, f.rows, st);
+}
+
+int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st)
+{
+    Builder b;
+    TileOp *o = nullptr;
+    // dY1 = dY2 W2, contraction over n2 in <= 256-column slabs (the scatter refills the A buffer per slab)
+    for (int c0 = 0; c0 < f.n[2]; c0 += 256) {
+        const int kc = f.n[2] - c0 < 256 ? f.n[2] - c0 : 256;
+        o = b.add(f.wb[2], f.nwb[2], 0, c0 / 4, f.n[1], kc / 4, 0);
+        o->pre = PRE_SCATTER; o->pre_a = c0; o->accumulate = c0 > 0 ? 1 : 0; o->epi = EPI_NONE;
+    }
+    o->epi = EPI_MASK; o->mglobal = f.m1;
+    o = b.add(f.wb[1], f.nwb[1], 0, 0, f.n[0], f.n[1] / 4, 0);
+    o->epi = EPI_MASK; o->mglobal = f.m0;
+    for (int c0 = 0; c0 < gcols; c0 += 256) {
+        const int n = gcols - c0 < 256 ? gcols - c0 : 256;
+        o = b.add(f.wb[0], f.nwb[0], c0, 0, n, f.n[0] / 4, 0);
+        o->epi = EPI_STORE; o->out = dG; o->out.c0 += c0 / 4;
+    }
+    TileSrc &s = b.a.src;
+    s.K = f.K; s.dout = dout; s.outv = f.out; s.sarg = f.arg; s.sargC = f.n[2];
+    return launch_program(b, f.rows, st);
+}
+
+// -------------------------------------------------------------------------------------------------
+// feature-propagation level (weights streamed)
+// -------------------------------------------------------------------------------------------------
+bool psg_fp_streamable(const PsgFpStream &f, bool forward)
+{
+    if (f.nl < 1 || f.nl > 3 || f.C1 % 16 || f.C2 % 16) return false;
+    for (int j = 0; j < f.nl; ++j)
+        if (f.n[j] % 32 || f.n[j] > 256) return false;
+    if (forward) return (size_t)(f.C1 + f.C2) * 512 + 2 * 16 * 1024 + kMaskSlots * 8 * 128 * 4 + 1024 <= kSmemMax;
+    return true;
+}
+
+// [skip | interp] -> nl x (conv + folded BN + ReLU); last layer stored (it is the next level's
+// interpolation source and its ReLU mask), hidden layers leave their ReLU bits in `m[j]`
+int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st)
+{
+    Builder b;
+    int kprev = f.C1 + f.C2;
+    for (int j = 0; j < f.nl; ++j) {
+        TileOp *o = b.add(f.wf[j], f.nwf[j], 0, 0, f.n[j], kprev / 4, 0);
+        o->bias = f.bias[j];
+        if (j == 0) o->pre = PRE_FP;
+        if (j + 1 < f.nl) { o->epi = EPI_RELU; o->mglobal = f.m[j]; }
+        else { o->epi = EPI_STORE; o->relu = 1; o->out = f.y_last; }
+        kprev = f.n[j];
+    }
+    TileSrc &s = b.a.src;
+    s.lsrc = f.skip; s.lcols = f.C1;
+    s.isrc = f.coarse; s.iS = f.S; s.iNf = f.Nf; s.icols = f.C2; s.iplane0 = f.C1 / 4; s.nn_idx = f.nn_idx; s.nn_w = f.nn_w;
+    return launch_program(b, f.rows, st);
+}
+
+// dY_last (pre-activation gradient, already masked) -> dgrad chain -> d[skip | interp] stored to dcat
+int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStream_t st)
+{
+    Builder b;
+    for (int j = f.nl - 1; j >= 0; --j) {
+        const int nin = j > 0 ? f.n[j - 1] : f.C1 + f.C2;
+        if (j > 0) {
+            TileOp *o = b.add(f.wb[j], f.nwb[j], 0, 0, nin, f.n[j] / 4, 0);
+            o->epi = EPI_MASK; o->mglobal = f.m[j - 1];
+            if (j == f.nl - 1) o->pre = PRE_LOAD;
+        } else {
+            for (int c0 = 0; c0 < nin; c0 += 256) {
+                const int n = nin - c0 < 256 ? nin - c0 : 256;
+                TileOp *o = b.add(f.wb[0], f.nwb[0], c0, 0, n, f.n[0] / 4, 0);
+                o->epi = EPI_STORE; o->out = dcat; o->out.c0 += c0 / 4;
+                if (f.nl == 1 && c0 == 0) o->pre = PRE_LOAD;
+            }
+        }
+    }
+    TileSrc &s = b.a.src;
+    s.lsrc = dy_last; s.lcols = f.n[f.nl - 1];
+    b.want_a(f.n[f.nl - 1]);
+    return launch_program(b, f.rows, st);
 }

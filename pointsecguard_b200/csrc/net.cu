@@ -208,6 +208,7 @@ struct Branch {
     unsigned char *arg;
     int *ball;             // [T*B][S][K]
     bool fused;            // tcgen05 mode runs the branch as one kernel per direction (sa_fused.cu)
+    bool streamed;         // ... or, for wide layers, as a tile program with streamed weights (chain_fused.cu)
     unsigned *m0, *m1;     // ReLU bits of layers 0 / 1 (fused path)
     int *csr_off, *csr_perm;   // [T*B][R+1], [T*B][S*K]
 };
@@ -226,6 +227,8 @@ struct FpLevel {
     int *nn_idx;           // [T*B][Nf][3]
     float *nn_w;           // [T*B][Nf][3]
     int *csr_off, *csr_perm;   // [T*B][Nc+1], [T*B][Nf*3]
+    bool streamed;         // tcgen05 mode: forward and backward run as tile programs (chain_fused.cu)
+    unsigned *m[3];        // ReLU bits of the hidden layers (streamed path)
 };
 
 }  // namespace
@@ -355,6 +358,8 @@ extern "C" int psg_net_set_mlp_mode(psg_net *n, int mode)
     return PSG_OK;
 }
 
+static PsgFpStream fp_stream_desc(psg_net *n, int f, int t, TView coarse);
+
 // carve (or, with base == null, only size) the workspace
 static size_t plan(psg_net *n, int B, int N, int T, char *base)
 {
@@ -390,8 +395,10 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
             }
             Br.arg = bp.take<unsigned char>((size_t)B * S * Br.mlp[Br.nl - 1]->npad);
             Br.fused = Br.nl == 3 && psg_sa_fusable(Br.K, Br.gpad, Br.mlp[0]->npad, Br.mlp[1]->npad, Br.mlp[2]->npad);
+            Br.streamed = !Br.fused && Br.nl == 3 &&
+                          psg_sa_streamable(Br.K, Br.gpad, Br.mlp[0]->npad, Br.mlp[1]->npad, Br.mlp[2]->npad);
             Br.m0 = Br.m1 = nullptr;
-            if (Br.fused) {
+            if (Br.fused || Br.streamed) {
                 Br.m0 = bp.take<unsigned>(psg_sa_mask_words(rows, Br.mlp[0]->npad));
                 Br.m1 = bp.take<unsigned>(psg_sa_mask_words(rows, Br.mlp[1]->npad));
             }
@@ -416,6 +423,14 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
             if ((size_t)F.mlp[j]->npad > wmax) wmax = F.mlp[j]->npad;
         }
         if (f == 0 && (size_t)n->conv1->npad > wmax) wmax = n->conv1->npad;
+        F.streamed = false;
+        for (int j = 0; j < 3; ++j) F.m[j] = nullptr;
+        if (f > 0) {
+            PsgFpStream q = fp_stream_desc(n, f, 0, TView{nullptr, 0, 0});
+            F.streamed = psg_fp_streamable(q, true) && psg_fp_streamable(q, false);
+            if (F.streamed)
+                for (int j = 0; j + 1 < F.nl; ++j) F.m[j] = bp.take<unsigned>(psg_sa_mask_words(rows, F.mlp[j]->npad));
+        }
         size_t s = (size_t)round_up_ll(rows, 128) * wmax;
         if (s > scratch) scratch = s;
     }
@@ -535,6 +550,26 @@ static PsgSaFused sa_fused_desc(psg_net *n, int l, int b, int t)
     return f;
 }
 
+// feature-propagation level f >= 1 (fine level f, coarse level f + 1) as a tile program
+static PsgFpStream fp_stream_desc(psg_net *n, int f, int t, TView coarse)
+{
+    FpLevel &F = n->fp[f];
+    const int B = n->B, Nf = n->npts[f], Nc = n->npts[f + 1];
+    PsgFpStream q;
+    memset(&q, 0, sizeof(q));
+    q.skip = tv(n->feats[f], n->wfeat[f]); q.C1 = F.C1;
+    q.coarse = coarse; q.C2 = F.C2; q.S = Nc; q.Nf = Nf; q.rows = (long long)B * Nf;
+    q.nn_idx = F.nn_idx + (size_t)t * B * Nf * 3; q.nn_w = F.nn_w + (size_t)t * B * Nf * 3;
+    q.nl = F.nl;
+    for (int j = 0; j < F.nl; ++j) {
+        const psg_mlp *m = F.mlp[j];
+        q.n[j] = m->npad; q.wf[j] = m->wf; q.nwf[j] = m->nwf; q.bias[j] = m->bias; q.wb[j] = m->wb; q.nwb[j] = m->nwb;
+        q.m[j] = F.m[j];
+    }
+    q.y_last = tv(F.Y[F.nl - 1], F.mlp[F.nl - 1]->npad);
+    return q;
+}
+
 // fp1 (+ conv1 as one more hidden layer) + conv2 head, interpolating from `coarse` (fp2's output)
 static PsgChain head_chain_desc(psg_net *n, int t, TView coarse)
 {
@@ -567,9 +602,9 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
         for (int b = 0; b < L.nbr; ++b) {
             Branch &Br = L.br[b];
             const long long rows = (long long)B * S * Br.K;
-            if (mode == 1 && Br.fused) {
+            if (mode == 1 && (Br.fused || Br.streamed)) {
                 PsgSaFused f = sa_fused_desc(n, l, b, t);
-                PSG_RUN(PF_GEMM_FWD, psg_sa_fused_fwd(f, st));
+                PSG_RUN(PF_GEMM_FWD, Br.fused ? psg_sa_fused_fwd(f, st) : psg_sa_stream_fwd(f, st));
                 continue;
             }
             PSG_RUN(PF_GROUP, psg_group(tv(n->feats[l - 1], n->wfeat[l - 1]), D, lvl_xyz(n, l - 1, t), (long long)R * 3, B, R,
@@ -605,6 +640,12 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
                 n->z_valid = true;
             }
             break;
+        }
+        if (mode == 1 && F.streamed) {
+            PsgFpStream q = fp_stream_desc(n, f, t, tv(up, upw));
+            PSG_RUN(PF_GEMM_FWD, psg_fp_stream_fwd(q, st));
+            up = F.Y[F.nl - 1]; upw = F.mlp[F.nl - 1]->npad;
+            continue;
         }
         PSG_RUN(PF_INTERP, psg_interp(tv(up, upw), Nc, F.nn_idx + (size_t)t * B * Nf * 3, F.nn_w + (size_t)t * B * Nf * 3, B, Nf,
                            F.C2 / 4, tv(F.I, F.C2), st));
@@ -706,6 +747,10 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             c.loss_rows = n->loss.loss_rows; c.hit = n->loss.hit;
             c.dI = tv(n->S[0], F.C2);
             PSG_RUN(PF_GEMM_BWD, psg_chain_fused(c, st));
+        } else if (f > 0 && n->mode == 1 && F.streamed) {
+            PsgFpStream q = fp_stream_desc(n, f, t, TView{nullptr, 0, 0});
+            cat_buf = top_buf == 0 ? 1 : 0;
+            PSG_RUN(PF_GEMM_BWD, psg_fp_stream_bwd(q, top, tv(n->S[cat_buf], F.C1 + F.C2), st));
         } else
         PSG_TRY(chain_bwd(n, mlps, Ys, nl, rows, top, top_buf, &cat_buf, st));
         const int catw = F.C1 + F.C2;
@@ -734,10 +779,11 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             Branch &Br = L.br[b];
             const long long rows = (long long)B * S * Br.K;
             const int cw = Br.mlp[Br.nl - 1]->npad;
-            if (n->mode == 1 && Br.fused) {
+            if (n->mode == 1 && (Br.fused || Br.streamed)) {
                 PsgSaFused f = sa_fused_desc(n, l, b, t);
                 const int gcols = round_up(D, 16);       // feature columns only: xyz gets no gradient on this path
-                PSG_RUN(PF_GEMM_BWD, psg_sa_fused_bwd(f, tv(n->dfeat[l], n->wfeat[l], Br.col0), tv(n->S[0], Br.gpad), gcols, st));
+                TView dl = tv(n->dfeat[l], n->wfeat[l], Br.col0), dg = tv(n->S[0], Br.gpad);
+                PSG_RUN(PF_GEMM_BWD, Br.fused ? psg_sa_fused_bwd(f, dl, dg, gcols, st) : psg_sa_stream_bwd(f, dl, dg, gcols, st));
                 const size_t go = (size_t)t * B;
                 const int M = S * Br.K;
                 PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[0], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,

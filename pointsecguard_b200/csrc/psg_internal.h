@@ -81,6 +81,20 @@ struct PsgChain {
     TView zout, dI;
 };
 int psg_chain_fused(const PsgChain &c, cudaStream_t st);
+// set-abstraction branch with streamed weights (widths beyond what sa_fused.cu keeps resident)
+bool psg_sa_streamable(int K, int gpad, int n0, int n1, int n2);
+int psg_sa_stream_fwd(const PsgSaFused &f, cudaStream_t st);
+int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st);
+// feature-propagation level: [skip | 3-NN interpolation] -> MLP, forward and dgrad chain
+struct PsgFpStream {
+    TView skip; int C1; TView coarse; int C2, S, Nf; const int *nn_idx; const float *nn_w; long long rows;
+    int nl; int n[3]; const float *wf[3]; int nwf[3]; const float *bias[3]; const float *wb[3]; int nwb[3];
+    unsigned *m[3];                    // ReLU bits of the hidden layers
+    TView y_last;                      // output of the last layer (stored: next level's interpolation source)
+};
+bool psg_fp_streamable(const PsgFpStream &f, bool forward);
+int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st);
+int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStream_t st);
 // elementwise.cu
 int psg_head_logsoftmax(TView z, long long rows, int ncls, float *logp, cudaStream_t st);
 int psg_dz_from_dlogp(TView z, const float *dlogp, long long rows, int ncls, TView dz, cudaStream_t st);
