@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
 }
 
 int g_sms = 0;
+inline int g_sms_hint() { return g_sms > 0 ? g_sms : 148; }
 constexpr size_t kSmemMax = 225 * 1024;
 
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
@@ -435,7 +436,7 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
         return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * kMaskSlots * 8 * 128 * 4 + 1024;
     };
     // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
-    int ng = (a.ntiles >= 2 * 148 && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
+    int ng = (a.ntiles > g_sms_hint() && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
     int stage = need(ng, 32 * 1024) <= kSmemMax ? 32 * 1024 : 16 * 1024;
     if (need(ng, stage) > kSmemMax || a.tcols * ng > 512) return PSG_EUNSUPPORTED;
     a.stage_bytes = stage;

@@ -178,7 +178,7 @@ int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P,
     if (N <= 2048) return launch_fps<512, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     // many problems in flight (attack geometry batches): fewer, fatter threads -- the per-round warp
     // overhead (REDUX, barrier, exchange) is amortised over 16 points and 4 CTAs share an SM
-    if (N <= 4096 && N > 2048 && P >= 256)
+    if (N <= 4096 && N > 2048 && P >= 128)
         return launch_fps<256, 16, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 4096) return launch_fps<1024, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 16384) return launch_fps<1024, 16, 1>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);

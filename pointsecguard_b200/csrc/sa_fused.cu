@@ -100,14 +100,16 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
     const uint32_t sbase = (s0 + 1023u) & ~1023u;
     unsigned char *base = smem_raw + (sbase - s0);
     const int szW0 = a.gpad * a.n0 * 4, szW1 = a.n0 * a.n1 * 4, szW2 = (a.n1 * a.n2 * 4 + 1023) & ~1023;
-    const int szA = max(a.gpad, a.n1) * 512, szG = szA + a.n0 * 512;   // per group: [A / Y1 | Y0]
+    // per tile ONE operand buffer: a layer's MMA has completed before its epilogue runs, so the
+    // epilogue overwrites the layer's own input in place (gather -> Y0 -> Y1)
+    const int szG = max(a.gpad, max(a.n0, a.n1)) * 512;
     unsigned char *pW0 = base, *pW1 = pW0 + szW0, *pW2 = pW1 + szW1, *pG = pW2 + szW2;
     const uint32_t sW0 = sbase, sW1 = sW0 + szW0, sW2 = sW1 + szW1, sG = sW2 + szW2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nmax = max(a.n0, max(a.n1, a.n2));
     const uint32_t gcols = tc::next_pow2_cols(nmax);       // TMEM columns per group
-    const uint32_t ncols = gcols * NG;
+    const uint32_t ncols = tc::next_pow2_cols((int)(gcols * NG));   // tcgen05.alloc takes powers of two
 
     load_weights(pW0, a.w0, a.gpad / 4, a.n0, a.nw0);
     load_weights(pW1, a.w1, a.n0 / 4, a.n1, a.nw1);
@@ -141,12 +143,12 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
             while (nact) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    if (!act[g] || !tc::mbar_try_wait(tc::smem_u32(&bar_in[g]), ph[g])) continue;
+                    if (!act[g] || !tc::mbar_test_wait(tc::smem_u32(&bar_in[g]), ph[g])) continue;
                     ph[g] ^= 1u;
                     tc::fence_after_sync();
-                    const uint32_t sA = sG + g * szG, sY0 = sA + szA, tm = tmem + g * gcols;
+                    const uint32_t sA = sG + g * szG, tm = tmem + g * gcols;
                     if (layer[g] == 0) issue_layer(tm, sA, sW0, a.gpad / 4, a.n0);
-                    else if (layer[g] == 1) issue_layer(tm, sY0, sW1, a.n0 / 4, a.n1);
+                    else if (layer[g] == 1) issue_layer(tm, sA, sW1, a.n0 / 4, a.n1);
                     else issue_layer(tm, sA, sW2, a.n1 / 4, a.n2);
                     tc::mma_commit(tc::smem_u32(&bar_acc[g]));
                     if (++layer[g] == 3) {
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
     } else {
         const int grp = warp >> 2, wq = warp & 3;
         const int r = threadIdx.x & 127;                 // tile row = TMEM lane
-        unsigned char *pA = pG + (size_t)grp * szG, *pY0 = pA + szA;
+        unsigned char *pA = pG + (size_t)grp * szG, *pY0 = pA;
         const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
         const uint32_t tl = tmem + grp * gcols + ((uint32_t)(wq * 32) << 16);
         const int k = r % K;
@@ -294,15 +296,15 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
     unsigned char *base = smem_raw + (sbase - s0);
     // dgrad weights of layer l: planes = cout_l / 4, rows = cin_l
     const int szW2 = a.n2 * a.n1 * 4, szW1 = a.n1 * a.n0 * 4, szW0 = (a.n0 * a.gpad * 4 + 1023) & ~1023;
-    // per group one buffer: dY2 [n2 cols]; then dY1 overwrites its first n1 columns and dY0 the next n0
-    const int szG = max(a.n2, a.n1 + a.n0) * 512;
+    // per tile ONE operand buffer, overwritten in place: dY2 -> dY1 -> dY0
+    const int szG = max(a.n2, max(a.n1, a.n0)) * 512;
     unsigned char *pW2 = base, *pW1 = pW2 + szW2, *pW0 = pW1 + szW1, *pG = pW0 + szW0;
     const uint32_t sW2 = sbase, sW1 = sW2 + szW2, sW0 = sW1 + szW1, sG = sW0 + szW0;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nmax = max(a.n0, max(a.n1, a.gpad));
     const uint32_t gcols = tc::next_pow2_cols(nmax);
-    const uint32_t ncols = gcols * NG;
+    const uint32_t ncols = tc::next_pow2_cols((int)(gcols * NG));   // tcgen05.alloc takes powers of two
 
     load_weights(pW2, a.wb2, a.n2 / 4, a.n1, a.nwb2);
     load_weights(pW1, a.wb1, a.n1 / 4, a.n0, a.nwb1);
@@ -335,10 +337,10 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
             while (nact) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    if (!act[g] || !tc::mbar_try_wait(tc::smem_u32(&bar_in[g]), ph[g])) continue;
+                    if (!act[g] || !tc::mbar_test_wait(tc::smem_u32(&bar_in[g]), ph[g])) continue;
                     ph[g] ^= 1u;
                     tc::fence_after_sync();
-                    const uint32_t sD2 = sG + g * szG, sD1 = sD2, sD0 = sD2 + a.n1 * 512, tm = tmem + g * gcols;
+                    const uint32_t sD2 = sG + g * szG, sD1 = sD2, sD0 = sD2, tm = tmem + g * gcols;
                     if (layer[g] == 0) issue_layer(tm, sD2, sW2, a.n2 / 4, a.n1);        // dY1 = dY2 W2
                     else if (layer[g] == 1) issue_layer(tm, sD1, sW1, a.n1 / 4, a.n0);   // dY0 = dY1 W1
                     else issue_layer(tm, sD0, sW0, a.n0 / 4, a.gpad);                   // dG  = dY0 W0
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
     } else {
         const int grp = warp >> 2, wq = warp & 3;
         const int r = threadIdx.x & 127;
-        unsigned char *pD2 = pG + (size_t)grp * szG, *pD1 = pD2, *pD0 = pD2 + (size_t)a.n1 * 512;
+        unsigned char *pD2 = pG + (size_t)grp * szG, *pD1 = pD2, *pD0 = pD2;
         const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
         const uint32_t tl = tmem + grp * gcols + ((uint32_t)(wq * 32) << 16);
         const int k = r % K;
@@ -411,15 +413,16 @@ constexpr size_t kSmemBudget = 226 * 1024;     // per SM, minus what the runtime
 constexpr size_t kSmemPerCtaMax = 224 * 1024;
 
 inline size_t r1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
+inline int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 inline size_t fwd_smem(int gpad, int n0, int n1, int n2, int ng)
 {
     return (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4) +
-           (size_t)ng * ((size_t)(gpad > n1 ? gpad : n1) + n0) * 512 + 1024;
+           (size_t)ng * (size_t)max3(gpad, n0, n1) * 512 + 1024;
 }
 inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng)
 {
     return (size_t)n2 * n1 * 4 + (size_t)n1 * n0 * 4 + r1k((size_t)n0 * gpad * 4) +
-           (size_t)ng * (size_t)(n2 > n1 + n0 ? n2 : n1 + n0) * 512 + 1024;
+           (size_t)ng * (size_t)max3(n2, n1, n0) * 512 + 1024;
 }
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
@@ -462,6 +465,21 @@ size_t psg_sa_mask_words(long long rows, int n)
     return (size_t)((rows + 127) / 128) * ((n + 31) / 32) * 128;
 }
 
+// tiles in flight per SM = NG (per CTA, sharing the resident weights) x CTAs per SM: take the
+// combination that keeps the most tiles in flight (the per-tile chain is latency-bound)
+template <class F>
+int pick_ng(F smem_of, int gc)
+{
+    int best = 1, best_tiles = 0;
+    for (int ng = 1; ng <= 4; ++ng) {
+        const size_t sm = smem_of(ng);
+        if (sm > kSmemPerCtaMax || ng * gc > 512) break;
+        const int tiles = ng * ctas_per_sm(sm, (int)pow2cols(ng * gc));
+        if (tiles > best_tiles) { best_tiles = tiles; best = ng; }
+    }
+    return best;
+}
+
 #define SA_LAUNCH(KERN, KK, NGG, ARGS, SMEM, COLS)                                         \
     do {                                                                                   \
         int grid__ = 0, rc__;                                                              \
@@ -480,14 +498,13 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     a.m0 = f.m0; a.m1 = f.m1; a.out = f.out; a.arg = f.arg;
     a.ntiles = (int)((f.rows + 127) / 128);
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.n2 ? a.n0 : a.n2) : (a.n1 > a.n2 ? a.n1 : a.n2));
-    // two tiles in flight per CTA (they share the resident weights) when shared memory allows
-    const int ng = fwd_smem(a.gpad, a.n0, a.n1, a.n2, 2) <= kSmemPerCtaMax ? 2 : 1;
+    const int ng = pick_ng([&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g); }, gc);
     const size_t smem = fwd_smem(a.gpad, a.n0, a.n1, a.n2, ng);
-    if (f.K == 32 && ng == 2) SA_LAUNCH(sa_fwd_kernel, 32, 2, a, smem, gc * 2);
-    else if (f.K == 32) SA_LAUNCH(sa_fwd_kernel, 32, 1, a, smem, gc);
-    else if (f.K == 16 && ng == 2) SA_LAUNCH(sa_fwd_kernel, 16, 2, a, smem, gc * 2);
-    else if (f.K == 16) SA_LAUNCH(sa_fwd_kernel, 16, 1, a, smem, gc);
-    else return PSG_EUNSUPPORTED;
+    if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
+#define SA_FWD_CASE(KK, NGG) if (f.K == KK && ng == NGG) SA_LAUNCH(sa_fwd_kernel, KK, NGG, a, smem, (int)pow2cols(gc * NGG))
+    SA_FWD_CASE(32, 1); SA_FWD_CASE(32, 2); SA_FWD_CASE(32, 3); SA_FWD_CASE(32, 4);
+    SA_FWD_CASE(16, 1); SA_FWD_CASE(16, 2); SA_FWD_CASE(16, 3); SA_FWD_CASE(16, 4);
+#undef SA_FWD_CASE
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
@@ -501,13 +518,13 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaS
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.gpad ? a.n0 : a.gpad) : (a.n1 > a.gpad ? a.n1 : a.gpad));
-    const int ng = bwd_smem(a.gpad, a.n0, a.n1, a.n2, 2) <= kSmemPerCtaMax ? 2 : 1;
+    const int ng = pick_ng([&](int g) { return bwd_smem(a.gpad, a.n0, a.n1, a.n2, g); }, gc);
     const size_t smem = bwd_smem(a.gpad, a.n0, a.n1, a.n2, ng);
-    if (f.K == 32 && ng == 2) SA_LAUNCH(sa_bwd_kernel, 32, 2, a, smem, gc * 2);
-    else if (f.K == 32) SA_LAUNCH(sa_bwd_kernel, 32, 1, a, smem, gc);
-    else if (f.K == 16 && ng == 2) SA_LAUNCH(sa_bwd_kernel, 16, 2, a, smem, gc * 2);
-    else if (f.K == 16) SA_LAUNCH(sa_bwd_kernel, 16, 1, a, smem, gc);
-    else return PSG_EUNSUPPORTED;
+    if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
+#define SA_BWD_CASE(KK, NGG) if (f.K == KK && ng == NGG) SA_LAUNCH(sa_bwd_kernel, KK, NGG, a, smem, (int)pow2cols(gc * NGG))
+    SA_BWD_CASE(32, 1); SA_BWD_CASE(32, 2); SA_BWD_CASE(32, 3); SA_BWD_CASE(32, 4);
+    SA_BWD_CASE(16, 1); SA_BWD_CASE(16, 2); SA_BWD_CASE(16, 3); SA_BWD_CASE(16, 4);
+#undef SA_BWD_CASE
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

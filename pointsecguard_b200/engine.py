@@ -83,6 +83,7 @@ class Engine:
         self._ws = None
         self.mlp_mode = mlp_mode
         self.shard = None           # distributed.Shard when the bound batch is a slice of a global batch
+        self._stream_handle = None
 
     def _fill(self, m: L.MlpDesc, w: np.ndarray, b: np.ndarray):
         w = np.ascontiguousarray(w, dtype=np.float32)
@@ -115,9 +116,14 @@ class Engine:
         L.psg_net_bind(self._net, B, N, T, base, need)
         self.B, self.N, self.T = B, N, T
 
-    @staticmethod
-    def _stream():
-        return torch.cuda.current_stream().cuda_stream
+    def _stream(self):
+        """Stream the C library enqueues on: the one set with ``use_stream`` (sub-batch pipelining,
+        torchattacks/attacks/nontarget.py) or torch's current stream."""
+        return self._stream_handle if self._stream_handle is not None else torch.cuda.current_stream().cuda_stream
+
+    def use_stream(self, stream):
+        """Pin this engine to a torch.cuda.Stream (None = follow torch's current stream)."""
+        self._stream_handle = stream.cuda_stream if stream is not None else None
 
     def draw_starts(self, T: int) -> torch.Tensor:
         """FPS start indices for T forwards, drawn on the global CPU generator in the reference's

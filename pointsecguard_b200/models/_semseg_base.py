@@ -46,11 +46,16 @@ class SemSegBase(nn.Module):
     arch = "ssg"
     mlp_mode = MLP_FP32
 
+    # number of independent sub-batches an attack pipelines over CUDA streams ("auto": by batch size)
+    sub_batches = "auto"
+
     def _init_runtime(self):
         self._engine = None
         self._engine_key = None
         self._generation = 0
         self._shard = None
+        self._sub_engines = []
+        self._sub_streams = []
 
     def set_shard(self, shard):
         """Multi-GPU runs: declare that the batches this replica sees are ``shard``
@@ -76,12 +81,32 @@ class SemSegBase(nn.Module):
             self._engine = Engine(self.describe(), device, self.mlp_mode)
             self._engine_key = key
             self._engine.set_shard(self._shard)
+            self._sub_engines = []
         return self._engine
+
+    def sub_engines(self, device, count: int):
+        """``count`` engines (same folded weights, own workspace) with one CUDA stream each.  The
+        attacks split a batch into independent sub-batches and enqueue them round-robin: the deep
+        levels of the network are latency-bound chains of small launches, and blocks are independent
+        in every op of the path, so sub-batches overlap on the GPU."""
+        primary = self.engine(device)
+        if count <= 1:
+            return [primary], [None]
+        while len(self._sub_engines) < count - 1:
+            self._sub_engines.append(Engine(self.describe(), primary.device, self.mlp_mode))
+        while len(self._sub_streams) < count:
+            self._sub_streams.append(torch.cuda.Stream(primary.device))
+        engs = [primary] + self._sub_engines[: count - 1]
+        for e in engs:
+            e.set_mlp_mode(self.mlp_mode)
+        return engs, self._sub_streams[:count]
 
     def set_mlp_mode(self, mode: int):
         self.mlp_mode = mode
         if self._engine is not None:
             self._engine.set_mlp_mode(mode)
+            for e in self._sub_engines:
+                e.set_mlp_mode(mode)
             self._engine_key = self._param_key(self._engine.device)
 
     def _sa_desc(self, sa):

@@ -25,24 +25,64 @@ class NB_attack(Attack):
         return _nb_loop(self, images, labels, target=-1, mask=None)
 
 
+def _sub_batches(model, B):
+    import os
+    want = os.environ.get("PSG_SUBBATCH") or getattr(model, "sub_batches", "auto")
+    if want == "auto":
+        want = 4 if B >= 16 else (2 if B >= 4 else 1)
+    return max(1, min(int(want), B))
+
+
 def _nb_loop(atk, images, labels, target, mask):
+    from pointsecguard_b200 import distributed as D
     eng = atk._engine(images)
+    dev = images.device
     B, C, N = images.shape
     adv = images.detach().clone(memory_format=torch.contiguous_format)
     ori = images.detach()[:, 3:6].contiguous()
-    lab = atk._labels_i32(labels, images.device) if target < 0 else None
-    msk = atk._mask_u8(mask, B, N, images.device) if mask is not None else None
+    src = images.detach()
+    lab = atk._labels_i32(labels, dev) if target < 0 else None
+    msk = atk._mask_u8(mask, B, N, dev) if mask is not None else None
     # nontarget.py:34: sum-CE / N;  target.py:38: mean CE over the B*N points
     scale = 1.0 / N if target < 0 else 1.0 / (B * N)
+    # Blocks are independent in every op of the path: split the batch into sub-batches, one engine and
+    # one CUDA stream each, and enqueue their steps round-robin so the latency-bound deep levels of
+    # one sub-batch overlap the others.  FPS starts are drawn ONCE for the whole batch (the
+    # reference's draw, pointnet_util.py:75) and sliced.
+    nsub = _sub_batches(atk.model, B)
+    engs, streams = atk.model.sub_engines(dev, nsub)
+    whole = eng.shard if eng.shard is not None else D.Shard(B, 0, B)
+    parts = [D.shard_for(B, i, nsub) for i in range(nsub)]
     chunk = max(1, min(atk.iters, _MAX_PROBLEMS // B))
-    eng.bind(B, N, chunk)
-    eng.set_input(images.detach())
-    done = 0
-    while done < atk.iters:
-        t = min(chunk, atk.iters - done)
-        eng.geometry(eng.draw_starts(t))
-        eng.nb_attack(adv, ori, msk, lab, target, t, 0, atk.alpha, atk.eps, scale)
-        done += t
+    cur = torch.cuda.current_stream()
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    for e, st_, p in zip(engs, streams, parts):
+        e.use_stream(st_)
+        if st_ is not None:
+            st_.wait_event(fork)
+        e.bind(p.size, N, chunk)
+        e.set_input(p.slice(src))
+    sizes = [N] + eng.npoints[:3]
+    try:
+        done = 0
+        while done < atk.iters:
+            t = min(chunk, atk.iters - done)
+            starts = D.draw_starts(sizes, t, whole)                       # int32 [4, t, B]
+            for e, p in zip(engs, parts):
+                e.geometry(p.slice(starts.permute(2, 0, 1)).permute(1, 2, 0).contiguous())
+            for i in range(t):
+                for e, p in zip(engs, parts):
+                    e.nb_attack(p.slice(adv), p.slice(ori), p.slice(msk) if msk is not None else None,
+                                p.slice(lab) if lab is not None else None, target, 1, i, atk.alpha, atk.eps, scale)
+            done += t
+    finally:
+        for e, st_ in zip(engs, streams):
+            if st_ is not None:
+                join = torch.cuda.Event()
+                join.record(st_)
+                cur.wait_event(join)
+            e.use_stream(None)
     atk.model._generation += 1
     return adv
 
