@@ -128,7 +128,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    sps, cores, sample, dt = cpu_reference(min(steps, 8), args.warmup)
+    sps, cores, sample, dt = cpu_reference(min(steps, 24), args.warmup, sample_blocks=4)
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak",
@@ -144,45 +144,60 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
+def _flops_rows_chain(widths):
+    """forward FLOPs per row of a conv chain [c0 -> c1 -> ...]"""
+    return sum(2 * a * b for a, b in zip(widths[:-1], widths[1:]))
+
+
 def run_native(args, rank, world, local_rank):
+    import ctypes as C
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from pointsecguard_b200 import _lib as L
+    from pointsecguard_b200 import distributed as D
     from pointsecguard_b200 import synthetic as syn, torchattacks
     from pointsecguard_b200 import metrics as MT
+    from pointsecguard_b200.engine import MLP_TF32
     from pointsecguard_b200.models.pointnet2_sem_seg import get_model
 
     model = get_model(13)
     model.load_state_dict(syn.make_state_dict("ssg"))
     model = model.to(dev).eval()
     if args.mlp == "tf32":
-        from pointsecguard_b200.engine import MLP_TF32
         model.set_mlp_mode(MLP_TF32)
-    x_host, labels, mask = make_inputs(B_PER_GPU, seed=rank)      # every rank attacks its own blocks
+    # weak scaling: a global batch of 16 blocks per GPU; every rank builds the same global batch from
+    # the seed, keeps its contiguous slice, and draws FPS starts for the GLOBAL batch (sliced), so an
+    # N-GPU run attacks exactly the blocks a 1-GPU run of the same global batch would, with the same draws
+    shard = D.shard_for(B_PER_GPU * world, rank, world)
+    model.set_shard(shard if world > 1 else None)
+    x_all, labels_all, mask_all = make_inputs(B_PER_GPU * world, seed=0)
+    x_host, labels, mask = shard.slice(x_all), shard.slice(labels_all), shard.slice(mask_all)
     x_pin = x_host.contiguous().pin_memory()                      # [B,9,N] contiguous pinned host copy
     x_dev = x_host.to(dev)
     lab_np = labels.numpy().astype(np.float64)
     K, W = args.steps, args.warmup
-    atk = torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=K, target=TARGET, mask=mask)
+    mk = lambda iters: torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=iters, target=TARGET, mask=mask)
+    atk = mk(K)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up: W untimed steps (also builds the engine and its workspace)
+    # warm-up: W untimed steps, then one untimed attack at the timed geometry-chunk size
     if W > 0:
-        torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=W, target=TARGET, mask=mask)(x_dev, lab_np)
-    model.engine(dev).bind(B_PER_GPU, N_POINTS, min(K, max(1, 1024 // B_PER_GPU)))
-    torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=1, target=TARGET, mask=mask)(x_dev, lab_np)
+        mk(W)(x_dev, lab_np)
+    mk(min(K, 64))(x_dev, lab_np)
 
     # ---- device-resident timing: exactly K steps ----
     clocks = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.manual_seed(0)
+    flush.fill_(1)
     barrier()
     clocks.start()
     l0 = L.psg_launch_count()
@@ -200,6 +215,7 @@ def run_native(args, rank, world, local_rank):
 
     # ---- end to end through the public API from pinned host memory, result read back ----
     torch.manual_seed(0)
+    flush.fill_(2)
     barrier()
     t0 = time.perf_counter()
     e0.record()
@@ -221,18 +237,16 @@ def run_native(args, rank, world, local_rank):
     torch.manual_seed(1)
     logp_adv, _ = model(adv)
     counters = MT.attack_counters(logp_adv, labels.to(dev), mask.to(dev), TARGET)
-    if world > 1:
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    D.all_reduce_sum_(counters)
     summary = MT.summarize(counters.cpu(), 13)
 
     line = None
     if rank == 0:
         # ---- live per-kernel-family timing (CUDA event pairs on the launching stream) ----
-        import ctypes as C
         L.psg_prof_enable(1)
         kp = min(K, 10)
         torch.manual_seed(0)
-        torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=kp, target=TARGET, mask=mask)(x_dev, lab_np)
+        mk(kp)(x_dev, lab_np)
         ncat = L.psg_prof_ncat()
         msb = (C.c_double * ncat)()
         cnt = (C.c_int64 * ncat)()
@@ -241,24 +255,49 @@ def run_native(args, rank, world, local_rank):
         fam = {L.psg_prof_name(i).decode(): {"ms_per_step": msb[i] / kp, "launches_per_step": cnt[i] / kp}
                for i in range(ncat) if cnt[i]}
         pk = peaks()
-        gemm_ms = fam.get("gemm_fwd", {}).get("ms_per_step", 0) + fam.get("gemm_bwd", {}).get("ms_per_step", 0)
-        gemm_launches = fam.get("gemm_fwd", {}).get("launches_per_step", 0) + fam.get("gemm_bwd", {}).get("launches_per_step", 0)
-        flops_step = FLOPS_PER_BLOCK_STEP * B_PER_GPU
-        ach = flops_step / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         # fp32 CUDA-core MLPs have no tensor peak; the TF32 tcgen05 peak is half the measured bf16 one
         peak = pk["bf16_tflops_sustained"] / 2.0
-        roofline = {
-            "bound": "tensor", "kernel": "shared-MLP GEMMs (forward + dgrad, all layers)",
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-            "peak_source": f"{pk['source']} bf16 sustained / 2 (TF32 dense rate)", "traffic": None,
-            "launches_per_step": gemm_launches, "ms_per_step": gemm_ms, "mlp_mode": args.mlp,
-            "fps_ms_per_step": fam.get("fps", {}).get("ms_per_step"),
-        }
+        rows0 = B_PER_GPU * N_POINTS
+        # dominant kernel: fp1 + head forward + backward (chain_fused.cu), one launch per step:
+        # 2 x (128->128->128->128 fp1, 128->128 conv1, 128->13 conv2) FLOPs per point
+        chain_flops = 2 * _flops_rows_chain([128, 128, 128, 128, 128, 13]) * rows0
+        if "head_chain" in fam:
+            dom = fam["head_chain"]
+            dur_ms = dom["ms_per_step"] / max(dom["launches_per_step"], 1)
+            ach = chain_flops / (dur_ms / 1e3) / 1e12
+            roofline = {
+                "bound": "tensor", "kernel": "chain_kernel: fp1 + conv1 + conv2 forward, loss gradient, dgrad chain (1 launch/step)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": f"{pk['source']} bf16 sustained / 2 (TF32 dense rate)",
+                "flops_per_launch": chain_flops, "ms_per_launch": dur_ms,
+                "traffic": _ncu_traffic("chain_kernel"),
+            }
+        else:
+            g = fam.get("gemm_fwd", {}).get("ms_per_step", 0) + fam.get("gemm_bwd", {}).get("ms_per_step", 0)
+            ach = FLOPS_PER_BLOCK_STEP * B_PER_GPU / (g / 1e3) / 1e12 if g else 0.0
+            roofline = {"bound": "tensor", "kernel": "fp32 CUDA-core GEMMs (all layers, parity mode)", "achieved": ach,
+                        "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": f"{pk['source']} bf16 sustained / 2 (TF32 dense rate)"}
+        mlp_ms = sum(fam.get(k, {}).get("ms_per_step", 0) for k in
+                     ("gemm_fwd", "gemm_bwd", "sa_fused_fwd", "sa_fused_bwd", "fp_fused_fwd", "fp_fused_bwd", "head_chain"))
+        roofline["all_mlp_kernels"] = {
+            "ms_per_step": mlp_ms, "tflops": FLOPS_PER_BLOCK_STEP * B_PER_GPU / (mlp_ms / 1e3) / 1e12 if mlp_ms else None,
+            "frac": FLOPS_PER_BLOCK_STEP * B_PER_GPU / (mlp_ms / 1e3) / 1e12 / peak if mlp_ms else None}
+        roofline["mlp_mode"] = args.mlp
+        # HBM-side primitives (SURVEY.md 8d byte formulas, all four levels), achieved GB/s vs measured copy bandwidth
+        npts = [N_POINTS, 1024, 256, 64, 16]
+        byt = {"fps": sum(12 * npts[l] + 8 * npts[l + 1] for l in range(4)),
+               "ball_query": sum(12 * npts[l] + 12 * npts[l + 1] + 8 * npts[l + 1] * 32 for l in range(4)),
+               "three_nn": sum(12 * npts[l] + 12 * npts[l + 1] + 36 * npts[l] for l in range(4))}
+        roofline["primitives_hbm"] = {
+            k: {"GBps": byt[k] * B_PER_GPU / (fam[k]["ms_per_step"] / 1e3) / 1e9,
+                "frac_of_hbm": byt[k] * B_PER_GPU / (fam[k]["ms_per_step"] / 1e3) / 1e9 / pk["hbm_gbs"]}
+            for k in byt if k in fam}
         # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
         if args.no_cpu:
             cpu = None
         else:
-            sps, cores, sample, _ = cpu_reference(3, 1)
+            sps, cores, sample, _ = cpu_reference(12, 1, sample_blocks=4)
             cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -268,7 +307,10 @@ def run_native(args, rank, world, local_rank):
                                    "alpha=0.1 target=7, mask=z-band class 11), B=16x4096 per GPU, random-init weights, "
                                    "synthetic S3DIS-shaped blocks",
                        "blocks_per_gpu": B_PER_GPU, "points": N_POINTS, "mlp": args.mlp,
-                       "l2": "per-step working set (~1 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+                       "tolerance": "fp32: logits rtol 1e-3; tf32: |dlogp| < 5e-3, grad rel < 8e-2, sign agreement > 99 % "
+                                    "(tests/test_gpu_gemm.py), FPS / ball-query / 3-NN indices bit-exact in both modes",
+                       "l2": "256 MB buffer written before each timed attack (L2 flush); steps inside an attack run "
+                             "back to back as in the reference loop"},
             "block_steps_per_s": value * B_PER_GPU,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "wall_s": wall, "identical_to_resident_run": same_as_resident},
@@ -286,13 +328,22 @@ def run_native(args, rank, world, local_rank):
     return line
 
 
+def _ncu_traffic(kernel):
+    """dram bytes (read + write) per launch of `kernel` from the committed ncu --set full summary, or None."""
+    try:
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--mlp", default=os.environ.get("PSG_MLP", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--mlp", default=os.environ.get("PSG_MLP", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

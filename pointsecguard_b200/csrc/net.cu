@@ -29,10 +29,12 @@ long long g_psg_launch_count = 0;
 // and sums the elapsed times per family.  Off by default (zero overhead, graph-capture safe).
 // ------------------------------------------------------------------------------------------------
 enum { PF_FPS, PF_BALL, PF_NN3, PF_CSR, PF_PACK, PF_GROUP, PF_GEMM_FWD, PF_MAXPOOL, PF_INTERP, PF_HEAD, PF_LOSS,
-       PF_GEMM_BWD, PF_MAXPOOL_BWD, PF_SEGSUM, PF_COPY, PF_PGD, PF_NCAT };
+       PF_GEMM_BWD, PF_MAXPOOL_BWD, PF_SEGSUM, PF_COPY, PF_PGD, PF_SA_FWD, PF_SA_BWD, PF_FP_FWD, PF_FP_BWD, PF_HEAD_CHAIN,
+       PF_NCAT };
 static const char *kProfNames[PF_NCAT] = {"fps", "ball_query", "three_nn", "csr_build", "pack", "group", "gemm_fwd",
                                           "maxpool", "interp", "head", "loss_grad", "gemm_bwd", "maxpool_bwd", "segsum",
-                                          "copy_cols", "pgd_update"};
+                                          "copy_cols", "pgd_update", "sa_fused_fwd", "sa_fused_bwd", "fp_fused_fwd",
+                                          "fp_fused_bwd", "head_chain"};
 namespace {
 struct ProfRec { cudaEvent_t a, b; int cat; };
 bool g_prof_on = false;
@@ -604,7 +606,7 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
             const long long rows = (long long)B * S * Br.K;
             if (mode == 1 && (Br.fused || Br.streamed)) {
                 PsgSaFused f = sa_fused_desc(n, l, b, t);
-                PSG_RUN(PF_GEMM_FWD, Br.fused ? psg_sa_fused_fwd(f, st) : psg_sa_stream_fwd(f, st));
+                PSG_RUN(PF_SA_FWD, Br.fused ? psg_sa_fused_fwd(f, st) : psg_sa_stream_fwd(f, st));
                 continue;
             }
             PSG_RUN(PF_GROUP, psg_group(tv(n->feats[l - 1], n->wfeat[l - 1]), D, lvl_xyz(n, l - 1, t), (long long)R * 3, B, R,
@@ -636,14 +638,14 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
             if (logp) {
                 PsgChain c = head_chain_desc(n, t, tv(up, upw));
                 c.backward = 0; c.zout = tv(n->Z, n->conv2->npad);
-                PSG_RUN(PF_GEMM_FWD, psg_chain_fused(c, st));
+                PSG_RUN(PF_HEAD_CHAIN, psg_chain_fused(c, st));
                 n->z_valid = true;
             }
             break;
         }
         if (mode == 1 && F.streamed) {
             PsgFpStream q = fp_stream_desc(n, f, t, tv(up, upw));
-            PSG_RUN(PF_GEMM_FWD, psg_fp_stream_fwd(q, st));
+            PSG_RUN(PF_FP_FWD, psg_fp_stream_fwd(q, st));
             up = F.Y[F.nl - 1]; upw = F.mlp[F.nl - 1]->npad;
             continue;
         }
@@ -746,11 +748,11 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             c.scale = n->loss.scale; c.kappa = n->loss.kappa; c.dlogp = n->loss.dlogp;
             c.loss_rows = n->loss.loss_rows; c.hit = n->loss.hit;
             c.dI = tv(n->S[0], F.C2);
-            PSG_RUN(PF_GEMM_BWD, psg_chain_fused(c, st));
+            PSG_RUN(PF_HEAD_CHAIN, psg_chain_fused(c, st));
         } else if (f > 0 && n->mode == 1 && F.streamed) {
             PsgFpStream q = fp_stream_desc(n, f, t, TView{nullptr, 0, 0});
             cat_buf = top_buf == 0 ? 1 : 0;
-            PSG_RUN(PF_GEMM_BWD, psg_fp_stream_bwd(q, top, tv(n->S[cat_buf], F.C1 + F.C2), st));
+            PSG_RUN(PF_FP_BWD, psg_fp_stream_bwd(q, top, tv(n->S[cat_buf], F.C1 + F.C2), st));
         } else
         PSG_TRY(chain_bwd(n, mlps, Ys, nl, rows, top, top_buf, &cat_buf, st));
         const int catw = F.C1 + F.C2;
@@ -783,7 +785,7 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
                 PsgSaFused f = sa_fused_desc(n, l, b, t);
                 const int gcols = round_up(D, 16);       // feature columns only: xyz gets no gradient on this path
                 TView dl = tv(n->dfeat[l], n->wfeat[l], Br.col0), dg = tv(n->S[0], Br.gpad);
-                PSG_RUN(PF_GEMM_BWD, Br.fused ? psg_sa_fused_bwd(f, dl, dg, gcols, st) : psg_sa_stream_bwd(f, dl, dg, gcols, st));
+                PSG_RUN(PF_SA_BWD, Br.fused ? psg_sa_fused_bwd(f, dl, dg, gcols, st) : psg_sa_stream_bwd(f, dl, dg, gcols, st));
                 const size_t go = (size_t)t * B;
                 const int M = S * Br.K;
                 PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[0], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,
