@@ -144,3 +144,46 @@ def test_attack_is_deterministic():
         torch.manual_seed(7)
         outs.append(torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=3)(x, lab))
     assert torch.equal(outs[0], outs[1])            # no float atomics anywhere on the path
+
+
+def test_sharded_attack_equals_full_batch_attack():
+    """Two 'ranks' (run one after the other on this GPU) that each attack their shard of a global batch
+    -- FPS starts drawn for the GLOBAL batch and sliced (distributed.py) -- reproduce the full-batch
+    attack block for block, bit for bit, and their summed counters equal the full-batch counters."""
+    from pointsecguard_b200 import distributed as D, metrics as MT, torchattacks
+    m = _model("ssg")
+    G = 4
+    x = syn.make_blocks(G, 2048, 5).cuda()
+    lab_t = syn.zband_labels(x.cpu())
+    lab = lab_t.numpy().astype(np.float64)
+    torch.manual_seed(3)
+    full = torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=3)(x, lab)
+    torch.manual_seed(4)
+    c_full = MT.attack_counters(m(full)[0], lab_t.cuda())
+    parts, counters = [], torch.zeros_like(c_full)
+    for r in range(2):
+        sh = D.shard_for(G, r, 2)
+        m.set_shard(sh)
+        torch.manual_seed(3)
+        adv = torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=3)(sh.slice(x), sh.slice(lab))
+        torch.manual_seed(4)
+        counters += MT.attack_counters(m(adv)[0], sh.slice(lab_t).cuda())
+        parts.append(adv)
+    m.set_shard(None)
+    assert torch.equal(torch.cat(parts), full)
+    assert torch.equal(counters, c_full)
+
+
+def test_sub_batch_pipelining_is_exact():
+    """Splitting a batch into sub-batches on separate CUDA streams (model.sub_batches) changes nothing."""
+    from pointsecguard_b200 import torchattacks
+    m = _model("ssg")
+    x = syn.make_blocks(4, 2048, 6).cuda()
+    lab = syn.zband_labels(x.cpu()).numpy().astype(np.float64)
+    outs = []
+    for nsub in (1, 2, 4):
+        m.sub_batches = nsub
+        torch.manual_seed(8)
+        outs.append(torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=3)(x, lab))
+    m.sub_batches = "auto"
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
