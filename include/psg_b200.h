@@ -166,6 +166,12 @@ typedef struct {
     float *cost;                  /* [>= number of steps] cost history (target.py:95) */
     int32_t *status;              /* [4] */
     float *scratch;               /* psg_nu_scratch_floats(B, N) floats */
+    /* attack field: channels [field_c0, field_c0 + field_nc) move, channel j inside the tanh-space box
+     * [box_lo[j], box_hi[j]].  field_nc == 0 selects the reference's field: colours 3:6 in [0,1]
+     * (nontarget.py:54).  A field that includes coordinates (c0 < 3) is an extension of the reference
+     * (BASELINE.json configs[2]); w / adam_m / adam_v are then [B, field_nc, N]. */
+    int field_c0, field_nc;
+    float box_lo[8], box_hi[8];
 } psg_nu_buffers;
 size_t psg_nu_scratch_floats(int B, int N);
 /* w = atanh(2 colour - 1) (:57, :111-117), Adam moments and status zeroed */
@@ -176,7 +182,13 @@ int psg_nu_init(psg_net *net, const psg_nu_buffers *buf, psg_stream_t stream);
  * (exit_above = 0) or > thr (exit_above = 1), hits counted over all or only the masked points. */
 int psg_nu_step(psg_net *net, const psg_nu_buffers *buf, int t, int step, int target, int neighbour, float c,
                 float kappa, float targeted_sign, float step_size, float bc2_sqrt, int reset_adam, double acc_denom,
-                double thr, int exit_above, int count_masked_only, psg_stream_t stream);
+                double thr, int exit_above, int count_masked_only, const int32_t *starts, psg_stream_t stream);
+/* `starts` (device int32 [4][B], or null): when the field moves coordinates the geometry of forward
+ * slot t is rebuilt from the step's image with these FPS start indices before the forward pass. */
+
+/* Also produce d cost / d xyz through the grouping and the interpolation weights (autograd of
+ * pointnet_util.py:126-132, :301-308); it is added to input channels 0:3 of the feature gradient. */
+int psg_net_set_xyz_grad(psg_net *net, int on);
 /* x = clamp(x, lo, hi) elementwise (target.py:132 clamps all nine channels) */
 int psg_clamp(float *x, int64_t count, float lo, float hi, psg_stream_t stream);
 

@@ -96,18 +96,28 @@ def _smooth(adv, images, k):
 
 
 def nu_attack(model, images, labels, c=1e-4, kappa=0, steps=1000, lr=0.01, early_exit=True,
-              return_trace=False):
-    """nontarget.py:52-106."""
+              return_trace=False, field=slice(3, 6), box=None):
+    """nontarget.py:52-106.  ``field`` / ``box`` generalise the colour slice of the reference (3:6 in
+    [0,1]) to other channels inside a per-channel tanh-space box [lo, hi]; nothing else changes."""
     images = images.clone().detach()
     y = _labels(labels)
-    w = _atanh_space(images[:, 3:6].clone()).detach().requires_grad_(True)
+    if box is None:
+        w0 = _atanh_space(images[:, field].clone())
+        lo = hi = None
+    else:
+        lo = torch.tensor(box[0], dtype=images.dtype).view(1, -1, 1)
+        hi = torch.tensor(box[1], dtype=images.dtype).view(1, -1, 1)
+        w0 = _atanh_space((images[:, field].clone() - lo) / (hi - lo))
+    w = w0.detach().requires_grad_(True)
     best = images.clone()
     opt = torch.optim.Adam([w], lr=lr)
     trace = []
     for step in range(steps):
         col = 0.5 * (torch.tanh(w) + 1)
+        if box is not None:
+            col = lo + (hi - lo) * col
         adv = best.clone().detach()
-        adv[:, 3:6] = col
+        adv[:, field] = col
         l2 = ((adv - images) ** 2).flatten(1).sum(1).sum()
         logp, _ = model(adv)
         f = _cw_f(logp, y, kappa).sum()

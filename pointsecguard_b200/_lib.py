@@ -42,7 +42,8 @@ class NetDesc(C.Structure):
 class NuBuffers(C.Structure):
     _fields_ = [("w", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("adv", C.c_void_p),
                 ("base", C.c_void_p), ("images", C.c_void_p), ("mask", C.c_void_p), ("labels", C.c_void_p),
-                ("cost", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p)]
+                ("cost", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p),
+                ("field_c0", C.c_int), ("field_nc", C.c_int), ("box_lo", C.c_float * 8), ("box_hi", C.c_float * 8)]
 
 
 _vp, _i, _i64, _f, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_double
@@ -84,7 +85,8 @@ _PROTOS = {
     "psg_nb_attack": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp]),
     "psg_nu_scratch_floats": (_sz, [_i, _i]),
     "psg_nu_init": (_i, [_vp, C.POINTER(NuBuffers), _vp]),
-    "psg_nu_step": (_i, [_vp, C.POINTER(NuBuffers), _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _d, _d, _i, _i, _vp]),
+    "psg_nu_step": (_i, [_vp, C.POINTER(NuBuffers), _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _d, _d, _i, _i, _vp, _vp]),
+    "psg_net_set_xyz_grad": (_i, [_vp, _i]),
     "psg_clamp": (_i, [_vp, _i64, _f, _f, _vp]),
     "psg_prof_enable": (_i, [_i]),
     "psg_prof_ncat": (_i, []),

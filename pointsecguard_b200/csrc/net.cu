@@ -256,6 +256,9 @@ struct psg_net {
     int last_t;
     // tcgen05 mode: fp1 + head run as one forward+backward kernel (chain_fused.cu); the loss is then
     // evaluated inside psg_net_backward from this deferred specification
+    bool xyz_grad;         // also produce the geometric gradient w.r.t. coordinates (geomgrad.cu)
+    float *dxyz[5];        // [B][npts[l]][3]
+    float *xyz_tmp;        // [B][N*3][3] coarse-side vectors of the interpolation backward
     bool head_fused;
     bool z_valid;          // logits of the last forward are materialised in Z
     struct { int kind, target; const float *dlogp; const int *labels; float scale, kappa; float *loss_rows;
@@ -362,6 +365,13 @@ extern "C" int psg_net_set_mlp_mode(psg_net *n, int mode)
 
 static PsgFpStream fp_stream_desc(psg_net *n, int f, int t, TView coarse);
 
+extern "C" int psg_net_set_xyz_grad(psg_net *n, int on)
+{
+    if (!n) return PSG_EINVAL;
+    n->xyz_grad = on != 0;
+    return PSG_OK;
+}
+
 // carve (or, with base == null, only size) the workspace
 static size_t plan(psg_net *n, int B, int N, int T, char *base)
 {
@@ -442,6 +452,8 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
         size_t s = (size_t)round_up_ll((long long)B * n->npts[l], 128) * n->wfeat[l];
         if (s > scratch) scratch = s;
     }
+    for (int l = 0; l <= 4; ++l) n->dxyz[l] = bp.take<float>((size_t)B * n->npts[l] * 3);
+    n->xyz_tmp = bp.take<float>((size_t)B * N * 9);
     n->H = bp.tl((long long)B * N, n->conv1->npad);
     n->Z = bp.tl((long long)B * N, n->conv2->npad);
     n->dZ = bp.tl((long long)B * N, n->conv2->npad);
@@ -729,6 +741,9 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
     if (!n || !n->bound || t < 0 || t >= n->T || t != n->last_t) return PSG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int B = n->B;
+    if (n->xyz_grad)
+        for (int l = 0; l <= 4; ++l)
+            if (cudaMemsetAsync(n->dxyz[l], 0, (size_t)B * n->npts[l] * 3 * sizeof(float), st) != cudaSuccess) return PSG_ECUDA;
     // ---- head + feature propagation, fine to coarse ----
     TView top = tv(n->dZ, n->conv2->npad);
     int top_buf = -1;
@@ -759,6 +774,15 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
         if (F.C1) PSG_RUN(PF_COPY, psg_copy_cols(tv(n->S[cat_buf], catw), tv(n->dfeat[f], n->wfeat[f]), rows, F.C1, 0, st));
         // interpolation backward: scatter the three weighted copies to the coarse level, in CSR order
         const size_t go = (size_t)t * B;
+        if (n->xyz_grad) {
+            // d cost / d coordinates through the inverse-distance weights (pointnet_util.py:301-308)
+            float *coarse = f < 3 ? n->fp[f + 1].Y[n->fp[f + 1].nl - 1] : n->feats[4];
+            const int cw2 = f < 3 ? n->fp[f + 1].mlp[n->fp[f + 1].nl - 1]->npad : n->wfeat[4];
+            PSG_RUN(PF_SEGSUM, psg_fp_xyz_backward(tv(n->S[cat_buf], catw, F.C1), tv(coarse, cw2), F.C2, lvl_xyz(n, f, t),
+                                                   (long long)Nf * 3, B, lvl_xyz(n, f + 1, t), Nc, F.nn_idx + go * Nf * 3,
+                                                   F.csr_off + go * (Nc + 1), F.csr_perm + go * Nf * 3, B, Nf, n->dxyz[f],
+                                                   n->dxyz[f + 1], n->xyz_tmp, st));
+        }
         if (f < 3) {
             FpLevel &C = n->fp[f + 1];
             const int cw = C.mlp[C.nl - 1]->npad;
@@ -783,13 +807,17 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             const int cw = Br.mlp[Br.nl - 1]->npad;
             if (n->mode == 1 && (Br.fused || Br.streamed)) {
                 PsgSaFused f = sa_fused_desc(n, l, b, t);
-                const int gcols = round_up(D, 16);       // feature columns only: xyz gets no gradient on this path
+                // feature columns only, unless the coordinate gradient is wanted too
+                const int gcols = n->xyz_grad ? Br.gpad : round_up(D, 16);
                 TView dl = tv(n->dfeat[l], n->wfeat[l], Br.col0), dg = tv(n->S[0], Br.gpad);
                 PSG_RUN(PF_SA_BWD, Br.fused ? psg_sa_fused_bwd(f, dl, dg, gcols, st) : psg_sa_stream_bwd(f, dl, dg, gcols, st));
                 const size_t go = (size_t)t * B;
                 const int M = S * Br.K;
                 PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[0], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,
                                    B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, st));
+                if (n->xyz_grad)
+                    PSG_RUN(PF_SEGSUM, psg_sa_xyz_backward(tv(n->S[0], Br.gpad), D, Br.K, S, B, Br.csr_off + go * (R + 1),
+                                                           Br.csr_perm + go * M, R, n->dxyz[l - 1], n->dxyz[l], st));
                 continue;
             }
             TView dy = tv(n->S[0], cw);
@@ -801,8 +829,15 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             const int M = S * Br.K;
             PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[gbuf], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,
                                B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, st));
+            if (n->xyz_grad)
+                PSG_RUN(PF_SEGSUM, psg_sa_xyz_backward(tv(n->S[gbuf], Br.gpad), D, Br.K, S, B, Br.csr_off + go * (R + 1),
+                                                       Br.csr_perm + go * M, R, n->dxyz[l - 1], n->dxyz[l], st));
         }
+        // xyz_l = xyz_{l-1}[fps_idx]: everything that reached the centroids' coordinates flows to their source points
+        if (n->xyz_grad)
+            PSG_RUN(PF_SEGSUM, psg_fps_xyz_backward(n->dxyz[l], n->fps_idx[l] + (size_t)t * B * S, S, R, B, n->dxyz[l - 1], st));
     }
+    if (n->xyz_grad) PSG_RUN(PF_SEGSUM, psg_add_xyz_to_feat(n->dxyz[0], (long long)B * n->N, tv(n->dfeat[0], n->wfeat[0]), st));
     if (grad_x) PSG_RUN(PF_PACK, psg_unpack_cf(tv(n->dfeat[0], n->wfeat[0]), B, n->in_channels, n->N, grad_x, 0, st));
     return PSG_OK;
 }
@@ -855,18 +890,38 @@ extern "C" size_t psg_nu_scratch_floats(int B, int N)
     return 2 * bn + 4 * (size_t)N + (bn + 3) / 4 + 16;
 }
 
+static int nu_field(const psg_net *n, const psg_nu_buffers *b, PsgNuField *f)
+{
+    if (b->field_nc == 0) {                       // the reference's field: colours 3:6 in [0, 1]
+        f->c0 = 3; f->nc = 3;
+        for (int j = 0; j < 8; ++j) { f->lo[j] = 0.f; f->hi[j] = 1.f; }
+        return PSG_OK;
+    }
+    if (b->field_c0 < 0 || b->field_nc < 1 || b->field_nc > 8 || b->field_c0 + b->field_nc > n->in_channels) return PSG_EINVAL;
+    f->c0 = b->field_c0; f->nc = b->field_nc;
+    for (int j = 0; j < 8; ++j) {
+        f->lo[j] = j < f->nc ? b->box_lo[j] : 0.f;
+        f->hi[j] = j < f->nc ? b->box_hi[j] : 1.f;
+        if (j < f->nc && !(f->hi[j] > f->lo[j])) return PSG_EINVAL;
+    }
+    return PSG_OK;
+}
+
 extern "C" int psg_nu_init(psg_net *n, const psg_nu_buffers *b, psg_stream_t stream)
 {
     if (!n || !n->bound || !b || !b->w || !b->adam_m || !b->adam_v || !b->images || !b->status) return PSG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    PsgNuField fld;
+    PSG_TRY(nu_field(n, b, &fld));
     if (cudaMemsetAsync(b->status, 0, 4 * sizeof(int32_t), st) != cudaSuccess) return PSG_ECUDA;
-    PSG_RUN(PF_PGD, psg_nu_init_k(b->images, n->B, n->in_channels, n->N, b->w, b->adam_m, b->adam_v, st));
+    PSG_RUN(PF_PGD, psg_nu_init_k(b->images, n->B, n->in_channels, n->N, fld, b->w, b->adam_m, b->adam_v, st));
     return PSG_OK;
 }
 
 extern "C" int psg_nu_step(psg_net *n, const psg_nu_buffers *b, int t, int step, int target, int neighbour, float c,
                            float kappa, float targeted_sign, float step_size, float bc2_sqrt, int reset_adam,
-                           double acc_denom, double thr, int exit_above, int count_masked_only, psg_stream_t stream)
+                           double acc_denom, double thr, int exit_above, int count_masked_only, const int32_t *starts,
+                           psg_stream_t stream)
 {
     if (!n || !n->bound || !b || !b->w || !b->adv || !b->base || !b->images || !b->labels || !b->cost || !b->status ||
         !b->scratch || step < 0 || acc_denom <= 0.0)
@@ -876,7 +931,15 @@ extern "C" int psg_nu_step(psg_net *n, const psg_nu_buffers *b, int t, int step,
     const long long rows = (long long)B * N;
     NuScratch s = nu_carve(b->scratch, B, N);
     TView f0 = tv(n->feats[0], n->wfeat[0]), g0 = tv(n->dfeat[0], n->wfeat[0]);
-    PSG_RUN(PF_PGD, psg_nu_build_adv_k(b->w, b->base, b->images, b->mask, B, C, N, f0, b->adv, s.l2_rows, b->status, st));
+    PsgNuField fld;
+    PSG_TRY(nu_field(n, b, &fld));
+    PSG_RUN(PF_PGD, psg_nu_build_adv_k(b->w, b->base, b->images, b->mask, B, C, N, fld, f0, b->adv, s.l2_rows, b->status, st));
+    if (fld.c0 < 3) {
+        // the coordinates moved: refresh xyz from the step's image and rebuild the geometry of slot t
+        if (!starts || t != 0) return PSG_EINVAL;
+        PSG_TRY(psg_net_set_input(n, b->adv, (int64_t)C * N, N, 1, stream));
+        PSG_TRY(psg_net_geometry(n, starts, 1, stream));
+    }
     PSG_TRY(psg_net_forward(n, t, nullptr, nullptr, stream));
     // f(outputs, labels) of nontarget.py:120-128 / target.py:149-168 and its gradient; `hit` feeds
     // the accuracy test of :86-87 / :96-105
@@ -889,7 +952,7 @@ extern "C" int psg_nu_step(psg_net *n, const psg_nu_buffers *b, int t, int step,
     }
     PSG_RUN(PF_LOSS, psg_nu_reduce_k(s.f_rows, s.l2_rows, s.smooth_rows, s.hit, b->mask, rows, N, c, step, acc_denom, thr,
                                      exit_above, count_masked_only, b->cost, b->status, st));
-    PSG_RUN(PF_PGD, psg_nu_adam_k(b->w, b->adam_m, b->adam_v, g0, b->adv, b->images, s.smooth_grad, b->mask, B, C, N, c,
+    PSG_RUN(PF_PGD, psg_nu_adam_k(b->w, b->adam_m, b->adam_v, g0, b->adv, b->images, s.smooth_grad, b->mask, B, C, N, fld, c,
                                   step_size, bc2_sqrt, 0.9f, 0.999f, 1e-8f, reset_adam, b->status, st));
     return PSG_OK;
 }

@@ -17,15 +17,17 @@ namespace {
 inline unsigned nb(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // w = 0.5 * log((1 + x) / (1 - x)), x = 2 c - 1   (nontarget.py:111-117; +-inf at c = 0 / 1, Q6)
-__global__ void nu_init_kernel(const float *__restrict__ images, int B, int C, int N, float *__restrict__ w,
+// (general field: channel j of the field lives in the box [lo_j, hi_j]; the reference's colours are [0, 1])
+__global__ void nu_init_kernel(const float *__restrict__ images, int B, int C, int N, PsgNuField fld, float *__restrict__ w,
                                float *__restrict__ m, float *__restrict__ v)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)B * 3 * N) return;
+    if (t >= (long long)B * fld.nc * N) return;
     const int n = (int)(t % N);
-    const int j = (int)((t / N) % 3);
-    const int b = (int)(t / (3LL * N));
-    const float c = images[((long long)b * C + 3 + j) * N + n];
+    const int j = (int)((t / N) % fld.nc);
+    const int b = (int)(t / ((long long)fld.nc * N));
+    float c = images[((long long)b * C + fld.c0 + j) * N + n];
+    if (fld.lo[j] != 0.f || fld.hi[j] != 1.f) c = (c - fld.lo[j]) / (fld.hi[j] - fld.lo[j]);
     const float x = __fsub_rn(__fmul_rn(c, 2.f), 1.f);
     w[t] = 0.5f * logf(__fdiv_rn(__fadd_rn(1.f, x), __fsub_rn(1.f, x)));
     m[t] = 0.f;
@@ -36,7 +38,7 @@ __global__ void nu_init_kernel(const float *__restrict__ images, int B, int C, i
 // (feats0 colour columns) and the per-point L2 term sum_ch (adv - image)^2 (nontarget.py:73-78).
 __global__ void nu_build_adv_kernel(const float *__restrict__ w, const float *__restrict__ base,
                                     const float *__restrict__ images, const unsigned char *__restrict__ mask,
-                                    int B, int C, int N, TView feats0, float *__restrict__ adv,
+                                    int B, int C, int N, PsgNuField fld, TView feats0, float *__restrict__ adv,
                                     float *__restrict__ l2_rows, const int *__restrict__ status)
 {
     if (status[0]) return;
@@ -48,7 +50,11 @@ __global__ void nu_build_adv_kernel(const float *__restrict__ w, const float *__
     for (int ch = 0; ch < C; ++ch) {
         const long long o = ((long long)b * C + ch) * N + n;
         float val = base[o];
-        if (on && ch >= 3 && ch < 6) val = 0.5f * (tanhf(w[((long long)b * 3 + (ch - 3)) * N + n]) + 1.f);
+        if (on && ch >= fld.c0 && ch < fld.c0 + fld.nc) {
+            const int j = ch - fld.c0;
+            val = 0.5f * (tanhf(w[((long long)b * fld.nc + j) * N + n]) + 1.f);
+            if (fld.lo[j] != 0.f || fld.hi[j] != 1.f) val = fld.lo[j] + (fld.hi[j] - fld.lo[j]) * val;
+        }
         adv[o] = val;
         feats0.base[tv_off(feats0, row, ch >> 2) + (ch & 3)] = val;
         const float d = val - images[o];
@@ -166,7 +172,7 @@ nu_reduce_kernel(const float *__restrict__ f_rows, const float *__restrict__ l2_
 __global__ void nu_adam_kernel(float *__restrict__ w, float *__restrict__ m, float *__restrict__ v, TView grad0,
                                const float *__restrict__ adv, const float *__restrict__ images,
                                const float *__restrict__ smooth_grad, const unsigned char *__restrict__ mask, int B,
-                               int C, int N, float c, float step_size, float bc2_sqrt, float beta1, float beta2,
+                               int C, int N, PsgNuField fld, float c, float step_size, float bc2_sqrt, float beta1, float beta2,
                                float eps, int reset, const int *__restrict__ status)
 {
     if (status[0]) return;
@@ -174,17 +180,17 @@ __global__ void nu_adam_kernel(float *__restrict__ w, float *__restrict__ m, flo
     if (row >= (long long)B * N) return;
     if (mask && !mask[row]) return;
     const int b = (int)(row / N), n = (int)(row % N);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int ch = 3 + j;
-        const long long wi = ((long long)b * 3 + j) * N + n;
+    for (int j = 0; j < fld.nc; ++j) {
+        const int ch = fld.c0 + j;
+        const long long wi = ((long long)b * fld.nc + j) * N + n;
         const long long o = ((long long)b * C + ch) * N + n;
         float g = grad0.base[tv_off(grad0, row, ch >> 2) + (ch & 3)];
         g = fmaf(c, 2.f * (adv[o] - images[o]), g);
-        if (b == 0) g = fmaf(c, smooth_grad[(long long)j * N + n], g);
+        if (b == 0 && ch >= 3 && ch < 6) g = fmaf(c, smooth_grad[(long long)(ch - 3) * N + n], g);
         const float wv = w[wi];
         const float t = tanhf(wv);
-        const float gw = g * (0.5f * (1.f - t * t));
+        float gw = g * (0.5f * (1.f - t * t));
+        if (fld.lo[j] != 0.f || fld.hi[j] != 1.f) gw *= (fld.hi[j] - fld.lo[j]);
         float mm = reset ? 0.f : m[wi], vv = reset ? 0.f : v[wi];
         mm = mm + (gw - mm) * (1.f - beta1);
         vv = vv * beta2 + (1.f - beta2) * gw * gw;
@@ -203,17 +209,17 @@ __global__ void clamp_kernel(float *__restrict__ x, long long n, float lo, float
 
 }  // namespace
 
-int psg_nu_init_k(const float *images, int B, int C, int N, float *w, float *m, float *v, cudaStream_t st)
+int psg_nu_init_k(const float *images, int B, int C, int N, PsgNuField fld, float *w, float *m, float *v, cudaStream_t st)
 {
-    nu_init_kernel<<<nb((long long)B * 3 * N, 256), 256, 0, st>>>(images, B, C, N, w, m, v);
+    nu_init_kernel<<<nb((long long)B * fld.nc * N, 256), 256, 0, st>>>(images, B, C, N, fld, w, m, v);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
 
 int psg_nu_build_adv_k(const float *w, const float *base, const float *images, const unsigned char *mask, int B, int C,
-                     int N, TView feats0, float *adv, float *l2_rows, const int *status, cudaStream_t st)
+                     int N, PsgNuField fld, TView feats0, float *adv, float *l2_rows, const int *status, cudaStream_t st)
 {
-    nu_build_adv_kernel<<<nb((long long)B * N, 256), 256, 0, st>>>(w, base, images, mask, B, C, N, feats0, adv, l2_rows,
+    nu_build_adv_kernel<<<nb((long long)B * N, 256), 256, 0, st>>>(w, base, images, mask, B, C, N, fld, feats0, adv, l2_rows,
                                                                   status);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
@@ -249,10 +255,10 @@ int psg_nu_reduce_k(const float *f_rows, const float *l2_rows, const float *smoo
 }
 
 int psg_nu_adam_k(float *w, float *m, float *v, TView grad0, const float *adv, const float *images,
-                const float *smooth_grad, const unsigned char *mask, int B, int C, int N, float c, float step_size,
+                const float *smooth_grad, const unsigned char *mask, int B, int C, int N, PsgNuField fld, float c, float step_size,
                 float bc2_sqrt, float beta1, float beta2, float eps, int reset, const int *status, cudaStream_t st)
 {
-    nu_adam_kernel<<<nb((long long)B * N, 256), 256, 0, st>>>(w, m, v, grad0, adv, images, smooth_grad, mask, B, C, N, c,
+    nu_adam_kernel<<<nb((long long)B * N, 256), 256, 0, st>>>(w, m, v, grad0, adv, images, smooth_grad, mask, B, C, N, fld, c,
                                                             step_size, bc2_sqrt, beta1, beta2, eps, reset, status);
     PSG_LAUNCH_CHECK();
     return PSG_OK;

@@ -95,6 +95,14 @@ struct PsgFpStream {
 bool psg_fp_streamable(const PsgFpStream &f, bool forward);
 int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st);
 int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStream_t st);
+// geomgrad.cu: gradient w.r.t. coordinates through grouping and interpolation weights
+int psg_sa_xyz_backward(TView dG, int D, int K, long long groups_per_p, long long P, const int *offs, const int *perm, int R,
+                        float *dxyz_src, float *dxyz_ctr, cudaStream_t st);
+int psg_fps_xyz_backward(const float *dxyz_l, const int *fps_idx, int S, int R, int P, float *dxyz_src, cudaStream_t st);
+int psg_fp_xyz_backward(TView dI, TView coarse, int C2, const float *xyz1, long long stride1, int nclouds1, const float *xyz2,
+                        int S, const int *nn_idx, const int *offs, const int *perm, long long P, int N, float *dxyz1,
+                        float *dxyz2, float *ctmp, cudaStream_t st);
+int psg_add_xyz_to_feat(const float *dxyz0, long long rows, TView dfeat0, cudaStream_t st);
 // elementwise.cu
 int psg_head_logsoftmax(TView z, long long rows, int ncls, float *logp, cudaStream_t st);
 int psg_dz_from_dlogp(TView z, const float *dlogp, long long rows, int ncls, TView dz, cudaStream_t st);
@@ -107,15 +115,16 @@ int psg_pgd_update(float *adv, const float *ori, TView grad, TView feats0, const
 int psg_confusion(const float *logp, const int *labels, const unsigned char *mask, int target, long long rows, int ncls,
                   long long *conf, cudaStream_t st);
 // nu.cu
-int psg_nu_init_k(const float *images, int B, int C, int N, float *w, float *m, float *v, cudaStream_t st);
+struct PsgNuField { int c0, nc; float lo[8], hi[8]; };   // perturbed channels [c0, c0+nc) and their tanh-space box
+int psg_nu_init_k(const float *images, int B, int C, int N, PsgNuField fld, float *w, float *m, float *v, cudaStream_t st);
 int psg_nu_build_adv_k(const float *w, const float *base, const float *images, const unsigned char *mask, int B, int C,
-                     int N, TView feats0, float *adv, float *l2_rows, const int *status, cudaStream_t st);
+                     int N, PsgNuField fld, TView feats0, float *adv, float *l2_rows, const int *status, cudaStream_t st);
 int psg_nu_smooth_k(const float *adv0, const float *images0, int C, int N, int k, float *rows_out, float *grad_out,
                   cudaStream_t st);
 int psg_nu_reduce_k(const float *f_rows, const float *l2_rows, const float *smooth_rows, const unsigned char *hit,
                   const unsigned char *mask, long long rows, int nsmooth, float c, int step, double acc_denom, double thr,
                   int exit_above, int count_masked_only, float *cost, int *status, cudaStream_t st);
 int psg_nu_adam_k(float *w, float *m, float *v, TView grad0, const float *adv, const float *images,
-                const float *smooth_grad, const unsigned char *mask, int B, int C, int N, float c, float step_size,
+                const float *smooth_grad, const unsigned char *mask, int B, int C, int N, PsgNuField fld, float c, float step_size,
                 float bc2_sqrt, float beta1, float beta2, float eps, int reset, const int *status, cudaStream_t st);
 int psg_clamp_k(float *x, long long n, float lo, float hi, cudaStream_t st);

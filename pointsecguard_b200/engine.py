@@ -121,6 +121,10 @@ class Engine:
         torchattacks/attacks/nontarget.py) or torch's current stream."""
         return self._stream_handle if self._stream_handle is not None else torch.cuda.current_stream().cuda_stream
 
+    def set_xyz_grad(self, on: bool):
+        """Also produce the geometric gradient w.r.t. coordinates (csrc/geomgrad.cu) in backward()."""
+        L.psg_net_set_xyz_grad(self._net, 1 if on else 0)
+
     def use_stream(self, stream):
         """Pin this engine to a torch.cuda.Stream (None = follow torch's current stream)."""
         self._stream_handle = stream.cuda_stream if stream is not None else None

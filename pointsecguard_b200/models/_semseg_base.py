@@ -36,7 +36,9 @@ class _NetFn(torch.autograd.Function):
             raise RuntimeError("pointsecguard_b200: the activations of this forward were overwritten by a later "
                                "forward of the same model; back-propagate before running the model again")
         ctx.eng.loss_grad_generic(dlogp)
+        ctx.eng.set_xyz_grad(bool(getattr(ctx.model, "xyz_grad", False)))
         g = ctx.eng.backward(0, True)
+        ctx.eng.set_xyz_grad(False)
         return g, None, None
 
 
@@ -45,6 +47,10 @@ class SemSegBase(nn.Module):
 
     arch = "ssg"
     mlp_mode = MLP_FP32
+    # autograd of forward(): False = gradient through the features only (all the colour attacks need);
+    # True = also through the geometry (centred neighbour coordinates, interpolation weights), which
+    # is what the reference's autograd produces on input channels 0:3
+    xyz_grad = False
 
     # number of independent sub-batches an attack pipelines over CUDA streams ("auto": by batch size)
     sub_batches = "auto"

@@ -39,12 +39,29 @@ def _draw_chunk(eng, T):
     return torch.cat(starts, dim=1), states
 
 
+# Default tanh-space box of the coordinate + colour field (an extension of the reference, whose field is
+# colour only): block-centred x, y in [-0.5, 0.5], z in [0, 3] metres (S3DISDataLoader.py:154-161) with
+# a 10 % margin so that points on the block boundary do not map to +-inf (Q6), colours in [0, 1].
+COORD_COLOR_BOX = ([-0.55, -0.55, -0.15, 0.0, 0.0, 0.0], [0.55, 0.55, 3.15, 1.0, 1.0, 1.0])
+
+
 def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None):
     """Shared driver.  ``masked_variant`` False -> NU_attack semantics (nontarget.py), True ->
-    tar_NU_attack semantics (target.py); default: masked iff a mask is given."""
+    tar_NU_attack semantics (target.py); default: masked iff a mask is given.
+
+    ``atk.field = (c0, c1)`` (default: the reference's colours, 3:6) selects the perturbed channels;
+    a field that includes coordinates makes every step rebuild the geometry from the step's image and
+    adds the geometric gradient (csrc/geomgrad.cu) to the coordinate channels."""
     eng = atk._engine(images)
     dev = images.device
     B, Cc, N = images.shape
+    field = getattr(atk, "field", None) or (3, 6)
+    c0, nc = int(field[0]), int(field[1]) - int(field[0])
+    moves_xyz = c0 < 3
+    box = getattr(atk, "box", None)
+    if box is None:
+        box = ([COORD_COLOR_BOX[0][c] for c in range(c0, c0 + nc)], [COORD_COLOR_BOX[1][c] for c in range(c0, c0 + nc)]) \
+            if c0 + nc <= 6 else ([0.0] * nc, [1.0] * nc)
     tar_variant = (mask is not None) if masked_variant is None else masked_variant
     if tar_variant and mask is None:
         raise ValueError("tar_NU_attack needs a mask (target.py:53)")
@@ -55,7 +72,7 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
     steps = int(atk.steps)
     st = torch.cuda.current_stream().cuda_stream
 
-    w = torch.empty(B, 3, N, dtype=torch.float32, device=dev)
+    w = torch.empty(B, nc, N, dtype=torch.float32, device=dev)
     am, av = torch.empty_like(w), torch.empty_like(w)
     adv = img.clone()
     cost = torch.zeros(max(steps, 1), dtype=torch.float32, device=dev)
@@ -64,6 +81,10 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
     buf = L.NuBuffers(w.data_ptr(), am.data_ptr(), av.data_ptr(), adv.data_ptr(), base.data_ptr(), img.data_ptr(),
                       msk.data_ptr() if msk is not None else None, lab.data_ptr(), cost.data_ptr(), status.data_ptr(),
                       scratch.data_ptr())
+    if (c0, nc) != (3, 3) or getattr(atk, "box", None) is not None:
+        buf.field_c0, buf.field_nc = c0, nc
+        for j in range(nc):
+            buf.box_lo[j], buf.box_hi[j] = float(box[0][j]), float(box[1][j])
 
     if tar_variant:
         m_cpu = torch.as_tensor(np.asarray(mask)) if not torch.is_tensor(mask) else mask.cpu()
@@ -92,9 +113,12 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
         if tar_variant and m_cpu.dim() == 2:
             dn = torch.tensor([denom], dtype=torch.float64, device=dev)
             denom = max(float(D.all_reduce_sum_(dn).item()), 1.0)
+    if moves_xyz:
+        chunk_cap = 1                                                  # geometry changes with every step
     eng.bind(B, N, min(chunk_cap, max(steps, 1)))
     eng.set_input(img)
     L.psg_nu_init(eng._net, C.byref(buf), st)
+    L.psg_net_set_xyz_grad(eng._net, 1 if moves_xyz else 0)
 
     lr = float(atk.lr)
     adam_k, reset = 0, 0
@@ -106,14 +130,19 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
             end = min(end, max(20, (step + 9) // 10 * 10) + 1)
         T = end - step
         starts, states = _draw_chunk(eng, T)
-        eng.geometry(starts)
+        starts_dev = None
+        if moves_xyz:
+            starts_dev = starts.to(device=dev, dtype=torch.int32).contiguous()     # [4, 1, B]: rebuilt inside the step
+        else:
+            eng.geometry(starts)
         for i in range(T):
             s = step + i
             adam_k += 1
             step_size = lr / (1.0 - 0.9 ** adam_k)
             bc2 = math.sqrt(1.0 - 0.999 ** adam_k)
             L.psg_nu_step(eng._net, C.byref(buf), i, s, tgt, int(neighbour), float(atk.c), float(atk.kappa), sign,
-                          step_size, bc2, reset, denom, thr_dev, above, masked_only, st)
+                          step_size, bc2, reset, denom, thr_dev, above, masked_only,
+                          starts_dev.data_ptr() if starts_dev is not None else None, st)
             reset = 0
             if tar_variant and s > 0 and s % 50 == 0:                 # target.py:123-125
                 lr = lr / 2
@@ -148,6 +177,7 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
                     buf.base = base.data_ptr()
                     eng.set_input(base)
         step = end
+    L.psg_net_set_xyz_grad(eng._net, 0)
     atk.model._generation += 1
     return adv
 

@@ -90,12 +90,17 @@ def _nb_loop(atk, images, labels, target, mask):
 
 
 class NU_attack(Attack):
-    def __init__(self, model, c=1e-4, kappa=0, steps=1000, lr=0.01):
+    """nontarget.py:44-135.  ``field`` / ``box`` are extensions (default = the reference: colours 3:6 in
+    [0,1]): ``field=(0, 6)`` perturbs coordinates and colours (BASELINE.json configs[2])."""
+
+    def __init__(self, model, c=1e-4, kappa=0, steps=1000, lr=0.01, field=None, box=None):
         super().__init__("NU_attack", model)
         self.c = c
         self.kappa = kappa
         self.steps = steps
         self.lr = lr
+        self.field = field
+        self.box = box
 
     def forward(self, images, labels):
         from pointsecguard_b200 import nu

@@ -187,3 +187,25 @@ def test_sub_batch_pipelining_is_exact():
         outs.append(torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=3)(x, lab))
     m.sub_batches = "auto"
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("arch", ["ssg", "msg"])
+def test_coordinate_gradient_vs_reference_golden(golden_dir, arch):
+    """With model.xyz_grad the autograd of forward() is complete on all nine channels: channels 0:3 get
+    the gradient through the features AND through the geometry (centred neighbour coordinates of every
+    SA level, inverse-distance weights of every FP level), as the reference's autograd computes it."""
+    g = dict(np.load(os.path.join(golden_dir, f"model_{arch}.npz")))
+    m = _model(arch)
+    m.xyz_grad = True
+    x = syn.make_blocks(2, 2048, 0, "uniform").cuda().requires_grad_(True)
+    torch.manual_seed(0)
+    logp, _ = m(x)
+    y = torch.from_numpy(g["y"]).long().cuda()
+    cost = torch.nn.functional.cross_entropy(logp.reshape(-1, 13), y.view(-1), reduction="sum") / logp.size(1)
+    cost.backward()
+    mine = x.grad.cpu().numpy()
+    rel, sign, close = _grad_report(mine[:, :3], g["grad"][:, :3])
+    print(f"{arch}: xyz grad rel={rel:.2e} sign={sign:.5f} within-rtol-1e-3={close:.4f}")
+    assert rel < 2e-2 and sign > 0.995
+    rel_all, sign_all, _ = _grad_report(mine, g["grad"])
+    assert rel_all < 2e-2 and sign_all > 0.998

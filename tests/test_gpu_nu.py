@@ -114,3 +114,31 @@ def test_nu_is_deterministic():
         outs.append(torchattacks.NU_attack(m, c=0.1, kappa=0, steps=3, lr=0.01)(x, lab))
     assert torch.equal(outs[0], outs[1])
     assert not torch.equal(outs[0], x)
+
+
+def test_nu_coordinate_and_colour_field_vs_oracle():
+    """BASELINE configs[2]: NU over channels 0:6 (coordinates + colours) -- an extension with no
+    reference code (SURVEY.md finding 1), pinned against the oracle's NU loop with the colour slice
+    widened to 0:6 inside the same per-channel tanh box and nothing else changed.  Geometry (FPS, ball
+    query, 3-NN) is rebuilt every step from the moved coordinates; the coordinate gradient includes the
+    geometric path."""
+    from oracle import attacks_oracle as AO
+    from oracle import pointnet2_oracle as PO
+    from pointsecguard_b200 import torchattacks
+    from pointsecguard_b200.nu import COORD_COLOR_BOX
+    sd = syn.make_state_dict("ssg")
+    m = _model()
+    x = syn.make_blocks(2, 1024, 7)
+    torch.manual_seed(9)
+    lab = PO.OracleModel(sd, "ssg")(x)[0].max(2)[1].numpy().astype(np.float64)
+    torch.manual_seed(1)
+    ref = AO.nu_attack(PO.OracleModel(sd, "ssg"), x, lab, c=0.1, kappa=0, steps=3, lr=0.01, field=slice(0, 6),
+                       box=COORD_COLOR_BOX)
+    torch.manual_seed(1)
+    adv = torchattacks.NU_attack(m, c=0.1, kappa=0, steps=3, lr=0.01, field=(0, 6))(x.cuda(), lab)
+    assert torch.equal(adv[:, 6:].cpu(), x[:, 6:])
+    moved = (adv[:, :3].cpu() - x[:, :3]).abs().max().item()
+    assert 0 < moved < 0.05                                   # 2 Adam steps of lr 0.01 inside a ~1 m box
+    frac, mx = _report(adv.cpu().numpy(), ref.numpy(), atol=5e-4)
+    print("NU field 0:6 within-atol fraction", frac, "max dev", mx)
+    assert frac > 0.98 and mx < 0.1
