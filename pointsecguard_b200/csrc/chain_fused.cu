@@ -22,6 +22,7 @@
 #include "psg_internal.h"
 #include "psg_loss.cuh"
 #include "psg_tc.cuh"
+#include "psg_epi.cuh"
 
 namespace {
 
@@ -277,60 +278,74 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                 tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
                 const int words = (op.n + 31) / 32;
                 if (op.epi == EPI_RELU) {
-                    unsigned bits = 0;
-                    for (int c16 = 0; c16 < op.n; c16 += 16) {
+                    int c = 0;
+                    for (; c + 32 <= op.n; c += 32) {
+                        float v[32];
+                        tc::tmem_ld32(tl + (uint32_t)c, v);
+                        const unsigned w = psg_relu_bias_bits<32>(v, op.bias + c);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *plane_ptr(pA, (c >> 2) + q, r) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (op.slot >= 0) mbits[((size_t)op.slot * 8 + (c >> 5)) * 128 + r] = w;
+                        if (op.mglobal) op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r] = w;
+                    }
+                    if (c < op.n) {
                         float v[16];
-                        tc::tmem_ld16(tl + (uint32_t)c16, v);
+                        tc::tmem_ld16(tl + (uint32_t)c, v);
+                        const unsigned w = psg_relu_bias_bits<16>(v, op.bias + c);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            v[i] = fmaxf(v[i] + __ldg(op.bias + c16 + i), 0.f);
-                            bits |= (v[i] > 0.f ? 1u : 0u) << ((c16 & 16) + i);
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *plane_ptr(pA, (c16 >> 2) + c, r) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                        if ((c16 & 16) || c16 + 16 >= op.n) {
-                            if (op.slot >= 0) mbits[((size_t)op.slot * 8 + (c16 >> 5)) * 128 + r] = bits;
-                            if (op.mglobal) op.mglobal[((size_t)tile * words + (c16 >> 5)) * 128 + r] = bits;
-                            bits = 0;
-                        }
+                        for (int q = 0; q < 4; ++q)
+                            *plane_ptr(pA, (c >> 2) + q, r) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (op.slot >= 0) mbits[((size_t)op.slot * 8 + (c >> 5)) * 128 + r] = w;
+                        if (op.mglobal) op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r] = w;
                     }
                 } else if (op.epi == EPI_MASK) {
-                    unsigned bits = 0;
-                    for (int c16 = 0; c16 < op.n; c16 += 16) {
-                        if ((c16 & 16) == 0)
-                            bits = op.mglobal ? op.mglobal[((size_t)tile * words + (c16 >> 5)) * 128 + r]
-                                              : mbits[((size_t)op.slot * 8 + (c16 >> 5)) * 128 + r];
+                    int c = 0;
+                    for (; c + 32 <= op.n; c += 32) {
+                        const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r]
+                                                      : mbits[((size_t)op.slot * 8 + (c >> 5)) * 128 + r];
+                        float v[32];
+                        tc::tmem_ld32(tl + (uint32_t)c, v);
+                        psg_apply_bits<32>(v, w);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *plane_ptr(pA, (c >> 2) + q, r) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                    if (c < op.n) {
+                        const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r]
+                                                      : mbits[((size_t)op.slot * 8 + (c >> 5)) * 128 + r];
                         float v[16];
-                        tc::tmem_ld16(tl + (uint32_t)c16, v);
+                        tc::tmem_ld16(tl + (uint32_t)c, v);
+                        psg_apply_bits<16>(v, w);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (!((bits >> ((c16 & 16) + i)) & 1u)) v[i] = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *plane_ptr(pA, (c16 >> 2) + c, r) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        for (int q = 0; q < 4; ++q)
+                            *plane_ptr(pA, (c >> 2) + q, r) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     }
                 } else if (op.epi == EPI_STORE) {
-                    unsigned bits = 0;
-                    for (int c16 = 0; c16 < op.n; c16 += 16) {
-                        float v[16];
-                        tc::tmem_ld16(tl + (uint32_t)c16, v);
-                        if (op.relu) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                v[i] = fmaxf(v[i] + __ldg(op.bias + c16 + i), 0.f);
-                                bits |= (v[i] > 0.f ? 1u : 0u) << ((c16 & 16) + i);
-                            }
-                        }
+                    int c = 0;
+                    for (; c + 32 <= op.n; c += 32) {
+                        float v[32];
+                        tc::tmem_ld32(tl + (uint32_t)c, v);
+                        unsigned w = 0;
+                        if (op.relu) w = psg_relu_bias_bits<32>(v, op.bias + c);
                         if (valid) {
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                tv_st(op.out, row, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                            for (int q = 0; q < 8; ++q)
+                                tv_st(op.out, row, (c >> 2) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
                         }
-                        if (op.mglobal && ((c16 & 16) || c16 + 16 >= op.n)) {
-                            op.mglobal[((size_t)tile * words + (c16 >> 5)) * 128 + r] = bits;
-                            bits = 0;
+                        if (op.mglobal) op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r] = w;
+                    }
+                    if (c < op.n) {
+                        float v[16];
+                        tc::tmem_ld16(tl + (uint32_t)c, v);
+                        unsigned w = 0;
+                        if (op.relu) w = psg_relu_bias_bits<16>(v, op.bias + c);
+                        if (valid) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                tv_st(op.out, row, (c >> 2) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
                         }
+                        if (op.mglobal) op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r] = w;
                     }
                 } else if (op.epi == EPI_MAXPOOL) {
                     const long long g = row / K;

@@ -21,6 +21,7 @@
 #include "psg_common.cuh"
 #include "psg_internal.h"
 #include "psg_tc.cuh"
+#include "psg_epi.cuh"
 
 namespace {
 
@@ -70,22 +71,24 @@ struct SaFwdArgs {
 __device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n, const float *__restrict__ bias,
                                                       unsigned char *dst, unsigned *mask_tile, int row)
 {
-    unsigned bits = 0;
-    for (int c16 = 0; c16 < n; c16 += 16) {
+    int c = 0;
+    for (; c + 32 <= n; c += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_lane + (uint32_t)c, v);
+        const unsigned w = psg_relu_bias_bits<32>(v, bias + c);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            *plane_ptr(dst, (c >> 2) + q, row) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        mask_tile[(size_t)(c >> 5) * 128 + row] = w;
+    }
+    if (c < n) {
         float v[16];
-        tc::tmem_ld16(tmem_lane + (uint32_t)c16, v);
+        tc::tmem_ld16(tmem_lane + (uint32_t)c, v);
+        const unsigned w = psg_relu_bias_bits<16>(v, bias + c);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            v[i] = fmaxf(v[i] + __ldg(bias + c16 + i), 0.f);
-            bits |= (v[i] > 0.f ? 1u : 0u) << ((c16 & 16) + i);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            *plane_ptr(dst, (c16 >> 2) + c, row) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        if ((c16 & 16) || c16 + 16 >= n) {
-            mask_tile[(size_t)(c16 >> 5) * 128 + row] = bits;
-            bits = 0;
-        }
+        for (int q = 0; q < 4; ++q)
+            *plane_ptr(dst, (c >> 2) + q, row) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        mask_tile[(size_t)(c >> 5) * 128 + row] = w;
     }
 }
 
@@ -270,17 +273,24 @@ struct SaBwdArgs {
 __device__ __forceinline__ void epilogue_mask_to_smem(uint32_t tmem_lane, int n, const unsigned *mask_tile,
                                                       unsigned char *dst, int row)
 {
-    unsigned bits = 0;
-    for (int c16 = 0; c16 < n; c16 += 16) {
-        if ((c16 & 16) == 0) bits = mask_tile[(size_t)(c16 >> 5) * 128 + row];
+    int c = 0;
+    for (; c + 32 <= n; c += 32) {
+        const unsigned w = mask_tile[(size_t)(c >> 5) * 128 + row];
+        float v[32];
+        tc::tmem_ld32(tmem_lane + (uint32_t)c, v);
+        psg_apply_bits<32>(v, w);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            *plane_ptr(dst, (c >> 2) + q, row) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (c < n) {
+        const unsigned w = mask_tile[(size_t)(c >> 5) * 128 + row];
         float v[16];
-        tc::tmem_ld16(tmem_lane + (uint32_t)c16, v);
+        tc::tmem_ld16(tmem_lane + (uint32_t)c, v);
+        psg_apply_bits<16>(v, w);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (!((bits >> ((c16 & 16) + i)) & 1u)) v[i] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            *plane_ptr(dst, (c16 >> 2) + c, row) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        for (int q = 0; q < 4; ++q)
+            *plane_ptr(dst, (c >> 2) + q, row) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
 }
 
