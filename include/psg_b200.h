@@ -55,6 +55,14 @@ int psg_ball_query(const float *xyz, int nclouds, int P, int N, const float *new
                    const double *radius_host, const int *nsample_host, int32_t *out0, int32_t *out1,
                    psg_stream_t stream);
 
+/* Same results through a uniform grid over the cloud (cell edge >= 1.01 r): a centroid tests only the
+ * points of its 27 neighbouring cells and emits the hits smallest index first; centroids with more than
+ * 96 hits fall back to the exhaustive scan.  ~8x less work than the scan at SA1 densities. */
+size_t psg_ball_grid_workspace(int nclouds, int N);
+int psg_ball_query_grid(const float *xyz, int nclouds, int P, int N, const float *new_xyz, int S, int nr,
+                        const double *radius_host, const int *nsample_host, int32_t *out0, int32_t *out1,
+                        void *workspace, size_t workspace_bytes, psg_stream_t stream);
+
 /* 3-NN + inverse-distance weights, pointnet_util.py:301-307.  w / d2 optional. */
 int psg_three_nn(const float *xyz1, int nclouds1, int P, int N, const float *xyz2, int S, int32_t *idx,
                  float *w, float *d2, psg_stream_t stream);

@@ -56,6 +56,8 @@ _PROTOS = {
     "psg_fps": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "psg_square_distance": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "psg_ball_query": (_i, [_vp, _i, _i, _i, _vp, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_int), _vp, _vp, _vp]),
+    "psg_ball_grid_workspace": (_sz, [_i, _i]),
+    "psg_ball_query_grid": (_i, [_vp, _i, _i, _i, _vp, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_int), _vp, _vp, _vp, _sz, _vp]),
     "psg_three_nn": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "psg_index_points": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp]),
     "psg_pack_channels_first": (_i, [_vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp]),

@@ -34,6 +34,24 @@ extern "C" int psg_ball_query(const float *xyz, int nclouds, int P, int N, const
                                  out1, (cudaStream_t)stream);
 }
 
+extern "C" size_t psg_ball_grid_workspace(int nclouds, int N) { return psg_ballgrid_workspace_bytes(nclouds, N); }
+
+extern "C" int psg_ball_query_grid(const float *xyz, int nclouds, int P, int N, const float *new_xyz, int S, int nr,
+                                   const double *radius_host, const int *nsample_host, int32_t *out0, int32_t *out1,
+                                   void *workspace, size_t workspace_bytes, psg_stream_t stream)
+{
+    if (!xyz || !new_xyz || !radius_host || !nsample_host || !out0 || (nr == 2 && !out1) || !workspace) return PSG_EINVAL;
+    if (nr < 1 || nr > 2) return PSG_EINVAL;
+    for (int i = 0; i < nr; ++i)
+        if (nsample_host[i] <= 0 || !(radius_host[i] > 0.0)) return PSG_EINVAL;
+    if (workspace_bytes < psg_ballgrid_workspace_bytes(nclouds, N)) return PSG_EWORKSPACE;
+    const double rmax = nr == 2 && radius_host[1] > radius_host[0] ? radius_host[1] : radius_host[0];
+    int rc = psg_ballgrid_build(xyz, (long long)N * 3, nclouds, N, rmax, workspace, (cudaStream_t)stream);
+    if (rc != PSG_OK) return rc;
+    return psg_ballgrid_query(workspace, xyz, (long long)N * 3, nclouds, P, N, new_xyz, S, nr, radius_host, nsample_host, out0,
+                              out1, (cudaStream_t)stream);
+}
+
 extern "C" int psg_three_nn(const float *xyz1, int nclouds1, int P, int N, const float *xyz2, int S, int32_t *idx,
                             float *w, float *d2, psg_stream_t stream)
 {

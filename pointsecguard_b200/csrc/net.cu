@@ -249,6 +249,8 @@ struct psg_net {
     int *starts;           // [4][T][B]
     void *fps_ws; size_t fps_ws_bytes;
     void *csr_ws;
+    void *grid_ws;         // uniform grid over the level-0 clouds (ballgrid.cu), when N is large
+    bool grid_valid;
     float *feats[5], *dfeat[5];
     float *H, *Z, *dZ;
     float *S[2]; size_t scratch_floats;
@@ -462,6 +464,8 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
     n->S[1] = bp.take<float>(scratch);
     n->fps_ws = bp.take<char>(n->fps_ws_bytes ? n->fps_ws_bytes : 16);
     n->csr_ws = bp.take<char>(csr_scratch);
+    n->grid_ws = N >= 2048 ? (void *)bp.take<char>(psg_ballgrid_workspace_bytes(B, N)) : nullptr;
+    n->grid_valid = false;
     return bp.off + 1024;
 }
 
@@ -498,6 +502,7 @@ extern "C" int psg_net_set_input(psg_net *n, const float *x, int64_t sb, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     PSG_RUN(PF_PACK, psg_pack_cf(x, sb, sc, sn, n->B, n->in_channels, n->N, TView{n->feats[0], n->wfeat[0] / 4, 0},
                                  n->wfeat[0], n->xyz0, st));
+    n->grid_valid = false;
     return PSG_OK;
 }
 
@@ -524,6 +529,16 @@ extern "C" int psg_net_geometry(psg_net *n, const int32_t *starts, int T, psg_st
         SaLevel &L = n->sa[l - 1];
         // MSG: the two radii of a level share one scan of the cloud (pointnet_util.py:246-248)
         int ns[2] = {L.br[0].K, L.nbr > 1 ? L.br[1].K : 0};
+        if (l == 1 && n->grid_ws) {
+            // level-0 clouds are shared by all T forwards: bin them once per input, query through the grid
+            if (!n->grid_valid) {
+                const double rmax = L.nbr > 1 && L.radius[1] > L.radius[0] ? L.radius[1] : L.radius[0];
+                PSG_RUN(PF_BALL, psg_ballgrid_build(cloud, stride, nclouds, R, rmax, n->grid_ws, st));
+                n->grid_valid = true;
+            }
+            PSG_RUN(PF_BALL, psg_ballgrid_query(n->grid_ws, cloud, stride, nclouds, P, R, n->xyz[l], S, L.nbr, L.radius, ns,
+                                                L.br[0].ball, L.nbr > 1 ? L.br[1].ball : nullptr, st));
+        } else
         PSG_RUN(PF_BALL, psg_ball_query_launch(cloud, stride, nclouds, P, R, n->xyz[l], S, L.nbr, L.radius, ns, L.br[0].ball,
                                       L.nbr > 1 ? L.br[1].ball : nullptr, st));
         for (int b = 0; b < L.nbr; ++b)

@@ -30,6 +30,11 @@ int psg_ball_query_launch(const float *xyz, long long cloud_stride, int nclouds,
 int psg_three_nn_launch(const float *xyz1, long long stride1, int nclouds1, int P, int N,
                         const float *xyz2, int S, int *idx, float *w, float *d2, cudaStream_t st);
 int psg_square_distance_launch(const float *src, const float *dst, int B, int N, int M, float *out, cudaStream_t st);
+// ballgrid.cu: ball query over a uniform grid (large clouds), same results as psg_ball_query_launch
+size_t psg_ballgrid_workspace_bytes(int nclouds, int N);
+int psg_ballgrid_build(const float *xyz, long long cloud_stride, int nclouds, int N, double rmax, void *ws, cudaStream_t st);
+int psg_ballgrid_query(const void *ws, const float *xyz, long long cloud_stride, int nclouds, int P, int N, const float *new_xyz,
+                       int S, int nr, const double *radius, const int *nsample, int *out0, int *out1, cudaStream_t st);
 // gather.cu
 int psg_pack_cf(const float *x, long long sb, long long sc, long long sn, int B, int C, int N, TView out,
                 int cpad, float *xyz, cudaStream_t st);

@@ -68,6 +68,20 @@ _LIB.define("ball_query(float radius, int nsample, Tensor xyz, Tensor new_xyz) -
 _LIB.define("ball_query2(float r0, int k0, float r1, int k1, Tensor xyz, Tensor new_xyz) -> (Tensor, Tensor)")
 
 
+_GRID_MIN_N = 1024      # clouds at least this large go through the uniform-grid kernel (same results)
+
+
+def _ball_launch(xyz, new_xyz, B, N, S, nr, r, k, o0, o1):
+    if N >= _GRID_MIN_N:
+        wsb = L.psg_ball_grid_workspace(B, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
+        L.psg_ball_query_grid(xyz.data_ptr(), B, B, N, new_xyz.data_ptr(), S, nr, r, k, o0.data_ptr(),
+                              o1.data_ptr() if o1 is not None else None, ws.data_ptr(), wsb, _stream())
+    else:
+        L.psg_ball_query(xyz.data_ptr(), B, B, N, new_xyz.data_ptr(), S, nr, r, k, o0.data_ptr(),
+                         o1.data_ptr() if o1 is not None else None, _stream())
+
+
 def _ball_cuda(radius, nsample, xyz, new_xyz):
     xyz, new_xyz = _f32c(xyz), _f32c(new_xyz)
     B, N, _ = xyz.shape
@@ -77,7 +91,7 @@ def _ball_cuda(radius, nsample, xyz, new_xyz):
     k = (C.c_int * 2)(nsample, 0)
     # the radius travels as a double: pointnet_util.py:102 squares the Python float in double
     # precision and only the comparison casts it to float32
-    L.psg_ball_query(xyz.data_ptr(), B, B, N, new_xyz.data_ptr(), S, 1, r, k, out.data_ptr(), None, _stream())
+    _ball_launch(xyz, new_xyz, B, N, S, 1, r, k, out, None)
     return out.to(torch.int64)
 
 
@@ -89,7 +103,7 @@ def _ball2_cuda(r0, k0, r1, k1, xyz, new_xyz):
     o1 = torch.empty(B, S, k1, dtype=torch.int32, device=xyz.device)
     r = (C.c_double * 2)(r0, r1)
     k = (C.c_int * 2)(k0, k1)
-    L.psg_ball_query(xyz.data_ptr(), B, B, N, new_xyz.data_ptr(), S, 2, r, k, o0.data_ptr(), o1.data_ptr(), _stream())
+    _ball_launch(xyz, new_xyz, B, N, S, 2, r, k, o0, o1)
     return o0.to(torch.int64), o1.to(torch.int64)
 
 

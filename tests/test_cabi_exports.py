@@ -61,7 +61,7 @@ def test_argument_errors_are_status_codes_not_crashes():
     with pytest.raises(L.PsgError):
         L.psg_net_forward(None, 0, None, None, None)
     with pytest.raises(L.PsgError):
-        L.psg_nu_step(None, None, 0, 0, -1, 10, 0.1, 0.0, 1.0, 0.01, 1.0, 0, 4096.0, 0.07, 0, 0, None)
+        L.psg_nu_step(None, None, 0, 0, -1, 10, 0.1, 0.0, 1.0, 0.01, 1.0, 0, 4096.0, 0.07, 0, 0, None, None)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
