@@ -466,9 +466,15 @@ int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, c
     else if (nch <= 16)
         segsum_kernel<16><<<nblocks(P * R * 16, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
                                                                     ncols & 3, dst, accumulate, rm);
-    else
+    else if (nch <= 32)
         segsum_kernel<32><<<nblocks(P * R * 32, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
                                                                     ncols & 3, dst, accumulate, rm);
+    else if (nch <= 64)      // wide rows of the small levels: more lanes per row, the bucket walk is the latency chain
+        segsum_kernel<64><<<nblocks(P * R * 64, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
+                                                                    ncols & 3, dst, accumulate, rm);
+    else
+        segsum_kernel<128><<<nblocks(P * R * 128, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
+                                                                      ncols & 3, dst, accumulate, rm);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
