@@ -206,6 +206,9 @@ int psg_clamp(float *x, int64_t count, float lo, float hi, psg_stream_t stream);
  * masked rows with pred == target (mask optional).  This buffer is what the NCCL all-reduce sums. */
 int psg_confusion_matrix(const float *logp, const int32_t *labels, const uint8_t *mask, int target, int64_t rows,
                          int ncls, int64_t *conf, psg_stream_t stream);
+/* library-wide switches for A/B measurements: "clusters" (default 1) = run the deep levels' tile programs on
+ * thread-block clusters (N split across CTAs, activations exchanged through distributed shared memory) */
+int psg_set_option(const char *name, int value);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t psg_launch_count(void);
 /* per-kernel-family device timing of the engine (CUDA event pairs on the launching stream);

@@ -159,9 +159,17 @@ __device__ __forceinline__ void pre_scatter(const TileSrc &s, unsigned char *pA,
     }
 }
 
-template <int NG>
+// CS > 1: a cluster of CS CTAs works on ONE tile (NG == 1); CTA q computes columns [q n/CS, (q+1) n/CS)
+// of every layer from the full A operand (replicated in each CTA), streams only its slice of the
+// weights, and its epilogue writes its activation slice into every CTA's A buffer through distributed
+// shared memory.  Synchronisation stays on mbarriers: the MMA commit is multicast to all CTAs'
+// accumulator barriers (nobody overwrites an operand a peer's MMA still reads) and the workers arrive
+// on all CTAs' operand barriers (nobody issues an MMA before every slice landed).  This is what lets
+// the deep levels -- few rows, large weights -- use more than one SM per tile.
+template <int NG, int CS>
 __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_constant__ TileArgs a)
 {
+    static_assert(CS == 1 || NG == 1, "cluster programs keep one tile in flight");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG], bar_full[kStages], bar_empty[kStages];
     __shared__ uint32_t tmem_slot;
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ncols = (uint32_t)(a.tcols * NG);
     if (threadIdx.x == 0) {
-        for (int g = 0; g < NG; ++g) { tc::mbar_init(tc::smem_u32(&bar_in[g]), kWorkers); tc::mbar_init(tc::smem_u32(&bar_acc[g]), 1); }
+        for (int g = 0; g < NG; ++g) { tc::mbar_init(tc::smem_u32(&bar_in[g]), kWorkers * CS); tc::mbar_init(tc::smem_u32(&bar_acc[g]), CS); }
         for (int s = 0; s < kStages; ++s) { tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1); }
         tc::fence_mbar_init();
     }
@@ -185,16 +193,20 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    if (CS > 1) tc::cluster_sync_all();            // peers' barriers exist before anyone arrives on them remotely
     const uint32_t tmem = tmem_slot;
-    const int tstride = gridDim.x * NG;
+    const int q = CS > 1 ? (int)tc::cluster_ctarank() : 0;
+    const int first_tile = (CS > 1 ? (int)blockIdx.x / CS : (int)blockIdx.x) * NG;
+    const int tstride = (CS > 1 ? (int)gridDim.x / CS : (int)gridDim.x) * NG;
 
     if (warp == NG * 4 + 1) {
         // ---------------- weight producer ----------------
         if (lane == 0) {
             int it = 0;
-            for (int tile0 = blockIdx.x * NG; tile0 < a.ntiles; tile0 += tstride) {
+            for (int tile0 = first_tile; tile0 < a.ntiles; tile0 += tstride) {
                 for (int o = 0; o < a.nops; ++o) {
                     const TileOp &op = a.ops[o];
+                    const int nl = op.n / CS;                     // this CTA's slice of the output columns
                     for (int pl = 0; pl < op.planes; pl += op.pps, ++it) {
                         const int np = min(op.pps, op.planes - pl);
                         const int slot = it % kStages;
@@ -202,13 +214,14 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                         tc::mbar_wait(tc::smem_u32(&bar_empty[slot]), ph ^ 1u);
                         const uint32_t full = tc::smem_u32(&bar_full[slot]);
                         const uint32_t dst = sW + slot * a.stage_bytes;
-                        tc::mbar_expect_tx(full, (uint32_t)np * op.n * 16);
-                        const float4 *wsrc = reinterpret_cast<const float4 *>(op.w) + (size_t)(op.wplane0 + pl) * op.wstride + op.wrow0;
-                        if (op.wstride == op.n) {
-                            tc::bulk_g2s(dst, wsrc, (uint32_t)np * op.n * 16, full);
+                        tc::mbar_expect_tx(full, (uint32_t)np * nl * 16);
+                        const float4 *wsrc = reinterpret_cast<const float4 *>(op.w) + (size_t)(op.wplane0 + pl) * op.wstride +
+                                             op.wrow0 + q * nl;
+                        if (op.wstride == nl) {
+                            tc::bulk_g2s(dst, wsrc, (uint32_t)np * nl * 16, full);
                         } else {
                             for (int j = 0; j < np; ++j)
-                                tc::bulk_g2s(dst + j * op.n * 16, wsrc + (size_t)j * op.wstride, (uint32_t)op.n * 16, full);
+                                tc::bulk_g2s(dst + j * nl * 16, wsrc + (size_t)j * op.wstride, (uint32_t)nl * 16, full);
                         }
                     }
                 }
@@ -221,10 +234,40 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
             uint32_t ph_in[NG];
 #pragma unroll
             for (int g = 0; g < NG; ++g) ph_in[g] = 0u;
-            for (int tile0 = blockIdx.x * NG; tile0 < a.ntiles; tile0 += tstride) {
+            for (int tile0 = first_tile; tile0 < a.ntiles; tile0 += tstride) {
                 for (int o = 0; o < a.nops; ++o) {
                     const TileOp &op = a.ops[o];
-                    const uint32_t idesc = tc::idesc_tf32(128, op.n);
+                    const int nl = op.n / CS;
+                    const uint32_t idesc = tc::idesc_tf32(128, nl);
+                    const int nst = (op.planes + op.pps - 1) / op.pps;
+                    if (NG == 2 && nst <= kStages) {
+                        // Tile-major order (the whole op fits in the ring): tile 0's accumulator completes after
+                        // ITS MMAs only, so its epilogue overlaps tile 1's MMAs and vice versa on the next op.
+                        const int glast = (tile0 + 1 < a.ntiles) ? 1 : 0;
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            if (g > glast) continue;
+                            tc::mbar_wait(tc::smem_u32(&bar_in[g]), ph_in[g]); ph_in[g] ^= 1u;
+                            for (int si = 0; si < nst; ++si) {
+                                const int pl = si * op.pps;
+                                const int np = min(op.pps, op.planes - pl);
+                                const int slot = (it + si) % kStages;
+                                if (g == 0) tc::mbar_wait(tc::smem_u32(&bar_full[slot]), (uint32_t)((it + si) / kStages) & 1u);
+                                tc::fence_after_sync();
+                                const uint32_t sA = sA0 + g * a.abytes + (uint32_t)(op.aplane0 + pl) * 2048u;
+                                const uint32_t sB = sW + slot * a.stage_bytes;
+                                for (int j = 0; j < np; j += 2) {
+                                    const uint64_t ad = tc::smem_desc(sA + j * 2048, 2048, 128);
+                                    const uint64_t bd = tc::smem_desc(sB + j * nl * 16, (uint32_t)(nl * 16), 128);
+                                    tc::mma_tf32(tmem + g * a.tcols, ad, bd, idesc, (op.accumulate || pl > 0 || j > 0) ? 1u : 0u);
+                                }
+                                if (g == glast) tc::mma_commit(tc::smem_u32(&bar_empty[slot]));
+                            }
+                            tc::mma_commit(tc::smem_u32(&bar_acc[g]));
+                        }
+                        it += nst;
+                        continue;
+                    }
                     for (int pl = 0; pl < op.planes; pl += op.pps, ++it) {
                         const int np = min(op.pps, op.planes - pl);
                         const int slot = it % kStages;
@@ -233,16 +276,23 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
                             if (tile0 + g >= a.ntiles) continue;
-                            if (pl == 0) { tc::mbar_wait(tc::smem_u32(&bar_in[g]), ph_in[g]); ph_in[g] ^= 1u; }
+                            if (pl == 0) {
+                                if (CS > 1) tc::mbar_wait_cluster(tc::smem_u32(&bar_in[g]), ph_in[g]);
+                                else tc::mbar_wait(tc::smem_u32(&bar_in[g]), ph_in[g]);
+                                ph_in[g] ^= 1u;
+                            }
                             tc::fence_after_sync();
                             const uint32_t sA = sA0 + g * a.abytes + (uint32_t)(op.aplane0 + pl) * 2048u;
                             const uint32_t sB = sW + slot * a.stage_bytes;
                             for (int j = 0; j < np; j += 2) {
                                 const uint64_t ad = tc::smem_desc(sA + j * 2048, 2048, 128);
-                                const uint64_t bd = tc::smem_desc(sB + j * op.n * 16, (uint32_t)(op.n * 16), 128);
+                                const uint64_t bd = tc::smem_desc(sB + j * nl * 16, (uint32_t)(nl * 16), 128);
                                 tc::mma_tf32(tmem + g * a.tcols, ad, bd, idesc, (op.accumulate || pl > 0 || j > 0) ? 1u : 0u);
                             }
-                            if (last) tc::mma_commit(tc::smem_u32(&bar_acc[g]));
+                            if (last) {
+                                if (CS > 1) tc::mma_commit_mc(tc::smem_u32(&bar_acc[g]), (uint16_t)((1u << CS) - 1u));
+                                else tc::mma_commit(tc::smem_u32(&bar_acc[g]));
+                            }
                         }
                         tc::mma_commit(tc::smem_u32(&bar_empty[slot]));     // stage free once every tile consumed it
                     }
@@ -261,101 +311,121 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
         const int k = r % K;
         const unsigned gmask = (K == 32) ? 0xffffffffu : (0xffffu << (16 * (lane / 16)));
         uint32_t ph = 0;
-        for (int tile = blockIdx.x * NG + grp; tile < a.ntiles; tile += tstride) {
+        // write 16 bytes of the A operand here and, in a cluster, at the same place in every peer CTA
+        auto put = [&](int chunk, float4 val) {
+            float4 *dstp = plane_ptr(pA, chunk, r);
+            *dstp = val;
+            if (CS > 1) {
+                const uint32_t la = tc::smem_u32(dstp);
+#pragma unroll
+                for (int pr = 0; pr < CS; ++pr)
+                    if (pr != q) tc::st_cluster_v4(tc::mapa(la, (uint32_t)pr), val);
+            }
+        };
+        for (int tile = first_tile + grp; tile < a.ntiles; tile += tstride) {
             const long long row = (long long)tile * 128 + r;
             const bool valid = row < a.rows;
             for (int o = 0; o < a.nops; ++o) {
                 const TileOp &op = a.ops[o];
+                const int nl = op.n / CS, c0l = q * nl;        // this CTA's output columns [c0l, c0l + nl)
                 // ---- refill the A operand, hand it to the MMA thread ----
                 if (op.pre == PRE_GROUP) pre_group(a.src, pA, row, valid, r);
                 else if (op.pre == PRE_FP) { if (a.src.lcols) pre_load(a.src, pA, row, valid, r); pre_interp(a.src, pA, row, valid, r); }
                 else if (op.pre == PRE_LOAD) pre_load(a.src, pA, row, valid, r);
                 else if (op.pre == PRE_SCATTER) pre_scatter(a.src, pA, row, valid, r, op.pre_a, op.planes);
                 tc::fence_before_sync();
-                tc::fence_async_smem();
-                tc::mbar_arrive(b_in);
+                if (CS > 1) {
+                    tc::fence_async_all();
+#pragma unroll
+                    for (int pr = 0; pr < CS; ++pr) tc::mbar_arrive_cluster(tc::mapa(b_in, (uint32_t)pr));
+                } else {
+                    tc::fence_async_smem();
+                    tc::mbar_arrive(b_in);
+                }
                 // ---- epilogue ----
-                tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+                if (CS > 1) tc::mbar_wait_cluster(b_acc, ph); else tc::mbar_wait(b_acc, ph);
+                ph ^= 1u; tc::fence_after_sync();
                 const int words = (op.n + 31) / 32;
+                const int w0l = c0l >> 5;
                 if (op.epi == EPI_RELU) {
                     int c = 0;
-                    for (; c + 32 <= op.n; c += 32) {
+                    for (; c + 32 <= nl; c += 32) {
                         float v[32];
                         tc::tmem_ld32(tl + (uint32_t)c, v);
-                        const unsigned w = psg_relu_bias_bits<32>(v, op.bias + c);
+                        const unsigned w = psg_relu_bias_bits<32>(v, op.bias + c0l + c);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *plane_ptr(pA, (c >> 2) + q, r) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (op.slot >= 0) mbits[((size_t)op.slot * 8 + (c >> 5)) * 128 + r] = w;
-                        if (op.mglobal) op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r] = w;
+                        for (int j = 0; j < 8; ++j)
+                            put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                        if (op.slot >= 0) mbits[((size_t)op.slot * 8 + w0l + (c >> 5)) * 128 + r] = w;
+                        if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
-                    if (c < op.n) {
+                    if (c < nl) {
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c, v);
-                        const unsigned w = psg_relu_bias_bits<16>(v, op.bias + c);
+                        const unsigned w = psg_relu_bias_bits<16>(v, op.bias + c0l + c);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *plane_ptr(pA, (c >> 2) + q, r) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (op.slot >= 0) mbits[((size_t)op.slot * 8 + (c >> 5)) * 128 + r] = w;
-                        if (op.mglobal) op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r] = w;
+                        for (int j = 0; j < 4; ++j)
+                            put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                        if (op.slot >= 0) mbits[((size_t)op.slot * 8 + w0l + (c >> 5)) * 128 + r] = w;
+                        if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
                 } else if (op.epi == EPI_MASK) {
                     int c = 0;
-                    for (; c + 32 <= op.n; c += 32) {
-                        const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r]
-                                                      : mbits[((size_t)op.slot * 8 + (c >> 5)) * 128 + r];
+                    for (; c + 32 <= nl; c += 32) {
+                        const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r]
+                                                      : mbits[((size_t)op.slot * 8 + w0l + (c >> 5)) * 128 + r];
                         float v[32];
                         tc::tmem_ld32(tl + (uint32_t)c, v);
                         psg_apply_bits<32>(v, w);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *plane_ptr(pA, (c >> 2) + q, r) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                     }
-                    if (c < op.n) {
-                        const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r]
-                                                      : mbits[((size_t)op.slot * 8 + (c >> 5)) * 128 + r];
+                    if (c < nl) {
+                        const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r]
+                                                      : mbits[((size_t)op.slot * 8 + w0l + (c >> 5)) * 128 + r];
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c, v);
                         psg_apply_bits<16>(v, w);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *plane_ptr(pA, (c >> 2) + q, r) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        for (int j = 0; j < 4; ++j)
+                            put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                     }
                 } else if (op.epi == EPI_STORE) {
                     int c = 0;
-                    for (; c + 32 <= op.n; c += 32) {
+                    for (; c + 32 <= nl; c += 32) {
                         float v[32];
                         tc::tmem_ld32(tl + (uint32_t)c, v);
                         unsigned w = 0;
-                        if (op.relu) w = psg_relu_bias_bits<32>(v, op.bias + c);
+                        if (op.relu) w = psg_relu_bias_bits<32>(v, op.bias + c0l + c);
                         if (valid) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                tv_st(op.out, row, (c >> 2) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                            for (int j = 0; j < 8; ++j)
+                                tv_st(op.out, row, ((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                         }
-                        if (op.mglobal) op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r] = w;
+                        if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
-                    if (c < op.n) {
+                    if (c < nl) {
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c, v);
                         unsigned w = 0;
-                        if (op.relu) w = psg_relu_bias_bits<16>(v, op.bias + c);
+                        if (op.relu) w = psg_relu_bias_bits<16>(v, op.bias + c0l + c);
                         if (valid) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                tv_st(op.out, row, (c >> 2) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                            for (int j = 0; j < 4; ++j)
+                                tv_st(op.out, row, ((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                         }
-                        if (op.mglobal) op.mglobal[((size_t)tile * words + (c >> 5)) * 128 + r] = w;
+                        if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
                 } else if (op.epi == EPI_MAXPOOL) {
                     const long long g = row / K;
-                    for (int c16 = 0; c16 < op.n; c16 += 16) {
+                    for (int c16 = 0; c16 < nl; c16 += 16) {
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c16, v);
                         unsigned am[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const unsigned b = __float_as_uint(fmaxf(v[i] + __ldg(op.bias + c16 + i), 0.f));
+                            const unsigned b = __float_as_uint(fmaxf(v[i] + __ldg(op.bias + c0l + c16 + i), 0.f));
                             const unsigned mx = __reduce_max_sync(gmask, b);
                             am[i] = __reduce_min_sync(gmask, b == mx ? (unsigned)k : 64u);
                             v[i] = __uint_as_float(mx);
@@ -363,16 +433,16 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                         if (k == 0 && valid) {
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
-                                tv_st(op.out, g, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                                tv_st(op.out, g, ((c0l + c16) >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
                             uint4 pk;
                             pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
                             pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
                             pk.z = am[8] | (am[9] << 8) | (am[10] << 16) | (am[11] << 24);
                             pk.w = am[12] | (am[13] << 8) | (am[14] << 16) | (am[15] << 24);
-                            *reinterpret_cast<uint4 *>(op.arg + g * op.argC + op.arg0 + c16) = pk;
+                            *reinterpret_cast<uint4 *>(op.arg + g * op.argC + op.arg0 + c0l + c16) = pk;
                         }
                     }
-                } else if (op.epi == EPI_HEAD) {
+                } else if (op.epi == EPI_HEAD) {          // CS == 1 only (16 logit columns do not split)
                     float v[16], dz[16];
                     tc::tmem_ld16(tl, v);
 #pragma unroll
@@ -397,9 +467,9 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                         }
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            float4 q = make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
-                            if (!valid) q = make_float4(0.f, 0.f, 0.f, 0.f);
-                            *plane_ptr(pA, c, r) = q;
+                            float4 qv = make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+                            if (!valid) qv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            *plane_ptr(pA, c, r) = qv;
                         }
                     }
                 }
@@ -410,11 +480,12 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
     }
     tc::fence_before_sync();
     __syncthreads();
+    if (CS > 1) tc::cluster_sync_all();            // no CTA exits while a peer may still write into it
     if (warp == NG * 4) tc::tmem_dealloc(tmem, ncols);
 }
 
 int g_sms = 0;
-inline int g_sms_hint() { return g_sms > 0 ? g_sms : 148; }
+bool g_use_clusters = true;
 constexpr size_t kSmemMax = 225 * 1024;
 
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
@@ -439,46 +510,91 @@ struct Builder {
     void want_a(int cols) { if (cols > amax_cols) amax_cols = cols; }
 };
 
-// choose NG / stage size to fit shared memory, fill the derived fields, launch
+// cluster size for a program: the largest CS in {4, 2} such that every tile still gets its own cluster
+// in one wave and every op's columns split into whole 16-column (32 for masked layers) slices
+int pick_cluster(const TileArgs &a, int ntiles, int sms)
+{
+    for (int cs = 4; cs >= 2; cs >>= 1) {
+        if (ntiles * cs > sms) continue;
+        bool ok = true;
+        for (int o = 0; o < a.nops && ok; ++o) {
+            const TileOp &op = a.ops[o];
+            if (op.epi == EPI_HEAD) ok = false;
+            const int unit = (op.epi == EPI_RELU || op.epi == EPI_MASK || op.mglobal) ? 32 : 16;
+            if (op.n % (unit * cs)) ok = false;
+        }
+        if (ok) return cs;
+    }
+    return 1;
+}
+
+template <int NG, int CS>
+int launch_tile(const TileArgs &a, int grid, size_t smem, cudaStream_t st)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(tile_kernel<NG, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
+            return PSG_ECUDA;
+        attr_done = true;
+    }
+    if (CS == 1) {
+        tile_kernel<NG, CS><<<grid, NG * 128 + 64, smem, st>>>(a);
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NG * 128 + 64); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, tile_kernel<NG, CS>, a) != cudaSuccess) return PSG_ECUDA;
+    }
+    return PSG_OK;
+}
+
+// choose cluster size / NG / stage size to fit shared memory, fill the derived fields, launch
 int launch_program(Builder &b, long long rows, cudaStream_t st)
 {
     if (!b.ok || b.a.nops < 1) return PSG_EUNSUPPORTED;
     TileArgs &a = b.a;
+    if (g_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return PSG_ECUDA;
+    }
     a.rows = rows; a.ntiles = (int)((rows + 127) / 128);
     a.abytes = b.amax_cols * 512;
-    a.tcols = (int)pow2cols(b.nmax);
+    const int cs = g_use_clusters ? pick_cluster(a, a.ntiles, g_sms) : 1;
+    a.tcols = (int)pow2cols(b.nmax / cs);
     auto need = [&](int ng, int stg) {
         return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * kMaskSlots * 8 * 128 * 4 + 1024;
     };
     // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
-    int ng = (a.ntiles > g_sms_hint() && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
+    int ng = (cs == 1 && a.ntiles > g_sms && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
     int stage = need(ng, 32 * 1024) <= kSmemMax ? 32 * 1024 : 16 * 1024;
     if (need(ng, stage) > kSmemMax || a.tcols * ng > 512) return PSG_EUNSUPPORTED;
     a.stage_bytes = stage;
     for (int o = 0; o < a.nops; ++o) {
         TileOp &op = a.ops[o];
-        int pps = stage / (op.n * 16);
+        int pps = stage / ((op.n / cs) * 16);
         pps &= ~1;
         if (pps < 2) return PSG_EUNSUPPORTED;
         op.pps = pps < op.planes ? pps : op.planes;
     }
-    const size_t smem = (size_t)ng * a.abytes + (size_t)kStages * stage + (size_t)ng * kMaskSlots * 8 * 128 * 4 + 1024;
-    if (g_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            return PSG_ECUDA;
-        if (cudaFuncSetAttribute(tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess ||
-            cudaFuncSetAttribute(tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
-            return PSG_ECUDA;
+    const size_t smem = need(ng, stage);
+    int rc;
+    if (cs == 1) {
+        const int want = (a.ntiles + ng - 1) / ng;
+        const int grid = want < g_sms ? want : g_sms;
+        rc = ng == 2 ? launch_tile<2, 1>(a, grid, smem, st) : launch_tile<1, 1>(a, grid, smem, st);
+    } else {
+        const int grid = a.ntiles * cs;                     // one cluster per tile, all resident in one wave
+        rc = cs == 4 ? launch_tile<1, 4>(a, grid, smem, st) : launch_tile<1, 2>(a, grid, smem, st);
     }
-    const int want = (a.ntiles + ng - 1) / ng;
-    const int grid = want < g_sms ? want : g_sms;
-    if (ng == 2) tile_kernel<2><<<grid, 2 * 128 + 64, smem, st>>>(a);
-    else tile_kernel<1><<<grid, 128 + 64, smem, st>>>(a);
+    if (rc != PSG_OK) return rc;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
-
 
 }  // namespace
 
@@ -557,9 +673,12 @@ int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cuda
 {
     Builder b;
     TileOp *o = nullptr;
-    // dY1 = dY2 W2, contraction over n2 in <= 256-column slabs (the scatter refills the A buffer per slab)
-    for (int c0 = 0; c0 < f.n[2]; c0 += 256) {
-        const int kc = f.n[2] - c0 < 256 ? f.n[2] - c0 : 256;
+    // dY1 = dY2 W2, contraction over n2 in slabs (the scatter refills the A buffer per slab); a slab is no
+    // wider than the hidden layers need the buffer to be anyway, so narrow levels keep two tiles in flight
+    int slab = f.n[0] > f.n[1] ? f.n[0] : f.n[1];
+    slab = slab < 128 ? 128 : (slab > 256 ? 256 : slab);
+    for (int c0 = 0; c0 < f.n[2]; c0 += slab) {
+        const int kc = f.n[2] - c0 < slab ? f.n[2] - c0 : slab;
         o = b.add(f.wb[2], f.nwb[2], 0, c0 / 4, f.n[1], kc / 4, 0);
         o->pre = PRE_SCATTER; o->pre_a = c0; o->accumulate = c0 > 0 ? 1 : 0; o->epi = EPI_NONE;
     }
@@ -632,3 +751,6 @@ int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStrea
     b.want_a(f.n[f.nl - 1]);
     return launch_program(b, f.rows, st);
 }
+
+// thread-block clusters for the deep levels (on by default; the switch exists for A/B measurements)
+void psg_tile_use_clusters(bool on) { g_use_clusters = on; }

@@ -367,6 +367,13 @@ extern "C" int psg_net_set_mlp_mode(psg_net *n, int mode)
 
 static PsgFpStream fp_stream_desc(psg_net *n, int f, int t, TView coarse);
 
+extern "C" int psg_set_option(const char *name, int value)
+{
+    if (!name) return PSG_EINVAL;
+    if (!strcmp(name, "clusters")) { psg_tile_use_clusters(value != 0); return PSG_OK; }
+    return PSG_EINVAL;
+}
+
 extern "C" int psg_net_set_xyz_grad(psg_net *n, int on)
 {
     if (!n) return PSG_EINVAL;
