@@ -128,7 +128,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    sps, cores, sample, dt = cpu_reference(min(steps, 24), args.warmup, sample_blocks=4)
+    sps, cores, sample, dt = cpu_reference(min(steps, 48), args.warmup, sample_blocks=4)
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak",
@@ -297,7 +297,7 @@ def run_native(args, rank, world, local_rank):
         if args.no_cpu:
             cpu = None
         else:
-            sps, cores, sample, _ = cpu_reference(12, 1, sample_blocks=4)
+            sps, cores, sample, _ = cpu_reference(40, 1, sample_blocks=4)
             cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

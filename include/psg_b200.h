@@ -207,7 +207,9 @@ int psg_clamp(float *x, int64_t count, float lo, float hi, psg_stream_t stream);
 int psg_confusion_matrix(const float *logp, const int32_t *labels, const uint8_t *mask, int target, int64_t rows,
                          int ncls, int64_t *conf, psg_stream_t stream);
 /* library-wide switches for A/B measurements: "clusters" (default 1) = run the deep levels' tile programs on
- * thread-block clusters (N split across CTAs, activations exchanged through distributed shared memory) */
+ * thread-block clusters (N split across CTAs, activations exchanged through distributed shared memory);
+ * "sm_cap" (default 0 = all) = spread persistent launches over at most that many SMs, so that sub-batches
+ * enqueued on different streams share the GPU instead of queueing behind each other */
 int psg_set_option(const char *name, int value);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t psg_launch_count(void);

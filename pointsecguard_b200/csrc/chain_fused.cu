@@ -564,13 +564,14 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     }
     a.rows = rows; a.ntiles = (int)((rows + 127) / 128);
     a.abytes = b.amax_cols * 512;
-    const int cs = g_use_clusters ? pick_cluster(a, a.ntiles, g_sms) : 1;
+    const int sms = (g_psg_sm_cap > 0 && g_psg_sm_cap < g_sms) ? g_psg_sm_cap : g_sms;
+    const int cs = g_use_clusters ? pick_cluster(a, a.ntiles, sms) : 1;
     a.tcols = (int)pow2cols(b.nmax / cs);
     auto need = [&](int ng, int stg) {
         return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * kMaskSlots * 8 * 128 * 4 + 1024;
     };
     // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
-    int ng = (cs == 1 && a.ntiles > g_sms && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
+    int ng = (cs == 1 && a.ntiles > sms && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
     int stage = need(ng, 32 * 1024) <= kSmemMax ? 32 * 1024 : 16 * 1024;
     if (need(ng, stage) > kSmemMax || a.tcols * ng > 512) return PSG_EUNSUPPORTED;
     a.stage_bytes = stage;
@@ -585,7 +586,7 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     int rc;
     if (cs == 1) {
         const int want = (a.ntiles + ng - 1) / ng;
-        const int grid = want < g_sms ? want : g_sms;
+        const int grid = want < sms ? want : sms;
         rc = ng == 2 ? launch_tile<2, 1>(a, grid, smem, st) : launch_tile<1, 1>(a, grid, smem, st);
     } else {
         const int grid = a.ntiles * cs;                     // one cluster per tile, all resident in one wave

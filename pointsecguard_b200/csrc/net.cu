@@ -22,6 +22,7 @@
 #include "psg_internal.h"
 
 long long g_psg_launch_count = 0;
+int g_psg_sm_cap = 0;
 
 // ------------------------------------------------------------------------------------------------
 // per-kernel-family device timing (bench.py's live roofline measurement).  When enabled, every
@@ -371,6 +372,7 @@ extern "C" int psg_set_option(const char *name, int value)
 {
     if (!name) return PSG_EINVAL;
     if (!strcmp(name, "clusters")) { psg_tile_use_clusters(value != 0); return PSG_OK; }
+    if (!strcmp(name, "sm_cap")) { g_psg_sm_cap = value > 0 ? value : 0; return PSG_OK; }
     return PSG_EINVAL;
 }
 

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
                 const long long srow = (long long)cloud * a.Nsrc + src;
                 const int D = a.D;
                 const int nfull = D >> 2;                 // chunks that are features only
-#pragma unroll 4
+#pragma unroll 8
                 for (int c = 0; c < nfull; ++c) {
                     float4 v = valid ? tv_ld(a.feats, srow, c) : make_float4(0.f, 0.f, 0.f, 0.f);
                     *plane_ptr(pA, c, r) = v;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
             const bool valid = row < a.rows;
             const long long g = (valid ? row : 0) / K;
             // ---- dY2[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0 ----
-#pragma unroll 4
+#pragma unroll 8
             for (int c = 0; c < a.n2 / 4; ++c) {
                 const float4 d = tv_ld(a.dout, g, c);
                 const float4 o = tv_ld(a.outv, g, c);
@@ -455,7 +455,8 @@ int launch_cfg(Kern kern, size_t smem, int ntiles, int ng, int tmem_cols, int *g
     }
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
     const int want = (ntiles + ng - 1) / ng;
-    const int cap = g_num_sms * ctas_per_sm(smem, tmem_cols);
+    const int sms = (g_psg_sm_cap > 0 && g_psg_sm_cap < g_num_sms) ? g_psg_sm_cap : g_num_sms;
+    const int cap = sms * ctas_per_sm(smem, tmem_cols);
     *grid = want < cap ? want : cap;
     return PSG_OK;
 }

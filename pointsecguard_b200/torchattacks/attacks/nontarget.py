@@ -53,6 +53,11 @@ def _nb_loop(atk, images, labels, target, mask):
     # reference's draw, pointnet_util.py:75) and sliced.
     nsub = _sub_batches(atk.model, B)
     engs, streams = atk.model.sub_engines(dev, nsub)
+    if nsub > 1:
+        # each sub-batch's persistent kernels take an equal share of the SMs, so the streams really overlap
+        from pointsecguard_b200 import _lib as L
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        L.psg_set_option(b"sm_cap", max(1, sms // nsub))
     whole = eng.shard if eng.shard is not None else D.Shard(B, 0, B)
     parts = [D.shard_for(B, i, nsub) for i in range(nsub)]
     chunk = max(1, min(atk.iters, _MAX_PROBLEMS // B))
@@ -85,6 +90,8 @@ def _nb_loop(atk, images, labels, target, mask):
                 join.record(st_)
                 cur.wait_event(join)
             e.use_stream(None)
+        if nsub > 1:
+            L.psg_set_option(b"sm_cap", 0)
     atk.model._generation += 1
     return adv
 
