@@ -110,7 +110,7 @@ def cpu_reference(steps, warmup, sample_blocks=2):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     PO.GEOMETRY = "torch"          # op-for-op the reference's geometry (Python FPS loop, matmul + sort)
-    model = PO.OracleModel(syn.make_state_dict("ssg"), "ssg")
+    model = PO.OracleModel(syn.make_state_dict("ssg", init="he"), "ssg")
     x, labels, mask = make_inputs(sample_blocks, 0)
     torch.manual_seed(0)
     if warmup > 0:
@@ -164,7 +164,8 @@ def run_native(args, rank, world, local_rank):
     from pointsecguard_b200.models.pointnet2_sem_seg import get_model
 
     model = get_model(13)
-    model.load_state_dict(syn.make_state_dict("ssg"))
+    # init="he": a random network whose predictions depend on the input, so attack_metrics are informative
+    model.load_state_dict(syn.make_state_dict("ssg", init="he"))
     model = model.to(dev).eval()
     if args.mlp == "tf32":
         model.set_mlp_mode(MLP_TF32)

@@ -129,8 +129,16 @@ def _bn_keys(prefix, c):
     ]
 
 
-def make_state_dict(arch: str = "ssg", seed: int = 1234, randomize_bn: bool = True) -> "OrderedDict[str, torch.Tensor]":
+def make_state_dict(arch: str = "ssg", seed: int = 1234, randomize_bn: bool = True,
+                    init: str = "default") -> "OrderedDict[str, torch.Tensor]":
     """A random checkpoint with the reference's key names and shapes.
+
+    ``init="default"`` (what the golden vectors were made with) uses PyTorch's default conv scale, under
+    which the signal shrinks layer by layer and the random network predicts one class everywhere -- fine
+    for numerics parity, useless for attack-success metrics.  ``init="he"`` draws conv weights from
+    U(+-sqrt(6 / fan_in)) (variance-preserving through ReLU) with zero conv biases and keeps BatchNorm
+    near identity, which gives a network whose per-point predictions depend on the input, so that the
+    attacks visibly move accuracy / mIoU / target hit-rate.
 
     Conv weights/biases ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (PyTorch's default scale).  With
     ``randomize_bn`` the BatchNorm affine parameters and running statistics are randomised too
@@ -142,6 +150,14 @@ def make_state_dict(arch: str = "ssg", seed: int = 1234, randomize_bn: bool = Tr
     for key, shape, kind in state_dict_spec(arch):
         if kind == "bn_n":
             sd[key] = torch.tensor(0, dtype=torch.int64)
+        elif init == "he" and kind in ("bn_w", "bn_v", "bn_b", "bn_m"):
+            r = torch.rand(shape, generator=g)
+            sd[key] = {"bn_w": 0.9 + 0.2 * r, "bn_v": 0.9 + 0.2 * r, "bn_b": 0.02 * (r - 0.5), "bn_m": 0.02 * (r - 0.5)}[kind]
+        elif init == "he" and key.endswith(".bias"):
+            torch.rand(shape, generator=g)
+            sd[key] = torch.zeros(shape)
+        elif init == "he":
+            sd[key] = (torch.rand(shape, generator=g) * 2.0 - 1.0) * math.sqrt(6.0 / kind)
         elif kind == "bn_w":
             sd[key] = torch.rand(shape, generator=g) + 0.5 if randomize_bn else torch.ones(shape)
         elif kind == "bn_v":

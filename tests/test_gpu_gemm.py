@@ -130,3 +130,40 @@ def test_model_tf32_gradient_close_to_fp32(arch):
     zero_same = ((g1 == 0) == (g0 == 0)).float().mean().item()
     print(f"{arch}: tf32 vs fp32 |dlogp| {err:.2e} l4 rel {l4err:.2e} grad rel {rel:.2e} sign {sign:.5f} zero-pattern {zero_same:.5f}")
     assert err < 5e-3 and l4err < 5e-3 and rel < 8e-2 and sign > 0.99 and zero_same > 0.999
+
+
+def test_attack_metrics_tf32_vs_fp32_within_half_a_point():
+    """north_star gate: accuracy / mIoU / attack success after the attack agree within +-0.5 pt between
+    the tcgen05 TF32 path and the fp32 parity path (same seeds, bit-identical geometry)."""
+    from pointsecguard_b200 import metrics as MT, synthetic as syn, torchattacks
+    from pointsecguard_b200.engine import MLP_FP32, MLP_TF32
+    from pointsecguard_b200.models.pointnet2_sem_seg import get_model
+    m = get_model(13)
+    m.load_state_dict(syn.make_state_dict("ssg", init="he"))  # input-sensitive random network (synthetic.py)
+    m = m.cuda().eval()
+    x = syn.make_blocks(16, 4096, 3).cuda()                   # 65536 points: the gate is on aggregate metrics
+    torch.manual_seed(5)
+    lab = m(x)[0].argmax(2)                                  # clean predictions: initial accuracy 100 %
+    zl = syn.zband_labels(x.cpu())
+    mask = zl == 11
+    res = {}
+    for mode in (MLP_FP32, MLP_TF32):
+        m.set_mlp_mode(mode)
+        torch.manual_seed(0)
+        adv = torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=10)(x, lab.cpu().numpy().astype(np.float64))
+        torch.manual_seed(1)
+        s1 = MT.summarize(MT.attack_counters(m(adv)[0], lab))
+        torch.manual_seed(0)
+        advt = torchattacks.tar_NB_attack(m, eps=0.5, alpha=0.1, iters=10, target=7, mask=mask)(x, zl.numpy().astype(np.float64))
+        torch.manual_seed(1)
+        s2 = MT.summarize(MT.attack_counters(m(advt)[0], zl.cuda(), mask.cuda(), 7))
+        res[mode] = (s1, s2, adv)
+    m.set_mlp_mode(MLP_FP32)
+    (a1, a2, adv0), (b1, b2, adv1) = res[MLP_FP32], res[MLP_TF32]
+    print("NB  fp32", a1, "\n    tf32", b1, "\ntar fp32", a2, "\n    tf32", b2)
+    same = (adv0 == adv1).float().mean().item()
+    print("identical perturbed elements fp32 vs tf32:", same)
+    assert abs(a1["acc"] - b1["acc"]) < 0.005 and abs(a1["miou"] - b1["miou"]) < 0.005
+    assert abs(a2["acc"] - b2["acc"]) < 0.005 and abs(a2["miou"] - b2["miou"]) < 0.005
+    assert abs((a2["target_acc"] or 0) - (b2["target_acc"] or 0)) < 0.005
+    assert a1["acc"] < 0.9                                   # the attack did something

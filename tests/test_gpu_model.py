@@ -209,3 +209,35 @@ def test_coordinate_gradient_vs_reference_golden(golden_dir, arch):
     assert rel < 2e-2 and sign > 0.995
     rel_all, sign_all, _ = _grad_report(mine, g["grad"])
     assert rel_all < 2e-2 and sign_all > 0.998
+
+
+def test_attack_metrics_vs_oracle_within_half_a_point():
+    """north_star gate: accuracy and mIoU after N attack iterations agree with the CPU oracle within
+    +-0.5 pt.  Uses the input-sensitive synthetic checkpoint (init="he"), on which the attack really
+    flips predictions (the default-scale checkpoint predicts one class everywhere)."""
+    from oracle import attacks_oracle as AO
+    from oracle import pointnet2_oracle as PO
+    from pointsecguard_b200 import metrics as MT, torchattacks
+    from pointsecguard_b200.models.pointnet2_sem_seg import get_model
+    sd = syn.make_state_dict("ssg", init="he")
+    m = get_model(13)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    om = PO.OracleModel(sd, "ssg")
+    x = syn.make_blocks(2, 2048, 3)
+    torch.manual_seed(5)
+    lab = om(x)[0].argmax(2)
+    torch.manual_seed(0)
+    ref = AO.nb_attack(om, x, lab.numpy().astype(np.float64), eps=0.1, alpha=0.05, iters=5)
+    torch.manual_seed(1)
+    ref_pred = om(ref)[0].argmax(2)
+    ref_m = AO.block_metrics(ref_pred.numpy(), lab.numpy().astype(np.float64))
+    torch.manual_seed(0)
+    adv = torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=5)(x.cuda(), lab.numpy().astype(np.float64))
+    torch.manual_seed(1)
+    mine = MT.summarize(MT.attack_counters(m(adv)[0], lab.cuda()))
+    same = (adv[:, 3:6].cpu() == ref[:, 3:6]).float().mean().item()
+    print(f"oracle acc {ref_m['acc']:.4f} miou {ref_m['miou']:.4f} | gpu acc {mine['acc']:.4f} miou {mine['miou']:.4f} | identical {same:.4f}")
+    assert ref_m["acc"] < 0.95                                # the attack moved the predictions
+    assert abs(mine["acc"] - ref_m["acc"]) < 0.005 and abs(mine["miou"] - ref_m["miou"]) < 0.005
+    assert same > 0.99
