@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
     __syncthreads();
     tc::fence_after_sync();
     if (CS > 1) tc::cluster_sync_all();            // peers' barriers exist before anyone arrives on them remotely
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();                                // everything above overlapped the previous kernel's tail
     const uint32_t tmem = tmem_slot;
     const int q = CS > 1 ? (int)tc::cluster_ctarank() : 0;
     const int first_tile = (CS > 1 ? (int)blockIdx.x / CS : (int)blockIdx.x) * NG;
@@ -537,18 +539,8 @@ int launch_tile(const TileArgs &a, int grid, size_t smem, cudaStream_t st)
             return PSG_ECUDA;
         attr_done = true;
     }
-    if (CS == 1) {
-        tile_kernel<NG, CS><<<grid, NG * 128 + 64, smem, st>>>(a);
-    } else {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NG * 128 + 64); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, tile_kernel<NG, CS>, a) != cudaSuccess) return PSG_ECUDA;
-    }
+    if (psg_launch_pdl(tile_kernel<NG, CS>, dim3((unsigned)grid), dim3(NG * 128 + 64), smem, st, CS, a) != cudaSuccess)
+        return PSG_ECUDA;
     return PSG_OK;
 }
 

@@ -297,6 +297,8 @@ segsum_kernel(TView src, long long src_rows_per_p, int div, const float *__restr
               const int *__restrict__ offs, const int *__restrict__ perm, int M, int R, long long P,
               int nch, int tail_cols, TView dst, int accumulate, TView rmask)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // launched with programmatic stream serialization
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long wid = gid / LPR;                 // destination row
     const int lane = (int)(gid % LPR);
@@ -457,24 +459,26 @@ int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, c
 {
     TView rm = relu_mask ? *relu_mask : TView{nullptr, 0, 0};
     const int nch = (ncols + 3) / 4;
+    cudaError_t err = cudaSuccess;
     if (nch <= 4)
-        segsum_kernel<4><<<nblocks(P * R * 4, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
-                                                                  ncols & 3, dst, accumulate, rm);
+        err = psg_launch_pdl(segsum_kernel<4>, dim3(nblocks(P * R * 4, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
     else if (nch <= 8)
-        segsum_kernel<8><<<nblocks(P * R * 8, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
-                                                                  ncols & 3, dst, accumulate, rm);
+        err = psg_launch_pdl(segsum_kernel<8>, dim3(nblocks(P * R * 8, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
     else if (nch <= 16)
-        segsum_kernel<16><<<nblocks(P * R * 16, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
-                                                                    ncols & 3, dst, accumulate, rm);
+        err = psg_launch_pdl(segsum_kernel<16>, dim3(nblocks(P * R * 16, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
     else if (nch <= 32)
-        segsum_kernel<32><<<nblocks(P * R * 32, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
-                                                                    ncols & 3, dst, accumulate, rm);
+        err = psg_launch_pdl(segsum_kernel<32>, dim3(nblocks(P * R * 32, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
     else if (nch <= 64)      // wide rows of the small levels: more lanes per row, the bucket walk is the latency chain
-        segsum_kernel<64><<<nblocks(P * R * 64, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
-                                                                    ncols & 3, dst, accumulate, rm);
+        err = psg_launch_pdl(segsum_kernel<64>, dim3(nblocks(P * R * 64, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
     else
-        segsum_kernel<128><<<nblocks(P * R * 128, 256), 256, 0, st>>>(src, src_rows_per_p, div, wgt, offs, perm, M, R, P, nch,
-                                                                      ncols & 3, dst, accumulate, rm);
+        err = psg_launch_pdl(segsum_kernel<128>, dim3(nblocks(P * R * 128, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
+    if (err != cudaSuccess) return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

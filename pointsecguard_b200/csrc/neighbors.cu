@@ -92,53 +92,75 @@ ball_query_kernel(const float *__restrict__ xyz, long long cloud_stride, int ncl
 }
 
 constexpr int kNnChunk = 2048;
+constexpr int kNnQ = 2;             // fine points per thread: one LDS.128 of a coarse point serves both
+
+// running top-3 of (d, j): strict '<' keeps the lowest index among equal distances (candidates arrive in
+// ascending index order), which is what the oracle pins for the reference's sort
+__device__ __forceinline__ void top3_push(float d, int jj, float &d0, float &d1, float &d2, int &i0, int &i1, int &i2)
+{
+    if (d < d2 || i2 < 0) {
+        if (d < d1 || i1 < 0) {
+            d2 = d1; i2 = i1;
+            if (d < d0 || i0 < 0) { d1 = d0; i1 = i0; d0 = d; i0 = jj; }
+            else { d1 = d; i1 = jj; }
+        } else { d2 = d; i2 = jj; }
+    }
+}
 
 __global__ void __launch_bounds__(256)
 three_nn_kernel(const float *__restrict__ xyz1, long long stride1, int nclouds1, int N,
                 const float *__restrict__ xyz2, int S,
                 int *__restrict__ idx, float *__restrict__ wout, float *__restrict__ d2out)
 {
-    __shared__ float sx[kNnChunk], sy[kNnChunk], sz[kNnChunk], sn[kNnChunk];
+    __shared__ float4 sp[kNnChunk];             // coarse points (x, y, z, |p|^2)
     const int p = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float *fine = xyz1 + (long long)(p % nclouds1) * stride1;
     const float *coarse = xyz2 + (long long)p * S * 3;
-    float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
-    if (i < N) { qx = fine[3 * i]; qy = fine[3 * i + 1]; qz = fine[3 * i + 2]; qn = psg_sqnorm(qx, qy, qz); }
-    float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY;
-    int i0 = -1, i1 = -1, i2 = -1;
+    int qi[kNnQ];
+    float qx[kNnQ], qy[kNnQ], qz[kNnQ], qn[kNnQ];
+    float d0[kNnQ], d1[kNnQ], d2[kNnQ];
+    int i0[kNnQ], i1[kNnQ], i2[kNnQ];
+#pragma unroll
+    for (int u = 0; u < kNnQ; ++u) {
+        qi[u] = (blockIdx.x * kNnQ + u) * blockDim.x + threadIdx.x;
+        qx[u] = qy[u] = qz[u] = qn[u] = 0.f;
+        if (qi[u] < N) {
+            qx[u] = fine[3 * qi[u]]; qy[u] = fine[3 * qi[u] + 1]; qz[u] = fine[3 * qi[u] + 2];
+            qn[u] = psg_sqnorm(qx[u], qy[u], qz[u]);
+        }
+        d0[u] = d1[u] = d2[u] = INFINITY;
+        i0[u] = i1[u] = i2[u] = -1;
+    }
     for (int base = 0; base < S; base += kNnChunk) {
         const int n = min(kNnChunk, S - base);
         __syncthreads();
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
             const float *c = coarse + (long long)(base + j) * 3;
-            float x = c[0], y = c[1], z = c[2];
-            sx[j] = x; sy[j] = y; sz[j] = z; sn[j] = psg_sqnorm(x, y, z);
+            const float x = c[0], y = c[1], z = c[2];
+            sp[j] = make_float4(x, y, z, psg_sqnorm(x, y, z));
         }
         __syncthreads();
-        if (i >= N) continue;
         for (int j = 0; j < n; ++j) {
-            float d = psg_sqdist(qx, qy, qz, qn, sx[j], sy[j], sz[j], sn[j]);
-            if (d < d2 || i2 < 0) {
-                const int jj = base + j;
-                if (d < d1 || i1 < 0) {
-                    d2 = d1; i2 = i1;
-                    if (d < d0 || i0 < 0) { d1 = d0; i1 = i0; d0 = d; i0 = jj; }
-                    else { d1 = d; i1 = jj; }
-                } else { d2 = d; i2 = jj; }
+            const float4 c = sp[j];
+#pragma unroll
+            for (int u = 0; u < kNnQ; ++u) {
+                const float d = psg_sqdist(qx[u], qy[u], qz[u], qn[u], c.x, c.y, c.z, c.w);
+                top3_push(d, base + j, d0[u], d1[u], d2[u], i0[u], i1[u], i2[u]);
             }
         }
     }
-    if (i < N) {
-        long long o = ((long long)p * N + i) * 3;
-        idx[o] = i0; idx[o + 1] = i1; idx[o + 2] = i2;
+#pragma unroll
+    for (int u = 0; u < kNnQ; ++u) {
+        if (qi[u] >= N) continue;
+        const long long o = ((long long)p * N + qi[u]) * 3;
+        idx[o] = i0[u]; idx[o + 1] = i1[u]; idx[o + 2] = i2[u];
         // pointnet_util.py:305-307: recip = 1/(d+1e-8); w = recip / (r0 + r1 + r2)
-        float r0 = __fdiv_rn(1.0f, __fadd_rn(d0, 1e-8f));
-        float r1 = __fdiv_rn(1.0f, __fadd_rn(d1, 1e-8f));
-        float r2 = __fdiv_rn(1.0f, __fadd_rn(d2, 1e-8f));
-        float nrm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        const float r0 = __fdiv_rn(1.0f, __fadd_rn(d0[u], 1e-8f));
+        const float r1 = __fdiv_rn(1.0f, __fadd_rn(d1[u], 1e-8f));
+        const float r2 = __fdiv_rn(1.0f, __fadd_rn(d2[u], 1e-8f));
+        const float nrm = __fadd_rn(__fadd_rn(r0, r1), r2);
         if (wout) { wout[o] = __fdiv_rn(r0, nrm); wout[o + 1] = __fdiv_rn(r1, nrm); wout[o + 2] = __fdiv_rn(r2, nrm); }
-        if (d2out) { d2out[o] = d0; d2out[o + 1] = d1; d2out[o + 2] = d2; }
+        if (d2out) { d2out[o] = d0[u]; d2out[o + 1] = d1[u]; d2out[o + 2] = d2[u]; }
     }
 }
 
@@ -193,7 +215,7 @@ int psg_three_nn_launch(const float *xyz1, long long stride1, int nclouds1, int 
                         const float *xyz2, int S, int *idx, float *w, float *d2, cudaStream_t st)
 {
     if (P <= 0 || N <= 0 || S < 3) return PSG_EINVAL;
-    dim3 grid((N + 255) / 256, P);
+    dim3 grid((N + 256 * kNnQ - 1) / (256 * kNnQ), P);
     three_nn_kernel<<<grid, 256, 0, st>>>(xyz1, stride1, nclouds1, N, xyz2, S, idx, w, d2);
     PSG_LAUNCH_CHECK();
     return PSG_OK;

@@ -75,3 +75,25 @@ __device__ __forceinline__ float psg_fpsdist(float px, float py, float pz, float
     float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
+
+// Launch with programmatic stream serialization (and optionally a cluster dimension).  Kernels launched
+// this way MUST execute griddepcontrol.wait in every CTA before touching data written by earlier kernels.
+template <class... KArgs, class... Args>
+static inline cudaError_t psg_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                                         Args &&...args)
+{
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+    if (cluster > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = (unsigned)na;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}

@@ -107,6 +107,12 @@ __device__ __forceinline__ void cluster_sync_all()
 // generic-proxy writes (local and peer shared memory) -> visible to the async proxy (tensor core reads)
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// ---- programmatic dependent launch: this grid may start while its predecessor in the stream is still
+// draining; `pdl_wait` blocks until the predecessor has completed and its writes are visible, so
+// everything before it (weight staging, barrier init, TMEM allocation) overlaps the predecessor's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- bulk async copy global -> shared, completion on an mbarrier (bytes % 16 == 0) ---------------------
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
 {

@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    tc::pdl_launch_dependents();      // the next kernel's prologue may overlap our tail ...
+    tc::pdl_wait();                   // ... and ours overlapped our predecessor's: wait for its results now
     const uint32_t tmem = tmem_slot;
     const int tstride = gridDim.x * NG;
 
@@ -332,6 +334,8 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    tc::pdl_launch_dependents();      // the next kernel's prologue may overlap our tail ...
+    tc::pdl_wait();                   // ... and ours overlapped our predecessor's: wait for its results now
     const uint32_t tmem = tmem_slot;
     const int tstride = gridDim.x * NG;
 
@@ -495,7 +499,7 @@ int pick_ng(F smem_of, int gc)
     do {                                                                                   \
         int grid__ = 0, rc__;                                                              \
         if ((rc__ = launch_cfg(KERN<KK, NGG>, SMEM, ARGS.ntiles, NGG, COLS, &grid__)) != PSG_OK) return rc__; \
-        KERN<KK, NGG><<<grid__, NGG * 128 + 32, SMEM, st>>>(ARGS);                         \
+        if (psg_launch_pdl(KERN<KK, NGG>, dim3(grid__), dim3(NGG * 128 + 32), SMEM, st, 1, ARGS) != cudaSuccess) return PSG_ECUDA; \
     } while (0)
 
 int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
