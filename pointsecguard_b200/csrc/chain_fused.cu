@@ -637,7 +637,7 @@ int psg_chain_fused(const PsgChain &c, cudaStream_t st)
 bool psg_sa_streamable(int K, int gpad, int n0, int n1, int n2)
 {
     if (K != 16 && K != 32) return false;
-    if (gpad % 16 || n0 % 32 || n1 % 32 || n2 % 16) return false;     // hidden widths: whole mask words
+    if (gpad % 16 || n0 % 16 || n1 % 16 || n2 % 16) return false;
     if (gpad > 288 || n0 > 256 || n1 > 256 || n2 > 512) return false;
     return true;
 }

@@ -95,8 +95,9 @@ class Engine:
 
     def __del__(self):
         net, self._net = getattr(self, "_net", None), None
-        if net:
-            L.psg_net_destroy(net)
+        destroy = getattr(L, "psg_net_destroy", None)      # module globals may already be gone at interpreter exit
+        if net and destroy is not None:
+            destroy(net)
 
     # ------------------------------------------------------------------------------------------
     def set_mlp_mode(self, mode: int):

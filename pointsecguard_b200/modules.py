@@ -57,8 +57,10 @@ class _Chain:
             self.cout.append(w.shape[0])
 
     def __del__(self):
+        destroy = getattr(L, "psg_mlp_destroy", None)
         for h in getattr(self, "handles", []):
-            L.psg_mlp_destroy(h)
+            if destroy is not None:
+                destroy(h)
         self.handles = []
 
 
