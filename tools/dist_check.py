@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Multi-GPU consistency check, run under torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dist_check.py
+
+Every rank attacks its shard of a global batch (NB and NU); rank 0 also runs the whole batch alone and
+checks that the gathered shards reproduce it bit for bit, that the all-reduced counters equal the
+single-GPU counters exactly, and that the sharded NU (whose accuracy test is a batch-wide sum exchanged
+every step) takes the same early exit as the unsharded one."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from pointsecguard_b200 import distributed as D, metrics as MT, synthetic as syn, torchattacks
+    from pointsecguard_b200.models.pointnet2_sem_seg import get_model
+    m = get_model(13)
+    m.load_state_dict(syn.make_state_dict("ssg", init="he"))
+    m = m.to(dev).eval()
+    G = 2 * world
+    x = syn.make_blocks(G, 2048, 11)
+    torch.manual_seed(5)
+    lab = m(x.to(dev))[0].argmax(2).cpu()
+    sh = D.shard_for(G)
+    ok = True
+
+    def gather(t):
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous())
+        return torch.cat(parts)
+
+    for name, make in (("NB", lambda mm: torchattacks.NB_attack(mm, eps=0.1, alpha=0.05, iters=4)),
+                       ("NU", lambda mm: torchattacks.NU_attack(mm, c=0.1, kappa=0, steps=6, lr=0.01))):
+        m.set_shard(sh)
+        torch.manual_seed(3)
+        adv = make(m)(sh.slice(x).to(dev), sh.slice(lab).numpy().astype(np.float64))
+        torch.manual_seed(4)
+        cnt = MT.attack_counters(m(adv)[0], sh.slice(lab).to(dev))
+        D.all_reduce_sum_(cnt)
+        full = gather(adv)
+        m.set_shard(None)
+        if rank == 0:
+            dist_backup = dist.get_world_size
+            # the single-GPU run must not see the process group as a sharded world
+            torch.manual_seed(3)
+            import pointsecguard_b200.distributed as DD
+            ws = DD.world_size
+            DD.world_size = lambda: 1
+            ref = make(m)(x.to(dev), lab.numpy().astype(np.float64))
+            torch.manual_seed(4)
+            rc = MT.attack_counters(m(ref)[0], lab.to(dev))
+            DD.world_size = ws
+            same = torch.equal(full, ref)
+            csame = torch.equal(cnt, rc)
+            print(f"{name}: shards == full batch: {same}; counters equal: {csame}; acc {MT.summarize(rc.cpu())['acc']:.4f}", flush=True)
+            ok = ok and same and csame
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
