@@ -206,6 +206,14 @@ int psg_clamp(float *x, int64_t count, float lo, float hi, psg_stream_t stream);
  * masked rows with pred == target (mask optional).  This buffer is what the NCCL all-reduce sums. */
 int psg_confusion_matrix(const float *logp, const int32_t *labels, const uint8_t *mask, int target, int64_t rows,
                          int ncls, int64_t *conf, psg_stream_t stream);
+/* Whole-scene voting, add_vote of NB_nontarget_test_semseg.py:55-62: for every row with
+ * weight != 0 (weight may be null = all), pool[point_idx[row]][first arg-max of logp[row]] += 1.  pool is
+ * float32 [pool_rows][ncls] holding exact integer counts; psg_confusion_matrix(pool, scene_labels, ...)
+ * then yields the scene-level seen / correct / union counters of :216-241 (np.argmax = first arg-max),
+ * and under sharding the pool is what ranks all-reduce. */
+int psg_add_vote(const float *logp, const int64_t *point_idx, const float *weight, int64_t rows, int ncls, float *pool,
+                 int64_t pool_rows, psg_stream_t stream);
+
 /* library-wide switches for A/B measurements: "clusters" (default 1) = run the deep levels' tile programs on
  * thread-block clusters (N split across CTAs, activations exchanged through distributed shared memory);
  * "sm_cap" (default 0 = all) = spread persistent launches over at most that many SMs, so that sub-batches

@@ -195,3 +195,17 @@ def block_metrics(pred, labels, num_classes=13):
     miou = float(np.mean(iou[seen != 0])) if (seen != 0).any() else 0.0
     acc = float((pred == lab).sum()) / pred.size
     return {"acc": acc, "seen": seen, "correct": correct, "union": union, "miou": miou}
+
+
+def add_vote(vote_label_pool, point_idx, pred_label, weight):
+    """NB_nontarget_test_semseg.py:55-62 (vectorised restatement of the double loop)."""
+    pi = np.asarray(point_idx).astype(np.int64).reshape(-1)
+    pl = np.asarray(pred_label).astype(np.int64).reshape(-1)
+    w = np.asarray(weight).reshape(-1) != 0
+    np.add.at(vote_label_pool, (pi[w], pl[w]), 1)
+    return vote_label_pool
+
+
+def scene_metrics(vote_label_pool, whole_scene_label, num_classes=13):
+    """:216-238: argmax of the pool, per-class seen / correct / union, scene mIoU over the seen classes."""
+    return block_metrics(np.argmax(vote_label_pool, 1), whole_scene_label, num_classes)

@@ -90,6 +90,7 @@ _PROTOS = {
     "psg_nu_step": (_i, [_vp, C.POINTER(NuBuffers), _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _d, _d, _i, _i, _vp, _vp]),
     "psg_net_set_xyz_grad": (_i, [_vp, _i]),
     "psg_clamp": (_i, [_vp, _i64, _f, _f, _vp]),
+    "psg_add_vote": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i64, _vp]),
     "psg_set_option": (_i, [C.c_char_p, _i]),
     "psg_prof_enable": (_i, [_i]),
     "psg_prof_ncat": (_i, []),

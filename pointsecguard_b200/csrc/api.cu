@@ -141,3 +141,10 @@ extern "C" int psg_confusion_matrix(const float *logp, const int32_t *labels, co
     if (!logp || !labels || !conf || rows <= 0) return PSG_EINVAL;
     return psg_confusion(logp, labels, mask, target, rows, ncls, (long long *)conf, (cudaStream_t)stream);
 }
+
+extern "C" int psg_add_vote(const float *logp, const int64_t *point_idx, const float *weight, int64_t rows, int ncls,
+                            float *pool, int64_t pool_rows, psg_stream_t stream)
+{
+    if (!logp || !point_idx || !pool || rows <= 0 || ncls < 1 || pool_rows <= 0) return PSG_EINVAL;
+    return psg_add_vote_k(logp, (const long long *)point_idx, weight, rows, ncls, pool, pool_rows, (cudaStream_t)stream);
+}

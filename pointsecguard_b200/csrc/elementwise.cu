@@ -131,6 +131,24 @@ __global__ void confusion_kernel(const float *__restrict__ logp, const int *__re
         if (h[i]) atomicAdd(conf + i, (unsigned long long)h[i]);
 }
 
+// add_vote of the attack scripts (NB_nontarget_test_semseg.py:55-62): for every block point with a
+// non-zero weight, vote_label_pool[point_idx, argmax(logp)] += 1.  The pool holds small exact integers
+// in float32, so the atomic adds commute exactly and the result is run-to-run identical.
+__global__ void add_vote_kernel(const float *__restrict__ logp, const long long *__restrict__ point_idx,
+                                const float *__restrict__ weight, long long rows, int ncls, float *__restrict__ pool,
+                                long long pool_rows)
+{
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    if (weight && weight[row] == 0.f) return;
+    const long long pi = point_idx[row];
+    if (pi < 0 || pi >= pool_rows) return;
+    const float *v = logp + row * ncls;
+    int best = 0; float bv = v[0];
+    for (int c = 1; c < ncls; ++c) if (v[c] > bv) { bv = v[c]; best = c; }
+    atomicAdd(pool + pi * ncls + best, 1.0f);
+}
+
 inline unsigned nb(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -178,6 +196,14 @@ int psg_confusion(const float *logp, const int *labels, const unsigned char *mas
     if (ncls > kMaxCls) return PSG_EUNSUPPORTED;
     const unsigned blocks = (unsigned)min((long long)592, (rows + 255) / 256);
     confusion_kernel<<<blocks, 256, 0, st>>>(logp, labels, mask, target, rows, ncls, (unsigned long long *)conf);
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}
+
+int psg_add_vote_k(const float *logp, const long long *point_idx, const float *weight, long long rows, int ncls, float *pool,
+                   long long pool_rows, cudaStream_t st)
+{
+    add_vote_kernel<<<nb(rows, 256), 256, 0, st>>>(logp, point_idx, weight, rows, ncls, pool, pool_rows);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

@@ -120,6 +120,8 @@ int psg_pgd_update(float *adv, const float *ori, TView grad, TView feats0, const
                    int N, int c0, int nc, float alpha_signed, float eps, float lo, float hi, cudaStream_t st);
 int psg_confusion(const float *logp, const int *labels, const unsigned char *mask, int target, long long rows, int ncls,
                   long long *conf, cudaStream_t st);
+int psg_add_vote_k(const float *logp, const long long *point_idx, const float *weight, long long rows, int ncls, float *pool,
+                   long long pool_rows, cudaStream_t st);
 // nu.cu
 struct PsgNuField { int c0, nc; float lo[8], hi[8]; };   // perturbed channels [c0, c0+nc) and their tanh-space box
 int psg_nu_init_k(const float *images, int B, int C, int N, PsgNuField fld, float *w, float *m, float *v, cudaStream_t st);

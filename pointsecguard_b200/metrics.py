@@ -48,3 +48,46 @@ def summarize(counters, ncls: int = 13) -> dict:
     miou = float(np.mean(iou[seen != 0])) if (seen != 0).any() else 0.0
     return {"points": rows, "acc": correct / max(rows, 1), "miou": miou,
             "target_acc": (hit / nmask) if nmask else None, "masked_points": nmask}
+
+
+class VotePool:
+    """Whole-scene vote pool of the attack scripts (NB_nontarget_test_semseg.py:139-140 allocation, :55-62
+    add_vote, :216-238 scene IoU) kept on the GPU.  Note the reference quirk: the attack scripts never fill
+    ``batch_smpw`` (it stays all zeros, :150-153 vs test_semseg.py), so with the scripts' own ``weight``
+    nothing is ever voted and the scene prediction is class 0 everywhere; pass ``weight=None`` to vote every
+    point."""
+
+    def __init__(self, num_points: int, num_classes: int = 13, device="cuda"):
+        self.pool = torch.zeros(num_points, num_classes, dtype=torch.float32, device=device)
+
+    def add(self, logp: torch.Tensor, point_idx: torch.Tensor, weight: torch.Tensor | None = None):
+        """logp [B,N,C] (CUDA), point_idx [B,N] scene indices, weight [B,N] or None."""
+        if not logp.is_cuda:
+            raise RuntimeError("VotePool needs CUDA tensors; there is no CPU fallback")
+        lp = logp.detach().contiguous()
+        idx = point_idx.to(device=lp.device, dtype=torch.int64).contiguous()
+        w = weight.to(device=lp.device, dtype=torch.float32).contiguous() if weight is not None else None
+        L.psg_add_vote(lp.data_ptr(), idx.data_ptr(), w.data_ptr() if w is not None else None, idx.numel(), lp.shape[-1],
+                       self.pool.data_ptr(), self.pool.shape[0], torch.cuda.current_stream().cuda_stream)
+        return self
+
+    def all_reduce_(self):
+        """Sum the pools of all ranks (blocks of one scene sharded over GPUs)."""
+        from . import distributed as D
+        D.all_reduce_sum_(self.pool)
+        return self
+
+    def counters(self, scene_labels: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """int64 [C*C + 4] counters of argmax(pool) against the scene labels (same layout as attack_counters)."""
+        return attack_counters(self.pool.unsqueeze(0), scene_labels.view(1, -1), out=out)
+
+
+def scene_iou(counters, ncls: int = 13) -> dict:
+    """Per-scene / global IoU arithmetic of NB_nontarget_test_semseg.py:216-241, :272-291 from counters."""
+    c = np.asarray(counters.cpu() if torch.is_tensor(counters) else counters, dtype=np.int64)
+    conf = c[: ncls * ncls].reshape(ncls, ncls)
+    seen, tp = conf.sum(1), np.diag(conf)
+    union = seen + conf.sum(0) - tp
+    iou = tp / (union.astype(np.float64) + 1e-6)
+    return {"iou": iou, "miou_seen": float(np.mean(iou[seen != 0])) if (seen != 0).any() else 0.0,
+            "class_acc": float(np.mean(tp / (seen.astype(np.float64) + 1e-6))), "acc": float(tp.sum() / (seen.sum() + 1e-6))}

@@ -241,3 +241,27 @@ def test_attack_metrics_vs_oracle_within_half_a_point():
     assert ref_m["acc"] < 0.95                                # the attack moved the predictions
     assert abs(mine["acc"] - ref_m["acc"]) < 0.005 and abs(mine["miou"] - ref_m["miou"]) < 0.005
     assert same > 0.99
+
+
+def test_whole_scene_voting_vs_oracle():
+    """add_vote + scene IoU on the GPU against the restated script arithmetic,
+    including the scripts' all-zero weight quirk (nothing is voted, scene prediction = class 0)."""
+    from oracle import attacks_oracle as AO
+    from pointsecguard_b200 import metrics as MT
+    rng = np.random.default_rng(0)
+    P, B, N = 5000, 4, 1024
+    logp = torch.randn(B, N, 13, generator=torch.Generator().manual_seed(0))
+    pidx = torch.from_numpy(rng.integers(0, P, (B, N)))
+    weight = torch.from_numpy((rng.random((B, N)) < 0.8).astype(np.float32))
+    scene_lab = torch.from_numpy(rng.integers(0, 13, P))
+    pool_ref = AO.add_vote(np.zeros((P, 13)), pidx.numpy(), logp.argmax(2).numpy(), weight.numpy())
+    vp = MT.VotePool(P, 13).add(logp.cuda(), pidx, weight).add(logp.cuda(), pidx, weight)      # two votes
+    assert np.array_equal(vp.pool.cpu().numpy(), 2 * pool_ref)
+    ref = AO.scene_metrics(pool_ref, scene_lab.numpy())
+    got = MT.scene_iou(vp.counters(scene_lab.cuda()))
+    assert abs(got["miou_seen"] - ref["miou"]) < 1e-9 and abs(got["acc"] - ref["acc"]) < 1e-6
+    # the scripts' own weights are all zero: empty pool, every scene point predicted as class 0
+    empty = MT.VotePool(P, 13).add(logp.cuda(), pidx, torch.zeros(B, N))
+    assert float(empty.pool.sum()) == 0.0
+    c = empty.counters(scene_lab.cuda()).cpu().numpy()[:169].reshape(13, 13)
+    assert c[:, 0].sum() == P and c[:, 1:].sum() == 0
