@@ -44,10 +44,9 @@ __device__ __forceinline__ void load_weights(unsigned char *dst, const float *sr
 }
 
 // D[128 x n] (+)= A[128 x 4*planes] * B[n x 4*planes]^T, both operands in shared memory
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t sA, uint32_t sB, int planes, int n)
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t sA, uint32_t sB, int planes, int n, uint32_t acc = 0)
 {
     const uint32_t idesc = tc::idesc_tf32(128, n);
-    uint32_t acc = 0;
     for (int j = 0; j < planes; j += 2) {
         const uint64_t ad = tc::smem_desc(sA + j * 2048, 2048, 128);
         const uint64_t bd = tc::smem_desc(sB + j * n * 16, (uint32_t)(n * 16), 128);
@@ -266,6 +265,7 @@ struct SaBwdArgs {
     const unsigned *m0, *m1;
     const float *wb0, *wb1, *wb2; int nwb0, nwb1, nwb2;   // dgrad weights [cout/4][nwb][4], rows = cin
     TView dG; int gcols;
+    int slab;                 // columns of dY2 scattered per pass (n2 is contracted in n2 / slab passes)
     long long rows;
     int gpad, n0, n1, n2;
     int ntiles;
@@ -308,8 +308,9 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
     unsigned char *base = smem_raw + (sbase - s0);
     // dgrad weights of layer l: planes = cout_l / 4, rows = cin_l
     const int szW2 = a.n2 * a.n1 * 4, szW1 = a.n1 * a.n0 * 4, szW0 = (a.n0 * a.gpad * 4 + 1023) & ~1023;
-    // per tile ONE operand buffer, overwritten in place: dY2 -> dY1 -> dY0
-    const int szG = max(a.n2, max(a.n1, a.n0)) * 512;
+    // per tile ONE operand buffer, overwritten in place: dY2 (one slab at a time) -> dY1 -> dY0
+    const int szG = max(a.slab, max(a.n1, a.n0)) * 512;
+    const int nslab = a.n2 / a.slab;
     unsigned char *pW2 = base, *pW1 = pW2 + szW2, *pW0 = pW1 + szW1, *pG = pW0 + szW0;
     const uint32_t sW2 = sbase, sW1 = sW2 + szW2, sW0 = sW1 + szW1, sG = sW0 + szW0;
 
@@ -355,11 +356,13 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
                     ph[g] ^= 1u;
                     tc::fence_after_sync();
                     const uint32_t sD2 = sG + g * szG, sD1 = sD2, sD0 = sD2, tm = tmem + g * gcols;
-                    if (layer[g] == 0) issue_layer(tm, sD2, sW2, a.n2 / 4, a.n1);        // dY1 = dY2 W2
-                    else if (layer[g] == 1) issue_layer(tm, sD1, sW1, a.n1 / 4, a.n0);   // dY0 = dY1 W1
-                    else issue_layer(tm, sD0, sW0, a.n0 / 4, a.gpad);                   // dG  = dY0 W0
+                    const int L = layer[g];
+                    if (L < nslab)                                                        // dY1 (+)= dY2[:, slab L] W2[slab L]
+                        issue_layer(tm, sD2, sW2 + (uint32_t)L * (a.slab / 4) * a.n1 * 16, a.slab / 4, a.n1, L > 0 ? 1u : 0u);
+                    else if (L == nslab) issue_layer(tm, sD1, sW1, a.n1 / 4, a.n0);        // dY0 = dY1 W1
+                    else issue_layer(tm, sD0, sW0, a.n0 / 4, a.gpad);                     // dG  = dY0 W0
                     tc::mma_commit(tc::smem_u32(&bar_acc[g]));
-                    if (++layer[g] == 3) {
+                    if (++layer[g] == nslab + 2) {
                         layer[g] = 0; tile[g] += tstride;
                         if (tile[g] >= a.ntiles) { act[g] = false; --nact; }
                     }
@@ -379,22 +382,27 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
             const long long row = (long long)tile * 128 + r;
             const bool valid = row < a.rows;
             const long long g = (valid ? row : 0) / K;
-            // ---- dY2[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0 ----
+            // ---- dY2[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0, one slab of columns at a
+            // time: the operand buffer stays small (more tiles in flight), the MMA accumulates over slabs ----
+            for (int sl = 0; sl < nslab; ++sl) {
+                const int c0 = sl * (a.slab / 4);
 #pragma unroll 8
-            for (int c = 0; c < a.n2 / 4; ++c) {
-                const float4 d = tv_ld(a.dout, g, c);
-                const float4 o = tv_ld(a.outv, g, c);
-                const uchar4 am = *reinterpret_cast<const uchar4 *>(a.arg + g * a.n2 + 4 * c);
-                float4 q;
-                q.x = (valid && am.x == k && o.x > 0.f) ? d.x : 0.f;
-                q.y = (valid && am.y == k && o.y > 0.f) ? d.y : 0.f;
-                q.z = (valid && am.z == k && o.z > 0.f) ? d.z : 0.f;
-                q.w = (valid && am.w == k && o.w > 0.f) ? d.w : 0.f;
-                *plane_ptr(pD2, c, r) = q;
+                for (int c = 0; c < a.slab / 4; ++c) {
+                    const float4 d = tv_ld(a.dout, g, c0 + c);
+                    const float4 o = tv_ld(a.outv, g, c0 + c);
+                    const uchar4 am = *reinterpret_cast<const uchar4 *>(a.arg + g * a.n2 + 4 * (c0 + c));
+                    float4 q;
+                    q.x = (valid && am.x == k && o.x > 0.f) ? d.x : 0.f;
+                    q.y = (valid && am.y == k && o.y > 0.f) ? d.y : 0.f;
+                    q.z = (valid && am.z == k && o.z > 0.f) ? d.z : 0.f;
+                    q.w = (valid && am.w == k && o.w > 0.f) ? d.w : 0.f;
+                    *plane_ptr(pD2, c, r) = q;
+                }
+                tc::fence_before_sync();
+                tc::fence_async_smem();
+                tc::mbar_arrive(b_in);
+                tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();     // this slab's MMAs are done
             }
-            tc::fence_async_smem();
-            tc::mbar_arrive(b_in);
-            tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
             epilogue_mask_to_smem(tl, a.n1, a.m1 + (size_t)tile * w1words * 128, pD1, r);
             tc::fence_before_sync();
             tc::fence_async_smem();
@@ -433,10 +441,19 @@ inline size_t fwd_smem(int gpad, int n0, int n1, int n2, int ng)
     return (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4) +
            (size_t)ng * (size_t)max3(gpad, n0, n1) * 512 + 1024;
 }
+// columns of dY2 scattered per pass: the largest 16-multiple divisor of n2 not wider than the hidden layers
+// (the operand buffer has to hold those anyway)
+inline int bwd_slab(int n0, int n1, int n2)
+{
+    const int cap = n0 > n1 ? n0 : n1;
+    for (int sl = cap - cap % 16; sl >= 16; sl -= 16)
+        if (n2 % sl == 0) return sl;
+    return n2;
+}
 inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng)
 {
     return (size_t)n2 * n1 * 4 + (size_t)n1 * n0 * 4 + r1k((size_t)n0 * gpad * 4) +
-           (size_t)ng * (size_t)max3(n2, n1, n0) * 512 + 1024;
+           (size_t)ng * (size_t)max3(bwd_slab(n0, n1, n2), n1, n0) * 512 + 1024;
 }
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
@@ -530,6 +547,7 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaS
     a.dout = dout; a.outv = f.out; a.arg = f.arg; a.m0 = f.m0; a.m1 = f.m1;
     a.wb0 = f.wb[0]; a.wb1 = f.wb[1]; a.wb2 = f.wb[2]; a.nwb0 = f.nwb[0]; a.nwb1 = f.nwb[1]; a.nwb2 = f.nwb[2];
     a.dG = dG; a.gcols = gcols; a.rows = f.rows;
+    a.slab = bwd_slab(f.n[0], f.n[1], f.n[2]);
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.gpad ? a.n0 : a.gpad) : (a.n1 > a.gpad ? a.n1 : a.gpad));
