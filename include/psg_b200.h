@@ -227,6 +227,10 @@ int psg_prof_enable(int on);
 int psg_prof_ncat(void);
 const char *psg_prof_name(int cat);
 int psg_prof_collect(double *ms_by_cat, int64_t *count_by_cat);
+/* debug: CTA 0 of each of the next `nlaunches` tile-program launches (csrc/chain_fused.cu) writes clock64
+ * stamps of its phases into buf ([nlaunches][4 roles][512] int64: worker tile 0, worker tile 1, MMA issuer);
+ * buf = NULL switches it off -- tools/tile_trace.py */
+int psg_debug_trace(int64_t *buf, int nlaunches);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,7 @@ _PROTOS = {
     "psg_prof_name": (C.c_char_p, [_i]),
     "psg_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "psg_confusion_matrix": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
+    "psg_debug_trace": (_i, [_vp, _i]),
 }
 
 EXPORTS = tuple(_PROTOS)

@@ -44,6 +44,7 @@ struct TileOp {
     int pre, pre_a;            // A refill before this op (PRE_SCATTER: first column)
     int epi, relu;
     const float *bias;
+    int boff;                  // offset of this op's bias copy in the shared-memory bias area (floats)
     int slot;                  // shared-memory mask slot or -1
     unsigned *mglobal;         // global ReLU bits of this op's output [tile][words][128] or null
     TView out;                 // EPI_STORE / EPI_MAXPOOL destination (column offset folded into c0)
@@ -68,11 +69,15 @@ struct TileArgs {
     TileSrc src;
     long long rows; int ntiles;
     int abytes, stage_bytes, tcols;      // A buffer bytes per tile, weight stage bytes, TMEM columns per tile
+    int bias_floats;                     // size of the shared-memory bias area
+    int mwords, mbytes;                  // ReLU-bit words per mask slot; bytes of the per-tile mask / scratch area
     // head / loss (EPI_HEAD)
     int backward, ncls, loss_kind, target;
     const int *labels; float scale, kappa; const float *dlogp;
     float *loss_rows; unsigned char *hit;
     TView zout;
+    int dbg;
+    long long *trace;                    // debug: clock64 stamps of CTA 0 ([role][512]; psg_debug_trace), or null
 };
 
 __device__ __forceinline__ float4 *plane_ptr(unsigned char *buf, int chunk, int row)
@@ -170,17 +175,20 @@ template <int NG, int CS>
 __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_constant__ TileArgs a)
 {
     static_assert(CS == 1 || NG == 1, "cluster programs keep one tile in flight");
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // no-swizzle UMMA operands and bulk copies need 16-byte alignment only: a 128-byte aligned dynamic
+    // segment keeps the static + padding overhead small (every KB decides whether 32 KB weight stages fit)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG], bar_full[kStages], bar_empty[kStages];
     __shared__ uint32_t tmem_slot;
 
     const uint32_t s0 = tc::smem_u32(smem_raw);
-    const uint32_t sbase = (s0 + 1023u) & ~1023u;
+    const uint32_t sbase = (s0 + 127u) & ~127u;
     unsigned char *base = smem_raw + (sbase - s0);
     // [A tile 0 .. NG-1][W stage 0][W stage 1][mask bits tile 0 .. NG-1]
     const uint32_t sA0 = sbase, sW = sbase + NG * a.abytes;
     unsigned char *pA0 = base;
     unsigned *pMask = reinterpret_cast<unsigned *>(base + (size_t)NG * a.abytes + (size_t)kStages * a.stage_bytes);
+    float *sbias = reinterpret_cast<float *>(pMask + (size_t)NG * (a.mbytes / 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ncols = (uint32_t)(a.tcols * NG);
@@ -190,6 +198,13 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
         tc::fence_mbar_init();
     }
     if (warp == NG * 4) tc::tmem_alloc(tc::smem_u32(&tmem_slot), ncols);
+    // biases are constants of the network (not produced by the previous kernel): staged into shared memory
+    // here, ahead of griddepcontrol.wait, so no epilogue ever waits on a global load for them
+    for (int o = 0; o < a.nops; ++o) {
+        const TileOp &op = a.ops[o];
+        if (op.bias)
+            for (int i = threadIdx.x; i < op.n; i += NG * 128 + 64) sbias[op.boff + i] = __ldg(op.bias + i);
+    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -233,6 +248,8 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             int it = 0;
+            long long *tr = (a.trace && blockIdx.x == 0) ? a.trace + 2 * 512 : nullptr;
+            int tn = 0;
             uint32_t ph_in[NG];
 #pragma unroll
             for (int g = 0; g < NG; ++g) ph_in[g] = 0u;
@@ -250,6 +267,7 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                         for (int g = 0; g < NG; ++g) {
                             if (g > glast) continue;
                             tc::mbar_wait(tc::smem_u32(&bar_in[g]), ph_in[g]); ph_in[g] ^= 1u;
+                            if (tr && tn < 510) tr[tn++] = clock64();
                             for (int si = 0; si < nst; ++si) {
                                 const int pl = si * op.pps;
                                 const int np = min(op.pps, op.planes - pl);
@@ -266,6 +284,7 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                                 if (g == glast) tc::mma_commit(tc::smem_u32(&bar_empty[slot]));
                             }
                             tc::mma_commit(tc::smem_u32(&bar_acc[g]));
+                            if (tr && tn < 510) tr[tn++] = clock64();
                         }
                         it += nst;
                         continue;
@@ -306,13 +325,14 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
         const int grp = warp >> 2, wq = warp & 3;
         const int r = threadIdx.x & 127;
         unsigned char *pA = pA0 + (size_t)grp * a.abytes;
-        unsigned *mbits = pMask + (size_t)grp * kMaskSlots * 8 * 128;
+        unsigned *mbits = pMask + (size_t)grp * (a.mbytes / 4);
+        const int mw = a.mwords;
         const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
         const uint32_t tl = tmem + grp * a.tcols + ((uint32_t)(wq * 32) << 16);
         const int K = a.src.K > 0 ? a.src.K : 32;
-        const int k = r % K;
-        const unsigned gmask = (K == 32) ? 0xffffffffu : (0xffffu << (16 * (lane / 16)));
         uint32_t ph = 0;
+        long long *tr = (a.trace && blockIdx.x == 0 && r == 0) ? a.trace + grp * 512 : nullptr;
+        int tn = 0;
         // write 16 bytes of the A operand here and, in a cluster, at the same place in every peer CTA
         auto put = [&](int chunk, float4 val) {
             float4 *dstp = plane_ptr(pA, chunk, r);
@@ -344,9 +364,11 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                     tc::fence_async_smem();
                     tc::mbar_arrive(b_in);
                 }
+                if (tr && tn < 510) tr[tn++] = clock64();
                 // ---- epilogue ----
                 if (CS > 1) tc::mbar_wait_cluster(b_acc, ph); else tc::mbar_wait(b_acc, ph);
                 ph ^= 1u; tc::fence_after_sync();
+                if (tr && tn < 510) tr[tn++] = clock64();
                 const int words = (op.n + 31) / 32;
                 const int w0l = c0l >> 5;
                 if (op.epi == EPI_RELU) {
@@ -354,28 +376,28 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                     for (; c + 32 <= nl; c += 32) {
                         float v[32];
                         tc::tmem_ld32(tl + (uint32_t)c, v);
-                        const unsigned w = psg_relu_bias_bits<32>(v, op.bias + c0l + c);
+                        const unsigned w = psg_relu_bias_bits<32>(v, sbias + op.boff + c0l + c);
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-                        if (op.slot >= 0) mbits[((size_t)op.slot * 8 + w0l + (c >> 5)) * 128 + r] = w;
+                        if (op.slot >= 0) mbits[((size_t)op.slot * mw + w0l + (c >> 5)) * 128 + r] = w;
                         if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
                     if (c < nl) {
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c, v);
-                        const unsigned w = psg_relu_bias_bits<16>(v, op.bias + c0l + c);
+                        const unsigned w = psg_relu_bias_bits<16>(v, sbias + op.boff + c0l + c);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-                        if (op.slot >= 0) mbits[((size_t)op.slot * 8 + w0l + (c >> 5)) * 128 + r] = w;
+                        if (op.slot >= 0) mbits[((size_t)op.slot * mw + w0l + (c >> 5)) * 128 + r] = w;
                         if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
                 } else if (op.epi == EPI_MASK) {
                     int c = 0;
                     for (; c + 32 <= nl; c += 32) {
                         const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r]
-                                                      : mbits[((size_t)op.slot * 8 + w0l + (c >> 5)) * 128 + r];
+                                                      : mbits[((size_t)op.slot * mw + w0l + (c >> 5)) * 128 + r];
                         float v[32];
                         tc::tmem_ld32(tl + (uint32_t)c, v);
                         psg_apply_bits<32>(v, w);
@@ -385,7 +407,7 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                     }
                     if (c < nl) {
                         const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r]
-                                                      : mbits[((size_t)op.slot * 8 + w0l + (c >> 5)) * 128 + r];
+                                                      : mbits[((size_t)op.slot * mw + w0l + (c >> 5)) * 128 + r];
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c, v);
                         psg_apply_bits<16>(v, w);
@@ -399,7 +421,7 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                         float v[32];
                         tc::tmem_ld32(tl + (uint32_t)c, v);
                         unsigned w = 0;
-                        if (op.relu) w = psg_relu_bias_bits<32>(v, op.bias + c0l + c);
+                        if (op.relu) w = psg_relu_bias_bits<32>(v, sbias + op.boff + c0l + c);
                         if (valid) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
@@ -411,7 +433,7 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c, v);
                         unsigned w = 0;
-                        if (op.relu) w = psg_relu_bias_bits<16>(v, op.bias + c0l + c);
+                        if (op.relu) w = psg_relu_bias_bits<16>(v, sbias + op.boff + c0l + c);
                         if (valid) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
@@ -420,35 +442,50 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                         if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
                 } else if (op.epi == EPI_MAXPOOL) {
-                    const long long g = row / K;
-                    for (int c16 = 0; c16 < nl; c16 += 16) {
-                        float v[16];
-                        tc::tmem_ld16(tl + (uint32_t)c16, v);
-                        unsigned am[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const unsigned b = __float_as_uint(fmaxf(v[i] + __ldg(op.bias + c0l + c16 + i), 0.f));
-                            const unsigned mx = __reduce_max_sync(gmask, b);
-                            am[i] = __reduce_min_sync(gmask, b == mx ? (unsigned)k : 64u);
-                            v[i] = __uint_as_float(mx);
+                    // neighbourhood max through a shared-memory transpose (psg_epi.cuh); the per-tile mask area
+                    // is unused by forward set-abstraction programs and serves as the warps' scratch.
+                    // (Everything here stays in registers: with the shared-memory carve-out at its maximum
+                    // there is next to no L1, so a local-memory array costs an L2 round trip per access.)
+                    float *scratch = reinterpret_cast<float *>(mbits) + wq * 1024;
+                    const long long g0 = ((long long)tile * 128 + wq * 32) / K;
+                    const float *bs = sbias + op.boff + c0l;
+                    auto emit1 = [&](long long gg, int col, float best, int arg) {
+                        if (gg * K < a.rows) {
+                            op.out.base[tv_off(op.out, gg, (c0l + col) >> 2) + ((c0l + col) & 3)] = best;
+                            op.arg[gg * op.argC + op.arg0 + c0l + col] = (unsigned char)arg;
                         }
-                        if (k == 0 && valid) {
+                    };
+                    for (int c = 0; c < nl; c += 32) {
+                        float v[32];
+                        const bool full = c + 32 <= nl;                 // else a 16-column tail
+                        if (full) tc::tmem_ld32(tl + (uint32_t)c, v);
+                        else {
+                            tc::tmem_ld16(tl + (uint32_t)c, v);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                tv_st(op.out, g, ((c0l + c16) >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
-                            uint4 pk;
-                            pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
-                            pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
-                            pk.z = am[8] | (am[9] << 8) | (am[10] << 16) | (am[11] << 24);
-                            pk.w = am[12] | (am[13] << 8) | (am[14] << 16) | (am[15] << 24);
-                            *reinterpret_cast<uint4 *>(op.arg + g * op.argC + op.arg0 + c0l + c16) = pk;
+                            for (int i = 16; i < 32; ++i) v[i] = 0.f;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b = (full || q < 4) ? *reinterpret_cast<const float4 *>(bs + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[4 * q] = fmaxf(v[4 * q] + b.x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y, 0.f);
+                            v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w, 0.f);
+                        }
+                        const bool mine = full || lane < 16;
+                        if (K == 32) {
+                            float best[1]; int arg[1];
+                            psg_pool_transposed<32, 32>(v, scratch, lane, best, arg);
+                            if (mine) emit1(g0, c + lane, best[0], arg[0]);
+                        } else {
+                            float best[2]; int arg[2];
+                            psg_pool_transposed<16, 32>(v, scratch, lane, best, arg);
+                            if (mine) { emit1(g0, c + lane, best[0], arg[0]); emit1(g0 + 1, c + lane, best[1], arg[1]); }
                         }
                     }
                 } else if (op.epi == EPI_HEAD) {          // CS == 1 only (16 logit columns do not split)
                     float v[16], dz[16];
                     tc::tmem_ld16(tl, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += __ldg(op.bias + i);
+                    for (int i = 0; i < 16; ++i) v[i] += sbias[op.boff + i];
                     if (!a.backward) {
                         if (valid) {
 #pragma unroll
@@ -476,6 +513,7 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
                     }
                 }
                 // EPI_NONE: the accumulator is continued by the next op
+                if (tr && tn < 510) tr[tn++] = clock64();
             }
             tc::fence_before_sync();
         }
@@ -488,7 +526,10 @@ __global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_consta
 
 int g_sms = 0;
 bool g_use_clusters = true;
-constexpr size_t kSmemMax = 225 * 1024;
+long long *g_trace = nullptr;
+int g_dbg = 0;
+int g_trace_cap = 0, g_trace_n = 0;
+constexpr size_t kSmemMax = 232448 - 256;      // 227 KB per CTA minus the static barriers
 
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
@@ -555,12 +596,30 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
             return PSG_ECUDA;
     }
     a.rows = rows; a.ntiles = (int)((rows + 127) / 128);
+    a.dbg = g_dbg;
+    a.trace = (g_trace && g_trace_n < g_trace_cap) ? g_trace + (size_t)(g_trace_n++) * 2048 : nullptr;
     a.abytes = b.amax_cols * 512;
     const int sms = (g_psg_sm_cap > 0 && g_psg_sm_cap < g_sms) ? g_psg_sm_cap : g_sms;
     const int cs = g_use_clusters ? pick_cluster(a, a.ntiles, sms) : 1;
     a.tcols = (int)pow2cols(b.nmax / cs);
+    a.bias_floats = 0;
+    for (int o = 0; o < a.nops; ++o) {
+        a.ops[o].boff = a.bias_floats;
+        if (a.ops[o].bias) a.bias_floats += (a.ops[o].n + 3) & ~3;
+    }
+    // per-tile mask area: (highest slot + 1) x (words of the widest masked layer) x 128 rows
+    int nslots = 0;
+    a.mwords = 0;
+    for (int o = 0; o < a.nops; ++o) {
+        if (a.ops[o].slot < 0) continue;
+        if (a.ops[o].slot + 1 > nslots) nslots = a.ops[o].slot + 1;
+        if ((a.ops[o].n + 31) / 32 > a.mwords) a.mwords = (a.ops[o].n + 31) / 32;
+    }
+    a.mbytes = nslots * a.mwords * 128 * 4;
+    for (int o = 0; o < a.nops; ++o)
+        if (a.ops[o].epi == EPI_MAXPOOL && a.mbytes < 16384) a.mbytes = 16384;     // pool scratch: 4 KB per worker warp
     auto need = [&](int ng, int stg) {
-        return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * kMaskSlots * 8 * 128 * 4 + 1024;
+        return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * a.mbytes + (size_t)a.bias_floats * 4 + 128;
     };
     // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
     int ng = (cs == 1 && a.ntiles > sms && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
@@ -696,7 +755,9 @@ bool psg_fp_streamable(const PsgFpStream &f, bool forward)
     if (f.nl < 1 || f.nl > 3 || f.C1 % 16 || f.C2 % 16) return false;
     for (int j = 0; j < f.nl; ++j)
         if (f.n[j] % 32 || f.n[j] > 256) return false;
-    if (forward) return (size_t)(f.C1 + f.C2) * 512 + 2 * 16 * 1024 + kMaskSlots * 8 * 128 * 4 + 1024 <= kSmemMax;
+    size_t bias = 0;
+    for (int j = 0; j < f.nl; ++j) bias += (size_t)f.n[j] * 4;
+    if (forward) return (size_t)(f.C1 + f.C2) * 512 + 2 * 16 * 1024 + bias + 128 <= kSmemMax;
     return true;
 }
 
@@ -747,3 +808,5 @@ int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStrea
 
 // thread-block clusters for the deep levels (on by default; the switch exists for A/B measurements)
 void psg_tile_use_clusters(bool on) { g_use_clusters = on; }
+void psg_tile_set_dbg(int v) { g_dbg = v; }
+void psg_tile_set_trace(long long *buf, int nlaunches) { g_trace = buf; g_trace_cap = nlaunches; g_trace_n = 0; }

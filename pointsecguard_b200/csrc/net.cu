@@ -372,8 +372,15 @@ extern "C" int psg_set_option(const char *name, int value)
 {
     if (!name) return PSG_EINVAL;
     if (!strcmp(name, "clusters")) { psg_tile_use_clusters(value != 0); return PSG_OK; }
+    if (!strcmp(name, "dbg")) { psg_tile_set_dbg(value); return PSG_OK; }
     if (!strcmp(name, "sm_cap")) { g_psg_sm_cap = value > 0 ? value : 0; return PSG_OK; }
     return PSG_EINVAL;
+}
+
+extern "C" int psg_debug_trace(int64_t *buf, int nlaunches)
+{
+    psg_tile_set_trace(reinterpret_cast<long long *>(buf), buf ? nlaunches : 0);
+    return PSG_OK;
 }
 
 extern "C" int psg_net_set_xyz_grad(psg_net *n, int on)

@@ -8,14 +8,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-// v[0..NC) <- relu(v + bias[0..NC)); returns the ReLU bits, column 0 in the MSB.  bias 16-byte aligned.
+// v[0..NC) <- relu(v + bias[0..NC)); returns the ReLU bits, column 0 in the MSB.  bias 16-byte aligned, in
+// SHARED memory (a broadcast LDS.128 per four columns; a global load here put an L2 round trip into every
+// 32-column step of every epilogue -- profiles/r1_notes.md, phase trace).
 template <int NC>
-__device__ __forceinline__ unsigned psg_relu_bias_bits(float *v, const float *__restrict__ bias)
+__device__ __forceinline__ unsigned psg_relu_bias_bits(float *v, const float *bias)
 {
     unsigned w = 0;
 #pragma unroll
     for (int q = 0; q < NC / 4; ++q) {
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + q);
+        const float4 b = *(reinterpret_cast<const float4 *>(bias) + q);
         const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -35,4 +37,38 @@ __device__ __forceinline__ void psg_apply_bits(float *v, unsigned w)
 {
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] = ((int)(w << i) < 0) ? v[i] : 0.f;
+}
+
+// ---- neighbourhood max-pool through a shared-memory transpose ----------------------------------------
+// A warp owns 32 consecutive tile rows = 32 / K whole neighbourhoods; lane l holds NC (16 or 32) columns of
+// row l in y[] (post bias + ReLU, so >= 0).  The warp writes them to its private 4 KB scratch transposed
+// ([column][row], XOR-swizzled in units of four rows so that both the scalar writes and the 128-bit reads
+// are bank-conflict free), then lane c scans column c over the K rows of each neighbourhood in ascending
+// row order with a strict '>' -- torch.max's first-max tie-break (pointnet_util.py:205).  This replaces two
+// warp REDUX per pooled element (measured ~50 cycles per column per warp) by ~1 STS + 1/4 LDS.128 + 3 ALU.
+// On return lanes [0, NC) hold best[g] / arg[g] of column `lane` for neighbourhood g of the warp.
+template <int K, int NC>
+__device__ __forceinline__ void psg_pool_transposed(const float *y, float *scratch, int lane, float *best, int *arg)
+{
+#pragma unroll
+    for (int c = 0; c < NC; ++c) scratch[c * 32 + (lane ^ ((c & 7) << 2))] = y[c];
+    __syncwarp();
+    if (lane < NC) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(scratch) + lane * 8;
+#pragma unroll
+        for (int g = 0; g < 32 / K; ++g) {
+            float b = -1.f; int bi = 0;
+#pragma unroll
+            for (int j = g * (K / 4); j < (g + 1) * (K / 4); ++j) {
+                const float4 q = s4[j ^ (lane & 7)];
+                const int r0 = 4 * j - g * K;
+                if (q.x > b) { b = q.x; bi = r0; }
+                if (q.y > b) { b = q.y; bi = r0 + 1; }
+                if (q.z > b) { b = q.z; bi = r0 + 2; }
+                if (q.w > b) { b = q.w; bi = r0 + 3; }
+            }
+            best[g] = b; arg[g] = bi;
+        }
+    }
+    __syncwarp();
 }

@@ -101,6 +101,8 @@ bool psg_fp_streamable(const PsgFpStream &f, bool forward);
 int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st);
 int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStream_t st);
 void psg_tile_use_clusters(bool on);
+void psg_tile_set_dbg(int v);
+void psg_tile_set_trace(long long *buf, int nlaunches);
 // geomgrad.cu: gradient w.r.t. coordinates through grouping and interpolation weights
 int psg_sa_xyz_backward(TView dG, int D, int K, long long groups_per_p, long long P, const int *offs, const int *perm, int R,
                         float *dxyz_src, float *dxyz_ctr, cudaStream_t st);

@@ -67,7 +67,7 @@ struct SaFwdArgs {
 };
 
 // accumulator -> bias + ReLU -> next A operand in shared memory (+ one ReLU bit per element)
-__device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n, const float *__restrict__ bias,
+__device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n, const float *bias,
                                                       unsigned char *dst, unsigned *mask_tile, int row)
 {
     int c = 0;
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[3][128];      // folded biases: epilogues read them with broadcast LDS
 
     const uint32_t s0 = tc::smem_u32(smem_raw);
     const uint32_t sbase = (s0 + 1023u) & ~1023u;
@@ -116,6 +117,11 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
     load_weights(pW0, a.w0, a.gpad / 4, a.n0, a.nw0);
     load_weights(pW1, a.w1, a.n0 / 4, a.n1, a.nw1);
     load_weights(pW2, a.w2, a.n1 / 4, a.n2, a.nw2);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        sbias[0][i] = i < a.n0 ? __ldg(a.b0 + i) : 0.f;
+        sbias[1][i] = i < a.n1 ? __ldg(a.b1 + i) : 0.f;
+        sbias[2][i] = i < a.n2 ? __ldg(a.b2 + i) : 0.f;
+    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -215,26 +221,61 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
             tc::mbar_arrive(b_in);
             // ---- layer 0 epilogue -> Y0 ----
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
-            epilogue_relu_to_smem(tl, a.n0, a.b0, pY0, a.m0 + (size_t)tile * w0words * 128, r);
+            epilogue_relu_to_smem(tl, a.n0, sbias[0], pY0, a.m0 + (size_t)tile * w0words * 128, r);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
             // ---- layer 1 epilogue -> Y1 (reuses the gather buffer) ----
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
-            epilogue_relu_to_smem(tl, a.n1, a.b1, pA, a.m1 + (size_t)tile * w1words * 128, r);
+            epilogue_relu_to_smem(tl, a.n1, sbias[1], pA, a.m1 + (size_t)tile * w1words * 128, r);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
             // ---- layer 2 epilogue: bias + ReLU + max over the K rows of each neighbourhood ----
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
             const long long g = row / K;
+            if (szG >= 16384) {
+                // transposed pool: the tile's operand buffer is dead once MMA 2 has completed (every warp of
+                // the tile waited on the same barrier), so warp wq borrows 4 KB of it as scratch
+                float *scratch = reinterpret_cast<float *>(pA + (size_t)wq * 4096);
+                const long long g0 = ((long long)tile * 128 + wq * 32) / K;          // first neighbourhood of this warp
+                auto emit = [&](int col, const float *best, const int *arg) {
+#pragma unroll
+                    for (int gi = 0; gi < 32 / K; ++gi) {
+                        const long long gg = g0 + gi;
+                        if (gg * K < a.rows) {
+                            a.out.base[tv_off(a.out, gg, col >> 2) + (col & 3)] = best[gi];
+                            a.arg[gg * a.n2 + col] = (unsigned char)arg[gi];
+                        }
+                    }
+                };
+                int c = 0;
+                for (; c + 32 <= a.n2; c += 32) {
+                    float v[32];
+                    tc::tmem_ld32(tl + (uint32_t)c, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + sbias[2][c + i], 0.f);
+                    float best[32 / K]; int arg[32 / K];
+                    psg_pool_transposed<K, 32>(v, scratch, lane, best, arg);
+                    emit(c + lane, best, arg);
+                }
+                if (c < a.n2) {
+                    float v[16];
+                    tc::tmem_ld16(tl + (uint32_t)c, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + sbias[2][c + i], 0.f);
+                    float best[32 / K]; int arg[32 / K];
+                    psg_pool_transposed<K, 16>(v, scratch, lane, best, arg);
+                    if (lane < 16) emit(c + lane, best, arg);
+                }
+            } else
             for (int c16 = 0; c16 < a.n2; c16 += 16) {
                 float v[16];
                 tc::tmem_ld16(tl + (uint32_t)c16, v);
                 unsigned am[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const unsigned b = __float_as_uint(fmaxf(v[i] + __ldg(a.b2 + c16 + i), 0.f));
+                    const unsigned b = __float_as_uint(fmaxf(v[i] + sbias[2][c16 + i], 0.f));
                     const unsigned mx = __reduce_max_sync(gmask, b);     // post-ReLU values order like their bits
                     am[i] = __reduce_min_sync(gmask, b == mx ? (unsigned)k : 64u);   // first arg-max
                     v[i] = __uint_as_float(mx);
@@ -433,6 +474,7 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
 int g_num_sms = 0;
 constexpr size_t kSmemBudget = 226 * 1024;     // per SM, minus what the runtime reserves per CTA
 constexpr size_t kSmemPerCtaMax = 224 * 1024;
+constexpr size_t kStatFwd = 3072, kStatBwd = 2048;   // static shared memory (barriers [+ biases]) + 1 KB reserved per CTA
 
 inline size_t r1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
 inline int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
@@ -458,15 +500,15 @@ inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng)
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
 // CTAs per SM: shared memory (dynamic + 1 KB static + 1 KB reserved) and TMEM columns (512 per SM)
-inline int ctas_per_sm(size_t smem, int tmem_cols)
+inline int ctas_per_sm(size_t smem, int tmem_cols, size_t stat = 2048)
 {
-    int occ = (int)(kSmemBudget / (smem + 2048));
+    int occ = (int)(kSmemBudget / (smem + stat));     // + static (barriers [, 1.5 KB biases]) + 1 KB reserved per CTA
     occ = occ < 512 / tmem_cols ? occ : 512 / tmem_cols;
     return occ < 1 ? 1 : (occ > 8 ? 8 : occ);
 }
 
 template <class Kern>
-int launch_cfg(Kern kern, size_t smem, int ntiles, int ng, int tmem_cols, int *grid)
+int launch_cfg(Kern kern, size_t smem, int ntiles, int ng, int tmem_cols, int *grid, size_t stat)
 {
     if (g_num_sms == 0) {
         int dev = 0;
@@ -477,7 +519,7 @@ int launch_cfg(Kern kern, size_t smem, int ntiles, int ng, int tmem_cols, int *g
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
     const int want = (ntiles + ng - 1) / ng;
     const int sms = (g_psg_sm_cap > 0 && g_psg_sm_cap < g_num_sms) ? g_psg_sm_cap : g_num_sms;
-    const int cap = sms * ctas_per_sm(smem, tmem_cols);
+    const int cap = sms * ctas_per_sm(smem, tmem_cols, stat);
     *grid = want < cap ? want : cap;
     return PSG_OK;
 }
@@ -500,22 +542,22 @@ size_t psg_sa_mask_words(long long rows, int n)
 // tiles in flight per SM = NG (per CTA, sharing the resident weights) x CTAs per SM: take the
 // combination that keeps the most tiles in flight (the per-tile chain is latency-bound)
 template <class F>
-int pick_ng(F smem_of, int gc)
+int pick_ng(F smem_of, int gc, size_t stat)
 {
     int best = 1, best_tiles = 0;
     for (int ng = 1; ng <= 4; ++ng) {
         const size_t sm = smem_of(ng);
         if (sm > kSmemPerCtaMax || ng * gc > 512) break;
-        const int tiles = ng * ctas_per_sm(sm, (int)pow2cols(ng * gc));
+        const int tiles = ng * ctas_per_sm(sm, (int)pow2cols(ng * gc), stat);
         if (tiles > best_tiles) { best_tiles = tiles; best = ng; }
     }
     return best;
 }
 
-#define SA_LAUNCH(KERN, KK, NGG, ARGS, SMEM, COLS)                                         \
+#define SA_LAUNCH(KERN, KK, NGG, ARGS, SMEM, COLS, STAT)                                       \
     do {                                                                                   \
         int grid__ = 0, rc__;                                                              \
-        if ((rc__ = launch_cfg(KERN<KK, NGG>, SMEM, ARGS.ntiles, NGG, COLS, &grid__)) != PSG_OK) return rc__; \
+        if ((rc__ = launch_cfg(KERN<KK, NGG>, SMEM, ARGS.ntiles, NGG, COLS, &grid__, STAT)) != PSG_OK) return rc__; \
         if (psg_launch_pdl(KERN<KK, NGG>, dim3(grid__), dim3(NGG * 128 + 32), SMEM, st, 1, ARGS) != cudaSuccess) return PSG_ECUDA; \
     } while (0)
 
@@ -530,10 +572,10 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     a.m0 = f.m0; a.m1 = f.m1; a.out = f.out; a.arg = f.arg;
     a.ntiles = (int)((f.rows + 127) / 128);
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.n2 ? a.n0 : a.n2) : (a.n1 > a.n2 ? a.n1 : a.n2));
-    const int ng = pick_ng([&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g); }, gc);
+    const int ng = pick_ng([&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g); }, gc, kStatFwd);
     const size_t smem = fwd_smem(a.gpad, a.n0, a.n1, a.n2, ng);
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
-#define SA_FWD_CASE(KK, NGG) if (f.K == KK && ng == NGG) SA_LAUNCH(sa_fwd_kernel, KK, NGG, a, smem, (int)pow2cols(gc * NGG))
+#define SA_FWD_CASE(KK, NGG) if (f.K == KK && ng == NGG) SA_LAUNCH(sa_fwd_kernel, KK, NGG, a, smem, (int)pow2cols(gc * NGG), kStatFwd)
     SA_FWD_CASE(32, 1); SA_FWD_CASE(32, 2); SA_FWD_CASE(32, 3); SA_FWD_CASE(32, 4);
     SA_FWD_CASE(16, 1); SA_FWD_CASE(16, 2); SA_FWD_CASE(16, 3); SA_FWD_CASE(16, 4);
 #undef SA_FWD_CASE
@@ -551,10 +593,10 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaS
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.gpad ? a.n0 : a.gpad) : (a.n1 > a.gpad ? a.n1 : a.gpad));
-    const int ng = pick_ng([&](int g) { return bwd_smem(a.gpad, a.n0, a.n1, a.n2, g); }, gc);
+    const int ng = pick_ng([&](int g) { return bwd_smem(a.gpad, a.n0, a.n1, a.n2, g); }, gc, kStatBwd);
     const size_t smem = bwd_smem(a.gpad, a.n0, a.n1, a.n2, ng);
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
-#define SA_BWD_CASE(KK, NGG) if (f.K == KK && ng == NGG) SA_LAUNCH(sa_bwd_kernel, KK, NGG, a, smem, (int)pow2cols(gc * NGG))
+#define SA_BWD_CASE(KK, NGG) if (f.K == KK && ng == NGG) SA_LAUNCH(sa_bwd_kernel, KK, NGG, a, smem, (int)pow2cols(gc * NGG), kStatBwd)
     SA_BWD_CASE(32, 1); SA_BWD_CASE(32, 2); SA_BWD_CASE(32, 3); SA_BWD_CASE(32, 4);
     SA_BWD_CASE(16, 1); SA_BWD_CASE(16, 2); SA_BWD_CASE(16, 3); SA_BWD_CASE(16, 4);
 #undef SA_BWD_CASE
