@@ -95,9 +95,19 @@ __device__ __forceinline__ void pre_group(const TileSrc &s, unsigned char *pA, l
     const int cloud = p % s.nclouds;
     const long long srow = (long long)cloud * s.Nsrc + src;
     const int D = s.D, nfull = D >> 2;
-#pragma unroll 4
-    for (int c = 0; c < nfull; ++c)
-        *plane_ptr(pA, c, r) = valid ? tv_ld(s.feats, srow, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const float *fb = s.feats.base + tv_off(s.feats, srow, 0);
+        constexpr int NB = 16;                       // independent 16-byte requests in flight per thread
+        for (int c0 = 0; c0 < nfull; c0 += NB) {
+            float4 x[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                x[j] = c0 + j < nfull ? __ldg(reinterpret_cast<const float4 *>(fb + (size_t)(c0 + j) * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if (c0 + j < nfull) *plane_ptr(pA, c0 + j, r) = valid ? x[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     const float *sp = s.xyz + (long long)cloud * s.cloud_stride + (long long)src * 3;
     const float *cp = s.new_xyz + ps * 3;
     const float dx = __fsub_rn(sp[0], cp[0]), dy = __fsub_rn(sp[1], cp[1]), dz = __fsub_rn(sp[2], cp[2]);
@@ -117,12 +127,23 @@ __device__ __forceinline__ void pre_group(const TileSrc &s, unsigned char *pA, l
 
 __device__ __forceinline__ void pre_load(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r)
 {
-#pragma unroll 4
-    for (int c = 0; c < s.lcols / 4; ++c)
-        *plane_ptr(pA, c, r) = valid ? tv_ld(s.lsrc, row, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *b = s.lsrc.base + tv_off(s.lsrc, valid ? row : 0, 0);
+    const int nch = s.lcols / 4;
+    constexpr int NB = 16;
+    for (int c0 = 0; c0 < nch; c0 += NB) {
+        float4 x[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+            x[j] = c0 + j < nch ? *reinterpret_cast<const float4 *>(b + (size_t)(c0 + j) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+            if (c0 + j < nch) *plane_ptr(pA, c0 + j, r) = valid ? x[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
-// (f[i0] w0 + f[i1] w1) + f[i2] w2, products rounded separately as torch does (pointnet_util.py:308)
+// (f[i0] w0 + f[i1] w1) + f[i2] w2, products rounded separately as torch does (pointnet_util.py:308).
+// The three gathered rows are 16-byte pieces 2 KB apart: a latency-bound gather, so the loads of eight chunks
+// (24 independent 16-byte requests per thread) are issued before the first one is consumed.
 __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r)
 {
     const long long rr = valid ? row : 0;
@@ -131,15 +152,33 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
     const float *ww = s.nn_w + rr * 3;
     const long long r0 = p * s.iS + ii[0], r1 = p * s.iS + ii[1], r2 = p * s.iS + ii[2];
     const float w0 = valid ? ww[0] : 0.f, w1 = valid ? ww[1] : 0.f, w2 = valid ? ww[2] : 0.f;
-#pragma unroll 4
-    for (int c = 0; c < s.icols / 4; ++c) {
-        const float4 x = tv_ld(s.isrc, r0, c), y = tv_ld(s.isrc, r1, c), z = tv_ld(s.isrc, r2, c);
-        float4 q;
-        q.x = __fadd_rn(__fadd_rn(__fmul_rn(x.x, w0), __fmul_rn(y.x, w1)), __fmul_rn(z.x, w2));
-        q.y = __fadd_rn(__fadd_rn(__fmul_rn(x.y, w0), __fmul_rn(y.y, w1)), __fmul_rn(z.y, w2));
-        q.z = __fadd_rn(__fadd_rn(__fmul_rn(x.z, w0), __fmul_rn(y.z, w1)), __fmul_rn(z.z, w2));
-        q.w = __fadd_rn(__fadd_rn(__fmul_rn(x.w, w0), __fmul_rn(y.w, w1)), __fmul_rn(z.w, w2));
-        *plane_ptr(pA, s.iplane0 + c, r) = q;
+    const float *b0 = s.isrc.base + tv_off(s.isrc, r0, 0), *b1 = s.isrc.base + tv_off(s.isrc, r1, 0),
+                *b2 = s.isrc.base + tv_off(s.isrc, r2, 0);
+    const int nch = s.icols / 4;
+    constexpr int NB = 8;
+    for (int c0 = 0; c0 < nch; c0 += NB) {
+        float4 x[NB], y[NB], z[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            // (every element is written on every path: a conditional assignment would carry the previous
+            // batch's registers around the loop)
+            const bool in = c0 + j < nch;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            x[j] = in ? __ldg(reinterpret_cast<const float4 *>(b0 + (size_t)(c0 + j) * 512)) : zero;
+            y[j] = in ? __ldg(reinterpret_cast<const float4 *>(b1 + (size_t)(c0 + j) * 512)) : zero;
+            z[j] = in ? __ldg(reinterpret_cast<const float4 *>(b2 + (size_t)(c0 + j) * 512)) : zero;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            if (c0 + j < nch) {
+                float4 q;
+                q.x = __fadd_rn(__fadd_rn(__fmul_rn(x[j].x, w0), __fmul_rn(y[j].x, w1)), __fmul_rn(z[j].x, w2));
+                q.y = __fadd_rn(__fadd_rn(__fmul_rn(x[j].y, w0), __fmul_rn(y[j].y, w1)), __fmul_rn(z[j].y, w2));
+                q.z = __fadd_rn(__fadd_rn(__fmul_rn(x[j].z, w0), __fmul_rn(y[j].z, w1)), __fmul_rn(z[j].z, w2));
+                q.w = __fadd_rn(__fadd_rn(__fmul_rn(x[j].w, w0), __fmul_rn(y[j].w, w1)), __fmul_rn(z[j].w, w2));
+                *plane_ptr(pA, s.iplane0 + c0 + j, r) = q;
+            }
+        }
     }
 }
 
@@ -150,17 +189,29 @@ __device__ __forceinline__ void pre_scatter(const TileSrc &s, unsigned char *pA,
     const long long g = (valid ? row : 0) / s.K;
     const int k = r % s.K;
     const int c0 = col0 >> 2;
-#pragma unroll 4
-    for (int c = 0; c < planes; ++c) {
-        const float4 d = tv_ld(s.dout, g, c0 + c);
-        const float4 o = tv_ld(s.outv, g, c0 + c);
-        const uchar4 am = *reinterpret_cast<const uchar4 *>(s.sarg + g * s.sargC + col0 + 4 * c);
-        float4 q;
-        q.x = (valid && am.x == k && o.x > 0.f) ? d.x : 0.f;
-        q.y = (valid && am.y == k && o.y > 0.f) ? d.y : 0.f;
-        q.z = (valid && am.z == k && o.z > 0.f) ? d.z : 0.f;
-        q.w = (valid && am.w == k && o.w > 0.f) ? d.w : 0.f;
-        *plane_ptr(pA, c, r) = q;
+    const float *db = s.dout.base + tv_off(s.dout, g, c0), *ob = s.outv.base + tv_off(s.outv, g, c0);
+    const unsigned char *ab = s.sarg + g * s.sargC + col0;
+    constexpr int NB = 8;
+    for (int cb = 0; cb < planes; cb += NB) {
+        float4 d[NB], o[NB]; uchar4 am[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const bool in = cb + j < planes;
+            d[j] = in ? *reinterpret_cast<const float4 *>(db + (size_t)(cb + j) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o[j] = in ? *reinterpret_cast<const float4 *>(ob + (size_t)(cb + j) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+            am[j] = in ? *reinterpret_cast<const uchar4 *>(ab + 4 * (cb + j)) : make_uchar4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            if (cb + j < planes) {
+                float4 q;
+                q.x = (valid && am[j].x == k && o[j].x > 0.f) ? d[j].x : 0.f;
+                q.y = (valid && am[j].y == k && o[j].y > 0.f) ? d[j].y : 0.f;
+                q.z = (valid && am[j].z == k && o[j].z > 0.f) ? d[j].z : 0.f;
+                q.w = (valid && am[j].w == k && o[j].w > 0.f) ? d[j].w : 0.f;
+                *plane_ptr(pA, cb + j, r) = q;
+            }
+        }
     }
 }
 
@@ -172,7 +223,7 @@ __device__ __forceinline__ void pre_scatter(const TileSrc &s, unsigned char *pA,
 // on all CTAs' operand barriers (nobody issues an MMA before every slice landed).  This is what lets
 // the deep levels -- few rows, large weights -- use more than one SM per tile.
 template <int NG, int CS>
-__global__ void __launch_bounds__(NG * 128 + 64) tile_kernel(const __grid_constant__ TileArgs a)
+__global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_constant__ TileArgs a)
 {
     static_assert(CS == 1 || NG == 1, "cluster programs keep one tile in flight");
     // no-swizzle UMMA operands and bulk copies need 16-byte alignment only: a 128-byte aligned dynamic
