@@ -132,7 +132,7 @@ extern "C" int psg_segment_sum(const float *src_base, int src_wchunks, int src_c
 {
     if (!src_base || !offsets || !perm || !dst_base || div <= 0) return PSG_EINVAL;
     return psg_segsum(mkview(src_base, src_wchunks, src_c0), src_rows_per_problem, div, weights, offsets, perm, M, R, P,
-                      ncols, mkview(dst_base, dst_wchunks, dst_c0), accumulate, nullptr, (cudaStream_t)stream);
+                      ncols, mkview(dst_base, dst_wchunks, dst_c0), accumulate, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int psg_confusion_matrix(const float *logp, const int32_t *labels, const uint8_t *mask, int target,

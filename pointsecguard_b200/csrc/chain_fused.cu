@@ -48,6 +48,8 @@ struct TileOp {
     int slot;                  // shared-memory mask slot or -1
     unsigned *mglobal;         // global ReLU bits of this op's output [tile][words][128] or null
     TView out;                 // EPI_STORE / EPI_MAXPOOL destination (column offset folded into c0)
+    float *rm; int rm_stride;  // EPI_STORE: optional row-major mirror of `out` (floats per row), or null
+    int rm_only;               // ... and skip the T-layout store
     unsigned char *arg; int argC, arg0;   // EPI_MAXPOOL
 };
 
@@ -59,6 +61,7 @@ struct TileSrc {
     // PRE_LOAD: lsrc rows only
     TView lsrc; int lcols;
     TView isrc; int iS, iNf, icols, iplane0; const int *nn_idx; const float *nn_w;
+    const float *irm; int irm_stride;    // row-major mirror of isrc (whole 32-byte sectors per request), or null
     // PRE_SCATTER
     TView dout, outv; const unsigned char *sarg; int sargC;
 };
@@ -152,9 +155,41 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
     const float *ww = s.nn_w + rr * 3;
     const long long r0 = p * s.iS + ii[0], r1 = p * s.iS + ii[1], r2 = p * s.iS + ii[2];
     const float w0 = valid ? ww[0] : 0.f, w1 = valid ? ww[1] : 0.f, w2 = valid ? ww[2] : 0.f;
+    const int nch = s.icols / 4;
+    if (s.irm) {
+        // row-major mirror: one 32-byte request per two chunks -- half the L1 tag work and only whole sectors
+        // from L2 (the T-layout pieces are 16 bytes, 2 KB apart)
+        const float *m0 = s.irm + r0 * s.irm_stride, *m1 = s.irm + r1 * s.irm_stride, *m2 = s.irm + r2 * s.irm_stride;
+        constexpr int NP = 4;                         // pairs of chunks per batch
+        for (int c0 = 0; c0 < nch; c0 += 2 * NP) {
+            float4 x[2 * NP], y[2 * NP], z[2 * NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const bool in = c0 + 2 * j < nch;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                x[2 * j] = x[2 * j + 1] = y[2 * j] = y[2 * j + 1] = z[2 * j] = z[2 * j + 1] = zero;
+                if (in) {
+                    tc::ldg256(m0 + (size_t)(c0 + 2 * j) * 4, x[2 * j], x[2 * j + 1]);
+                    tc::ldg256(m1 + (size_t)(c0 + 2 * j) * 4, y[2 * j], y[2 * j + 1]);
+                    tc::ldg256(m2 + (size_t)(c0 + 2 * j) * 4, z[2 * j], z[2 * j + 1]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * NP; ++j) {
+                if (c0 + j < nch) {
+                    float4 q;
+                    q.x = __fadd_rn(__fadd_rn(__fmul_rn(x[j].x, w0), __fmul_rn(y[j].x, w1)), __fmul_rn(z[j].x, w2));
+                    q.y = __fadd_rn(__fadd_rn(__fmul_rn(x[j].y, w0), __fmul_rn(y[j].y, w1)), __fmul_rn(z[j].y, w2));
+                    q.z = __fadd_rn(__fadd_rn(__fmul_rn(x[j].z, w0), __fmul_rn(y[j].z, w1)), __fmul_rn(z[j].z, w2));
+                    q.w = __fadd_rn(__fadd_rn(__fmul_rn(x[j].w, w0), __fmul_rn(y[j].w, w1)), __fmul_rn(z[j].w, w2));
+                    *plane_ptr(pA, s.iplane0 + c0 + j, r) = q;
+                }
+            }
+        }
+        return;
+    }
     const float *b0 = s.isrc.base + tv_off(s.isrc, r0, 0), *b1 = s.isrc.base + tv_off(s.isrc, r1, 0),
                 *b2 = s.isrc.base + tv_off(s.isrc, r2, 0);
-    const int nch = s.icols / 4;
     constexpr int NB = 8;
     for (int c0 = 0; c0 < nch; c0 += NB) {
         float4 x[NB], y[NB], z[NB];
@@ -474,9 +509,16 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         unsigned w = 0;
                         if (op.relu) w = psg_relu_bias_bits<32>(v, sbias + op.boff + c0l + c);
                         if (valid) {
+                            if (!op.rm_only) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                tv_st(op.out, row, ((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                                for (int j = 0; j < 8; ++j)
+                                    tv_st(op.out, row, ((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                            }
+                            if (op.rm) {
+                                float4 *d = reinterpret_cast<float4 *>(op.rm + row * op.rm_stride + c0l + c);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            }
                         }
                         if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
@@ -486,9 +528,16 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         unsigned w = 0;
                         if (op.relu) w = psg_relu_bias_bits<16>(v, sbias + op.boff + c0l + c);
                         if (valid) {
+                            if (!op.rm_only) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                tv_st(op.out, row, ((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                                for (int j = 0; j < 4; ++j)
+                                    tv_st(op.out, row, ((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                            }
+                            if (op.rm) {
+                                float4 *d = reinterpret_cast<float4 *>(op.rm + row * op.rm_stride + c0l + c);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            }
                         }
                         if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
@@ -729,12 +778,13 @@ int psg_chain_fused(const PsgChain &c, cudaStream_t st)
             const int nin = j > 0 ? c.n[j - 1] : c.kin;
             TileOp *o = b.add(c.wb[j], c.nwb[j], 0, 0, nin, c.n[j] / 4, 0);
             if (j > 0) { o->epi = EPI_MASK; o->slot = j - 1; }
-            else { o->epi = EPI_STORE; o->out = c.dI; }
+            else { o->epi = EPI_STORE; o->out = c.dI; o->rm = c.dI_rm; o->rm_stride = c.kin; o->rm_only = (c.dI_rm && c.rm_only) ? 1 : 0; }
         }
     }
     TileArgs &a = b.a;
     a.src.isrc = c.src; a.src.iS = c.S; a.src.iNf = c.Nf; a.src.icols = c.kin; a.src.iplane0 = 0;
     a.src.nn_idx = c.nn_idx; a.src.nn_w = c.nn_w; a.src.lcols = 0;
+    a.src.irm = c.src_rm; a.src.irm_stride = c.kin;
     a.backward = c.backward; a.ncls = c.ncls; a.loss_kind = c.loss_kind; a.target = c.target; a.labels = c.labels;
     a.scale = c.scale; a.kappa = c.kappa; a.dlogp = c.dlogp; a.loss_rows = c.loss_rows; a.hit = c.hit;
     a.zout = c.zout;
@@ -772,7 +822,7 @@ int psg_sa_stream_fwd(const PsgSaFused &f, cudaStream_t st)
     return launch_program(b, f.rows, st);
 }
 
-int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st)
+int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float *dG_rm, int rm_only, cudaStream_t st)
 {
     Builder b;
     TileOp *o = nullptr;
@@ -792,6 +842,7 @@ int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cuda
         const int n = gcols - c0 < 256 ? gcols - c0 : 256;
         o = b.add(f.wb[0], f.nwb[0], c0, 0, n, f.n[0] / 4, 0);
         o->epi = EPI_STORE; o->out = dG; o->out.c0 += c0 / 4;
+        if (dG_rm) { o->rm = dG_rm + c0; o->rm_stride = f.gpad; o->rm_only = rm_only; }
     }
     TileSrc &s = b.a.src;
     s.K = f.K; s.dout = dout; s.outv = f.out; s.sarg = f.arg; s.sargC = f.n[2];
@@ -823,17 +874,18 @@ int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st)
         o->bias = f.bias[j];
         if (j == 0) o->pre = PRE_FP;
         if (j + 1 < f.nl) { o->epi = EPI_RELU; o->mglobal = f.m[j]; }
-        else { o->epi = EPI_STORE; o->relu = 1; o->out = f.y_last; }
+        else { o->epi = EPI_STORE; o->relu = 1; o->out = f.y_last; o->rm = f.y_last_rm; o->rm_stride = f.n[j]; }
         kprev = f.n[j];
     }
     TileSrc &s = b.a.src;
     s.lsrc = f.skip; s.lcols = f.C1;
     s.isrc = f.coarse; s.iS = f.S; s.iNf = f.Nf; s.icols = f.C2; s.iplane0 = f.C1 / 4; s.nn_idx = f.nn_idx; s.nn_w = f.nn_w;
+    s.irm = f.coarse_rm; s.irm_stride = f.C2;
     return launch_program(b, f.rows, st);
 }
 
 // dY_last (pre-activation gradient, already masked) -> dgrad chain -> d[skip | interp] stored to dcat
-int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStream_t st)
+int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dcat_rm, cudaStream_t st)
 {
     Builder b;
     for (int j = f.nl - 1; j >= 0; --j) {
@@ -847,6 +899,7 @@ int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStrea
                 const int n = nin - c0 < 256 ? nin - c0 : 256;
                 TileOp *o = b.add(f.wb[0], f.nwb[0], c0, 0, n, f.n[0] / 4, 0);
                 o->epi = EPI_STORE; o->out = dcat; o->out.c0 += c0 / 4;
+                if (dcat_rm) { o->rm = dcat_rm + c0; o->rm_stride = f.C1 + f.C2; }
                 if (f.nl == 1 && c0 == 0) o->pre = PRE_LOAD;
             }
         }

@@ -295,7 +295,7 @@ template <int LPR>
 __global__ void __launch_bounds__(256)
 segsum_kernel(TView src, long long src_rows_per_p, int div, const float *__restrict__ wgt,
               const int *__restrict__ offs, const int *__restrict__ perm, int M, int R, long long P,
-              int nch, int tail_cols, TView dst, int accumulate, TView rmask)
+              int nch, int tail_cols, TView dst, int accumulate, TView rmask, const float *__restrict__ src_rm, int rm_stride)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");          // launched with programmatic stream serialization
@@ -318,7 +318,11 @@ segsum_kernel(TView src, long long src_rows_per_p, int div, const float *__restr
             for (int u = 0; u < 4; ++u) slot[u] = e + u < hi ? pm[e + u] : -1;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                v[u] = slot[u] >= 0 ? tv_ld(src, sbase + slot[u] / div, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // src_rm: row-major copy of the source rows -- the lanes of one destination row then read one
+                // contiguous piece of a source row (whole sectors) instead of 16-byte pieces 2 KB apart
+                v[u] = slot[u] < 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
+                     : src_rm  ? *reinterpret_cast<const float4 *>(src_rm + (sbase + slot[u] / div) * rm_stride + 4 * c)
+                               : tv_ld(src, sbase + slot[u] / div, c);
                 sc[u] = (ww && slot[u] >= 0) ? ww[slot[u]] : 1.f;
             }
 #pragma unroll
@@ -455,29 +459,30 @@ int psg_csr_build(const int *keys, long long P, int M, int R, int grp, int *offs
     return PSG_OK;
 }
 int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, const int *offs, const int *perm,
-               int M, int R, long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, cudaStream_t st)
+               int M, int R, long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, const float *src_rm,
+               int rm_stride, cudaStream_t st)
 {
     TView rm = relu_mask ? *relu_mask : TView{nullptr, 0, 0};
     const int nch = (ncols + 3) / 4;
     cudaError_t err = cudaSuccess;
     if (nch <= 4)
         err = psg_launch_pdl(segsum_kernel<4>, dim3(nblocks(P * R * 4, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
-                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm, src_rm, rm_stride);
     else if (nch <= 8)
         err = psg_launch_pdl(segsum_kernel<8>, dim3(nblocks(P * R * 8, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
-                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm, src_rm, rm_stride);
     else if (nch <= 16)
         err = psg_launch_pdl(segsum_kernel<16>, dim3(nblocks(P * R * 16, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
-                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm, src_rm, rm_stride);
     else if (nch <= 32)
         err = psg_launch_pdl(segsum_kernel<32>, dim3(nblocks(P * R * 32, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
-                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm, src_rm, rm_stride);
     else if (nch <= 64)      // wide rows of the small levels: more lanes per row, the bucket walk is the latency chain
         err = psg_launch_pdl(segsum_kernel<64>, dim3(nblocks(P * R * 64, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
-                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm, src_rm, rm_stride);
     else
         err = psg_launch_pdl(segsum_kernel<128>, dim3(nblocks(P * R * 128, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,
-                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm);
+                             offs, perm, M, R, P, nch, ncols & 3, dst, accumulate, rm, src_rm, rm_stride);
     if (err != cudaSuccess) return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;

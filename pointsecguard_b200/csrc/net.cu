@@ -227,6 +227,7 @@ struct FpLevel {
     psg_mlp *mlp[3];
     int C1, C2;            // skip width (fine level features), interpolated width (coarse features)
     float *I, *Y[3];
+    float *Yrm;            // row-major mirror of the last layer's output (the next finer level gathers from it)
     int *nn_idx;           // [T*B][Nf][3]
     float *nn_w;           // [T*B][Nf][3]
     int *csr_off, *csr_perm;   // [T*B][Nc+1], [T*B][Nf*3]
@@ -255,6 +256,7 @@ struct psg_net {
     float *feats[5], *dfeat[5];
     float *H, *Z, *dZ;
     float *S[2]; size_t scratch_floats;
+    float *Srm;            // row-major copy of the gradient rows a fused backward kernel hands to the segmented sum
     bool bound;
     int last_t;
     // tcgen05 mode: fp1 + head run as one forward+backward kernel (chain_fused.cu); the loss is then
@@ -453,6 +455,7 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
             if ((size_t)F.mlp[j]->npad > wmax) wmax = F.mlp[j]->npad;
         }
         if (f == 0 && (size_t)n->conv1->npad > wmax) wmax = n->conv1->npad;
+        F.Yrm = f > 0 ? bp.take<float>((size_t)round_up_ll(rows, 128) * F.mlp[F.nl - 1]->npad) : nullptr;
         F.streamed = false;
         for (int j = 0; j < 3; ++j) F.m[j] = nullptr;
         if (f > 0) {
@@ -478,6 +481,7 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
     n->scratch_floats = scratch;
     n->S[0] = bp.take<float>(scratch);
     n->S[1] = bp.take<float>(scratch);
+    n->Srm = bp.take<float>(scratch);
     n->fps_ws = bp.take<char>(n->fps_ws_bytes ? n->fps_ws_bytes : 16);
     n->csr_ws = bp.take<char>(csr_scratch);
     n->grid_ws = N >= 2048 ? (void *)bp.take<char>(psg_ballgrid_workspace_bytes(B, N)) : nullptr;
@@ -612,6 +616,9 @@ static PsgFpStream fp_stream_desc(psg_net *n, int f, int t, TView coarse)
         q.m[j] = F.m[j];
     }
     q.y_last = tv(F.Y[F.nl - 1], F.mlp[F.nl - 1]->npad);
+    q.y_last_rm = F.Yrm;
+    // the coarser level's mirror exists only if that level ran as a tile program too
+    q.coarse_rm = (f < 3 && n->fp[f + 1].streamed && n->mode == 1) ? n->fp[f + 1].Yrm : nullptr;
     return q;
 }
 
@@ -632,6 +639,7 @@ static PsgChain head_chain_desc(psg_net *n, int t, TView coarse)
     c.head_wf = n->conv2->wf; c.head_nwf = n->conv2->nwf; c.head_bias = n->conv2->bias;
     c.head_wb = n->conv2->wb; c.head_nwb = n->conv2->nwb;
     c.ncls = n->ncls; c.target = -1;
+    c.src_rm = (n->fp[1].streamed && n->mode == 1) ? n->fp[1].Yrm : nullptr;
     return c;
 }
 
@@ -786,6 +794,7 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
         for (int j = 0; j < F.nl; ++j) { mlps[nl] = F.mlp[j]; Ys[nl] = F.Y[j]; ++nl; }
         if (f == 0) { mlps[nl] = n->conv1; Ys[nl] = n->H; ++nl; mlps[nl] = n->conv2; Ys[nl] = n->Z; ++nl; }
         int cat_buf = 0;
+        const float *rm_src = nullptr; int rm_stride = 0;      // row-major copy of d[interp] when a fused kernel produced it
         if (f == 0 && n->mode == 1 && n->head_fused) {
             if (!n->loss.set) return PSG_EINVAL;
             FpLevel &C = n->fp[1];
@@ -794,11 +803,14 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             c.scale = n->loss.scale; c.kappa = n->loss.kappa; c.dlogp = n->loss.dlogp;
             c.loss_rows = n->loss.loss_rows; c.hit = n->loss.hit;
             c.dI = tv(n->S[0], F.C2);
+            c.dI_rm = n->Srm; c.rm_only = n->xyz_grad ? 0 : 1;
+            rm_src = n->Srm; rm_stride = F.C2;
             PSG_RUN(PF_HEAD_CHAIN, psg_chain_fused(c, st));
         } else if (f > 0 && n->mode == 1 && F.streamed) {
             PsgFpStream q = fp_stream_desc(n, f, t, TView{nullptr, 0, 0});
             cat_buf = top_buf == 0 ? 1 : 0;
-            PSG_RUN(PF_FP_BWD, psg_fp_stream_bwd(q, top, tv(n->S[cat_buf], F.C1 + F.C2), st));
+            PSG_RUN(PF_FP_BWD, psg_fp_stream_bwd(q, top, tv(n->S[cat_buf], F.C1 + F.C2), n->Srm, st));
+            rm_src = n->Srm + F.C1; rm_stride = F.C1 + F.C2;
         } else
         PSG_TRY(chain_bwd(n, mlps, Ys, nl, rows, top, top_buf, &cat_buf, st));
         const int catw = F.C1 + F.C2;
@@ -821,11 +833,11 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             TView dst = tv(n->S[dst_buf], cw);
             TView mk = tv(C.Y[C.nl - 1], cw);
             PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[cat_buf], catw, F.C1), Nf, 3, F.nn_w + go * Nf * 3, F.csr_off + go * (Nc + 1),
-                               F.csr_perm + go * Nf * 3, Nf * 3, Nc, B, F.C2, dst, 0, &mk, st));
+                               F.csr_perm + go * Nf * 3, Nf * 3, Nc, B, F.C2, dst, 0, &mk, rm_src, rm_stride, st));
             top = dst; top_buf = dst_buf;
         } else {
             PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[cat_buf], catw, F.C1), Nf, 3, F.nn_w + go * Nf * 3, F.csr_off + go * (Nc + 1),
-                               F.csr_perm + go * Nf * 3, Nf * 3, Nc, B, F.C2, tv(n->dfeat[4], n->wfeat[4]), 0, nullptr, st));
+                               F.csr_perm + go * Nf * 3, Nf * 3, Nc, B, F.C2, tv(n->dfeat[4], n->wfeat[4]), 0, nullptr, rm_src, rm_stride, st));
         }
     }
     // ---- set abstraction, coarse to fine ----
@@ -841,11 +853,12 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
                 // feature columns only, unless the coordinate gradient is wanted too
                 const int gcols = n->xyz_grad ? Br.gpad : round_up(D, 16);
                 TView dl = tv(n->dfeat[l], n->wfeat[l], Br.col0), dg = tv(n->S[0], Br.gpad);
-                PSG_RUN(PF_SA_BWD, Br.fused ? psg_sa_fused_bwd(f, dl, dg, gcols, st) : psg_sa_stream_bwd(f, dl, dg, gcols, st));
+                const int rmo = n->xyz_grad ? 0 : 1;
+                PSG_RUN(PF_SA_BWD, Br.fused ? psg_sa_fused_bwd(f, dl, dg, gcols, n->Srm, rmo, st) : psg_sa_stream_bwd(f, dl, dg, gcols, n->Srm, rmo, st));
                 const size_t go = (size_t)t * B;
                 const int M = S * Br.K;
                 PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[0], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,
-                                   B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, st));
+                                   B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, n->Srm, Br.gpad, st));
                 if (n->xyz_grad)
                     PSG_RUN(PF_SEGSUM, psg_sa_xyz_backward(tv(n->S[0], Br.gpad), D, Br.K, S, B, Br.csr_off + go * (R + 1),
                                                            Br.csr_perm + go * M, R, n->dxyz[l - 1], n->dxyz[l], st));
@@ -859,7 +872,7 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             const size_t go = (size_t)t * B;
             const int M = S * Br.K;
             PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[gbuf], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,
-                               B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, st));
+                               B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, nullptr, 0, st));
             if (n->xyz_grad)
                 PSG_RUN(PF_SEGSUM, psg_sa_xyz_backward(tv(n->S[gbuf], Br.gpad), D, Br.K, S, B, Br.csr_off + go * (R + 1),
                                                        Br.csr_perm + go * M, R, n->dxyz[l - 1], n->dxyz[l], st));

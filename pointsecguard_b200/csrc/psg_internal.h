@@ -51,7 +51,8 @@ int psg_interp(TView feats, int S, const int *idx, const float *w, long long P, 
 size_t psg_csr_scratch_bytes(long long P, int M, int R);
 int psg_csr_build(const int *keys, long long P, int M, int R, int grp, int *offs, int *perm, void *scratch, cudaStream_t st);
 int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, const int *offs, const int *perm,
-               int M, int R, long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, cudaStream_t st);
+               int M, int R, long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, const float *src_rm,
+               int rm_stride, cudaStream_t st);
 int psg_copy_cols(TView src, TView dst, long long rows, int ncols, int accumulate, cudaStream_t st);
 int psg_index_points_rm(const float *pts, const long long *idx, int B, int N, int C, long long M, float *out,
                         cudaStream_t st);
@@ -72,11 +73,12 @@ struct PsgSaFused {
 bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2);
 size_t psg_sa_mask_words(long long rows, int n);
 int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st);
-int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st);
+int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float *dG_rm, int rm_only, cudaStream_t st);
 // chain_fused.cu: finest FP level + head, forward [+ loss gradient + backward] in one kernel
 #define PSG_CHAIN_MAX_OPS 10
 struct PsgChain {
     TView src; int S; const int *nn_idx; const float *nn_w; int Nf; int kin; long long rows;
+    const float *src_rm;               // row-major mirror of src ([rows of src][kin]) or null
     int nlayers;                       // hidden layers (conv + folded BN + ReLU), <= 4
     int n[4]; const float *wf[4]; int nwf[4]; const float *bias[4]; const float *wb[4]; int nwb[4];
     const float *head_wf; int head_nwf; const float *head_bias; const float *head_wb; int head_nwb;
@@ -84,22 +86,25 @@ struct PsgChain {
     int ncls, loss_kind, target; const int *labels; float scale, kappa; const float *dlogp;
     float *loss_rows; unsigned char *hit;
     TView zout, dI;
+    float *dI_rm; int rm_only;         // row-major copy of dI ([rows][kin]) for the segmented sum; rm_only: skip the T-layout store
 };
 int psg_chain_fused(const PsgChain &c, cudaStream_t st);
 // set-abstraction branch with streamed weights (widths beyond what sa_fused.cu keeps resident)
 bool psg_sa_streamable(int K, int gpad, int n0, int n1, int n2);
 int psg_sa_stream_fwd(const PsgSaFused &f, cudaStream_t st);
-int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st);
+int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float *dG_rm, int rm_only, cudaStream_t st);
 // feature-propagation level: [skip | 3-NN interpolation] -> MLP, forward and dgrad chain
 struct PsgFpStream {
     TView skip; int C1; TView coarse; int C2, S, Nf; const int *nn_idx; const float *nn_w; long long rows;
     int nl; int n[3]; const float *wf[3]; int nwf[3]; const float *bias[3]; const float *wb[3]; int nwb[3];
     unsigned *m[3];                    // ReLU bits of the hidden layers
     TView y_last;                      // output of the last layer (stored: next level's interpolation source)
+    float *y_last_rm;                  // optional row-major mirror of y_last ([rows][n_last]) for the next level's gather
+    const float *coarse_rm;            // optional row-major mirror of `coarse` ([rows][C2])
 };
 bool psg_fp_streamable(const PsgFpStream &f, bool forward);
 int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st);
-int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, cudaStream_t st);
+int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dcat_rm, cudaStream_t st);
 void psg_tile_use_clusters(bool on);
 void psg_tile_set_dbg(int v);
 void psg_tile_set_trace(long long *buf, int nlaunches);

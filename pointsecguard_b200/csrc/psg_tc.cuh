@@ -123,6 +123,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
 // make generic-proxy writes to shared memory visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 256-bit read-only global load (sm_100: LDG.E.256): a whole 32-byte sector per request; p 32-byte aligned
+__device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.L2::128B.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE, descriptor version 1 (Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)

@@ -306,6 +306,7 @@ struct SaBwdArgs {
     const unsigned *m0, *m1;
     const float *wb0, *wb1, *wb2; int nwb0, nwb1, nwb2;   // dgrad weights [cout/4][nwb][4], rows = cin
     TView dG; int gcols;
+    float *dG_rm; int rm_only;    // row-major copy of the gradient rows ([rows][gpad]) for the segmented sum
     int slab;                 // columns of dY2 scattered per pass (n2 is contracted in n2 / slab passes)
     long long rows;
     int gpad, n0, n1, n2;
@@ -458,9 +459,16 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
                 float v[16];
                 tc::tmem_ld16(tl + (uint32_t)c16, v);
                 if (valid) {
+                    if (!a.rm_only) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        tv_st(a.dG, row, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                        for (int c = 0; c < 4; ++c)
+                            tv_st(a.dG, row, (c16 >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                    }
+                    if (a.dG_rm) {
+                        float4 *d = reinterpret_cast<float4 *>(a.dG_rm + row * a.gpad + c16);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) d[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    }
                 }
             }
             tc::fence_before_sync();
@@ -583,12 +591,13 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     return PSG_OK;
 }
 
-int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, cudaStream_t st)
+int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float *dG_rm, int rm_only, cudaStream_t st)
 {
     SaBwdArgs a;
     a.dout = dout; a.outv = f.out; a.arg = f.arg; a.m0 = f.m0; a.m1 = f.m1;
     a.wb0 = f.wb[0]; a.wb1 = f.wb[1]; a.wb2 = f.wb[2]; a.nwb0 = f.nwb[0]; a.nwb1 = f.nwb[1]; a.nwb2 = f.nwb[2];
     a.dG = dG; a.gcols = gcols; a.rows = f.rows;
+    a.dG_rm = dG_rm; a.rm_only = (dG_rm && rm_only) ? 1 : 0;
     a.slab = bwd_slab(f.n[0], f.n[1], f.n[2]);
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
