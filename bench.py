@@ -163,6 +163,9 @@ def run_native(args, rank, world, local_rank):
     from pointsecguard_b200.engine import MLP_TF32
     from pointsecguard_b200.models.pointnet2_sem_seg import get_model
 
+    for opt in ("sa_ng", "clusters"):                 # A/B switches of the library (experiments only)
+        if os.environ.get("PSG_OPT_" + opt.upper()):
+            L.psg_set_option(opt.encode(), int(os.environ["PSG_OPT_" + opt.upper()]))
     model = get_model(13)
     # init="he": a random network whose predictions depend on the input, so attack_metrics are informative
     model.load_state_dict(syn.make_state_dict("ssg", init="he"))

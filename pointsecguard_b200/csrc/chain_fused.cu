@@ -24,6 +24,8 @@
 #include "psg_tc.cuh"
 #include "psg_epi.cuh"
 
+long long *psg_tile_trace_slot();
+
 namespace {
 
 constexpr int kWorkers = 128;
@@ -697,7 +699,7 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     }
     a.rows = rows; a.ntiles = (int)((rows + 127) / 128);
     a.dbg = g_dbg;
-    a.trace = (g_trace && g_trace_n < g_trace_cap) ? g_trace + (size_t)(g_trace_n++) * 2048 : nullptr;
+    a.trace = psg_tile_trace_slot();
     a.abytes = b.amax_cols * 512;
     const int sms = (g_psg_sm_cap > 0 && g_psg_sm_cap < g_sms) ? g_psg_sm_cap : g_sms;
     const int cs = g_use_clusters ? pick_cluster(a, a.ntiles, sms) : 1;
@@ -913,4 +915,5 @@ int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dc
 // thread-block clusters for the deep levels (on by default; the switch exists for A/B measurements)
 void psg_tile_use_clusters(bool on) { g_use_clusters = on; }
 void psg_tile_set_dbg(int v) { g_dbg = v; }
+long long *psg_tile_trace_slot() { return (g_trace && g_trace_n < g_trace_cap) ? g_trace + (size_t)(g_trace_n++) * 2048 : nullptr; }
 void psg_tile_set_trace(long long *buf, int nlaunches) { g_trace = buf; g_trace_cap = nlaunches; g_trace_n = 0; }

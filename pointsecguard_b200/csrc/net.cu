@@ -374,6 +374,7 @@ extern "C" int psg_set_option(const char *name, int value)
 {
     if (!name) return PSG_EINVAL;
     if (!strcmp(name, "clusters")) { psg_tile_use_clusters(value != 0); return PSG_OK; }
+    if (!strcmp(name, "sa_ng")) { psg_sa_force_ng(value); return PSG_OK; }
     if (!strcmp(name, "dbg")) { psg_tile_set_dbg(value); return PSG_OK; }
     if (!strcmp(name, "sm_cap")) { g_psg_sm_cap = value > 0 ? value : 0; return PSG_OK; }
     return PSG_EINVAL;

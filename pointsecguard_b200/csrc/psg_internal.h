@@ -71,6 +71,7 @@ struct PsgSaFused {
     TView out; unsigned char *arg; // pooled rows [groups][n2 slice of the level's features], arg-max [groups][n2]
 };
 bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2);
+void psg_sa_force_ng(int ng);      // A/B switch: tiles in flight per CTA of the fused SA kernels (0 = automatic)
 size_t psg_sa_mask_words(long long rows, int n);
 int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st);
 int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float *dG_rm, int rm_only, cudaStream_t st);
@@ -107,6 +108,7 @@ int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st);
 int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dcat_rm, cudaStream_t st);
 void psg_tile_use_clusters(bool on);
 void psg_tile_set_dbg(int v);
+long long *psg_tile_trace_slot();   // next [4][512] block of the debug trace buffer, or null
 void psg_tile_set_trace(long long *buf, int nlaunches);
 // geomgrad.cu: gradient w.r.t. coordinates through grouping and interpolation weights
 int psg_sa_xyz_backward(TView dG, int D, int K, long long groups_per_p, long long P, const int *offs, const int *perm, int R,

@@ -18,6 +18,7 @@
 // activation (8 B per row in SA1).  Per tile: scatter dOut to the arg-max rows -> dY2 in shared
 // memory -> three dgrad GEMMs with the bit masks applied in the epilogues -> dG rows to HBM, which
 // the deterministic segmented sum (gather.cu) then reduces by source point.
+#include <cstdio>
 #include "psg_common.cuh"
 #include "psg_internal.h"
 #include "psg_tc.cuh"
@@ -55,6 +56,13 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t sA, uint32_t
     }
 }
 
+__device__ __forceinline__ long long gtimer()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct SaFwdArgs {
     TView feats; int D; const float *xyz; long long cloud_stride; int nclouds; int Nsrc;
     const float *new_xyz; const int *idx; long long rows; int S;
@@ -64,6 +72,7 @@ struct SaFwdArgs {
     unsigned *m0, *m1;
     TView out; unsigned char *arg;
     int ntiles;
+    long long *trace;
 };
 
 // accumulator -> bias + ReLU -> next A operand in shared memory (+ one ReLU bit per element)
@@ -92,7 +101,7 @@ __device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n,
 }
 
 template <int K, int NG>
-__global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
+__global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_fwd_kernel(SaFwdArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG];
@@ -110,6 +119,9 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
     const uint32_t sW0 = sbase, sW1 = sW0 + szW0, sW2 = sW1 + szW1, sG = sW2 + szW2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long *gtr = (a.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+                         ? a.trace + 3 * 512 + (blockIdx.x ? 8 : 0) : nullptr;
+    if (gtr) gtr[0] = gtimer();
     const int nmax = max(a.n0, max(a.n1, a.n2));
     const uint32_t gcols = tc::next_pow2_cols(nmax);       // TMEM columns per group
     const uint32_t ncols = tc::next_pow2_cols((int)(gcols * NG));   // tcgen05.alloc takes powers of two
@@ -135,36 +147,30 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    if (gtr) gtr[1] = gtimer();
     tc::pdl_launch_dependents();      // the next kernel's prologue may overlap our tail ...
     tc::pdl_wait();                   // ... and ours overlapped our predecessor's: wait for its results now
+    if (gtr) gtr[2] = gtimer();
     const uint32_t tmem = tmem_slot;
     const int tstride = gridDim.x * NG;
 
-    if (warp == NG * 4) {
+    if (warp >= NG * 4) {
         if (lane == 0) {
-            // ---- MMA issuer: serves whichever group has its next A operand ready ----
-            int tile[NG], layer[NG]; uint32_t ph[NG]; bool act[NG];
-            int nact = 0;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                tile[g] = blockIdx.x * NG + g; layer[g] = 0; ph[g] = 0;
-                act[g] = tile[g] < a.ntiles; nact += act[g] ? 1 : 0;
-            }
-            while (nact) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    if (!act[g] || !tc::mbar_test_wait(tc::smem_u32(&bar_in[g]), ph[g])) continue;
-                    ph[g] ^= 1u;
+            // ---- MMA issuers: one warp per tile in flight, so that a group's next layer never queues behind
+            // the other groups' issue work (a single polling thread cost ~1000 cycles per layer at NG = 4) ----
+            const int g = warp - NG * 4;
+            const uint32_t b_in = tc::smem_u32(&bar_in[g]), b_acc = tc::smem_u32(&bar_acc[g]);
+            const uint32_t sA = sG + g * szG, tm = tmem + g * gcols;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x * NG + g; tile < a.ntiles; tile += tstride) {
+#pragma unroll 1
+                for (int layer = 0; layer < 3; ++layer) {
+                    tc::mbar_wait(b_in, ph); ph ^= 1u;
                     tc::fence_after_sync();
-                    const uint32_t sA = sG + g * szG, tm = tmem + g * gcols;
-                    if (layer[g] == 0) issue_layer(tm, sA, sW0, a.gpad / 4, a.n0);
-                    else if (layer[g] == 1) issue_layer(tm, sA, sW1, a.n0 / 4, a.n1);
+                    if (layer == 0) issue_layer(tm, sA, sW0, a.gpad / 4, a.n0);
+                    else if (layer == 1) issue_layer(tm, sA, sW1, a.n0 / 4, a.n1);
                     else issue_layer(tm, sA, sW2, a.n1 / 4, a.n2);
-                    tc::mma_commit(tc::smem_u32(&bar_acc[g]));
-                    if (++layer[g] == 3) {
-                        layer[g] = 0; tile[g] += tstride;
-                        if (tile[g] >= a.ntiles) { act[g] = false; --nact; }
-                    }
+                    tc::mma_commit(b_acc);
                 }
             }
         }
@@ -178,6 +184,10 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
         const unsigned gmask = (K == 32) ? 0xffffffffu : (0xffffu << (16 * ((lane / 16))));
         const int w0words = (a.n0 + 31) / 32, w1words = (a.n1 + 31) / 32;
         uint32_t ph = 0;
+        long long *tr = (a.trace && blockIdx.x == 0 && r == 0 && grp < 2) ? a.trace + grp * 512 : nullptr;
+        int tn = 0;
+#define SA_STAMP() do { if (tr && tn < 510) tr[tn++] = clock64(); } while (0)
+        SA_STAMP();
         int tile = blockIdx.x * NG + grp;
         int src_next = (tile < a.ntiles && (long long)tile * 128 + r < a.rows) ? a.idx[(long long)tile * 128 + r] : 0;
         for (; tile < a.ntiles; tile += tstride) {
@@ -219,20 +229,26 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
             }
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
+            SA_STAMP();
             // ---- layer 0 epilogue -> Y0 ----
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            SA_STAMP();
             epilogue_relu_to_smem(tl, a.n0, sbias[0], pY0, a.m0 + (size_t)tile * w0words * 128, r);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
+            SA_STAMP();
             // ---- layer 1 epilogue -> Y1 (reuses the gather buffer) ----
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            SA_STAMP();
             epilogue_relu_to_smem(tl, a.n1, sbias[1], pA, a.m1 + (size_t)tile * w1words * 128, r);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
+            SA_STAMP();
             // ---- layer 2 epilogue: bias + ReLU + max over the K rows of each neighbourhood ----
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            SA_STAMP();
             const long long g = row / K;
             if (szG >= 16384) {
                 // transposed pool: the tile's operand buffer is dead once MMA 2 has completed (every warp of
@@ -292,11 +308,13 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_fwd_kernel(SaFwdArgs a)
                     *reinterpret_cast<uint4 *>(a.arg + g * a.n2 + c16) = pk;
                 }
             }
+            SA_STAMP();
             tc::fence_before_sync();
         }
     }
     tc::fence_before_sync();
     __syncthreads();
+    if (gtr) gtr[3] = gtimer();
     if (warp == NG * 4) tc::tmem_dealloc(tmem, ncols);
 }
 
@@ -311,6 +329,7 @@ struct SaBwdArgs {
     long long rows;
     int gpad, n0, n1, n2;
     int ntiles;
+    long long *trace;
 };
 
 // accumulator -> ReLU-bit mask -> next A operand in shared memory
@@ -339,7 +358,7 @@ __device__ __forceinline__ void epilogue_mask_to_smem(uint32_t tmem_lane, int n,
 }
 
 template <int K, int NG>
-__global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
+__global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_bwd_kernel(SaBwdArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG];
@@ -382,32 +401,23 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
     const uint32_t tmem = tmem_slot;
     const int tstride = gridDim.x * NG;
 
-    if (warp == NG * 4) {
+    if (warp >= NG * 4) {
         if (lane == 0) {
-            int tile[NG], layer[NG]; uint32_t ph[NG]; bool act[NG];
-            int nact = 0;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                tile[g] = blockIdx.x * NG + g; layer[g] = 0; ph[g] = 0;
-                act[g] = tile[g] < a.ntiles; nact += act[g] ? 1 : 0;
-            }
-            while (nact) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    if (!act[g] || !tc::mbar_test_wait(tc::smem_u32(&bar_in[g]), ph[g])) continue;
-                    ph[g] ^= 1u;
+            // ---- MMA issuers: one warp per tile in flight (see sa_fwd_kernel) ----
+            const int g = warp - NG * 4;
+            const uint32_t b_in = tc::smem_u32(&bar_in[g]), b_acc = tc::smem_u32(&bar_acc[g]);
+            const uint32_t sD = sG + g * szG, tm = tmem + g * gcols;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x * NG + g; tile < a.ntiles; tile += tstride) {
+#pragma unroll 1
+                for (int L = 0; L < nslab + 2; ++L) {
+                    tc::mbar_wait(b_in, ph); ph ^= 1u;
                     tc::fence_after_sync();
-                    const uint32_t sD2 = sG + g * szG, sD1 = sD2, sD0 = sD2, tm = tmem + g * gcols;
-                    const int L = layer[g];
                     if (L < nslab)                                                        // dY1 (+)= dY2[:, slab L] W2[slab L]
-                        issue_layer(tm, sD2, sW2 + (uint32_t)L * (a.slab / 4) * a.n1 * 16, a.slab / 4, a.n1, L > 0 ? 1u : 0u);
-                    else if (L == nslab) issue_layer(tm, sD1, sW1, a.n1 / 4, a.n0);        // dY0 = dY1 W1
-                    else issue_layer(tm, sD0, sW0, a.n0 / 4, a.gpad);                     // dG  = dY0 W0
-                    tc::mma_commit(tc::smem_u32(&bar_acc[g]));
-                    if (++layer[g] == nslab + 2) {
-                        layer[g] = 0; tile[g] += tstride;
-                        if (tile[g] >= a.ntiles) { act[g] = false; --nact; }
-                    }
+                        issue_layer(tm, sD, sW2 + (uint32_t)L * (a.slab / 4) * a.n1 * 16, a.slab / 4, a.n1, L > 0 ? 1u : 0u);
+                    else if (L == nslab) issue_layer(tm, sD, sW1, a.n1 / 4, a.n0);        // dY0 = dY1 W1
+                    else issue_layer(tm, sD, sW0, a.n0 / 4, a.gpad);                     // dG  = dY0 W0
+                    tc::mma_commit(b_acc);
                 }
             }
         }
@@ -420,6 +430,9 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
         const int k = r % K;
         const int w0words = (a.n0 + 31) / 32, w1words = (a.n1 + 31) / 32;
         uint32_t ph = 0;
+        long long *tr = (a.trace && blockIdx.x == 0 && r == 0 && grp < 2) ? a.trace + grp * 512 : nullptr;
+        int tn = 0;
+        SA_STAMP();
         for (int tile = blockIdx.x * NG + grp; tile < a.ntiles; tile += tstride) {
             const long long row = (long long)tile * 128 + r;
             const bool valid = row < a.rows;
@@ -443,18 +456,24 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
                 tc::fence_before_sync();
                 tc::fence_async_smem();
                 tc::mbar_arrive(b_in);
+                SA_STAMP();
                 tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();     // this slab's MMAs are done
+                SA_STAMP();
             }
             epilogue_mask_to_smem(tl, a.n1, a.m1 + (size_t)tile * w1words * 128, pD1, r);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
+            SA_STAMP();
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            SA_STAMP();
             epilogue_mask_to_smem(tl, a.n0, a.m0 + (size_t)tile * w0words * 128, pD0, r);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
+            SA_STAMP();
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
+            SA_STAMP();
             for (int c16 = 0; c16 < a.gcols; c16 += 16) {
                 float v[16];
                 tc::tmem_ld16(tl + (uint32_t)c16, v);
@@ -471,6 +490,7 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
                     }
                 }
             }
+            SA_STAMP();
             tc::fence_before_sync();
         }
     }
@@ -480,9 +500,7 @@ __global__ void __launch_bounds__(NG * 128 + 32) sa_bwd_kernel(SaBwdArgs a)
 }
 
 int g_num_sms = 0;
-constexpr size_t kSmemBudget = 226 * 1024;     // per SM, minus what the runtime reserves per CTA
 constexpr size_t kSmemPerCtaMax = 224 * 1024;
-constexpr size_t kStatFwd = 3072, kStatBwd = 2048;   // static shared memory (barriers [+ biases]) + 1 KB reserved per CTA
 
 inline size_t r1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
 inline int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
@@ -507,31 +525,82 @@ inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng)
 }
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
-// CTAs per SM: shared memory (dynamic + 1 KB static + 1 KB reserved) and TMEM columns (512 per SM)
-inline int ctas_per_sm(size_t smem, int tmem_cols, size_t stat = 2048)
+// CTAs per SM as the driver sees it (registers, threads, shared memory) and TMEM columns (512 per SM).
+// The first version of this file modelled shared memory only and believed in 4 CTAs per SM where the
+// register file allowed one (profiles/r1_notes.md: the last CTA of SA1 forward started 66 us after the first).
+template <class Kern>
+int ctas_per_sm(Kern kern, int threads, size_t smem, int tmem_cols)
 {
-    int occ = (int)(kSmemBudget / (smem + stat));     // + static (barriers [, 1.5 KB biases]) + 1 KB reserved per CTA
+    // one kernel instantiation serves several levels: raise the opt-in limit to the file's maximum once, never lower it
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax) != cudaSuccess) return 0;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) return 0;
     occ = occ < 512 / tmem_cols ? occ : 512 / tmem_cols;
-    return occ < 1 ? 1 : (occ > 8 ? 8 : occ);
+    return occ > 8 ? 8 : occ;
 }
 
-template <class Kern>
-int launch_cfg(Kern kern, size_t smem, int ntiles, int ng, int tmem_cols, int *grid, size_t stat)
+int num_sms()
 {
     if (g_num_sms == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess ||
             cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            return PSG_ECUDA;
+            g_num_sms = 0;
     }
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
-    const int want = (ntiles + ng - 1) / ng;
-    const int sms = (g_psg_sm_cap > 0 && g_psg_sm_cap < g_num_sms) ? g_psg_sm_cap : g_num_sms;
-    const int cap = sms * ctas_per_sm(smem, tmem_cols, stat);
-    *grid = want < cap ? want : cap;
-    return PSG_OK;
+    return (g_psg_sm_cap > 0 && g_psg_sm_cap < g_num_sms) ? g_psg_sm_cap : g_num_sms;
 }
 
+template <int K> void (*fwd_kern(int ng))(SaFwdArgs)
+{
+    return ng == 1 ? sa_fwd_kernel<K, 1> : ng == 2 ? sa_fwd_kernel<K, 2> : ng == 3 ? sa_fwd_kernel<K, 3> : sa_fwd_kernel<K, 4>;
+}
+template <int K> void (*bwd_kern(int ng))(SaBwdArgs)
+{
+    return ng == 1 ? sa_bwd_kernel<K, 1> : ng == 2 ? sa_bwd_kernel<K, 2> : ng == 3 ? sa_bwd_kernel<K, 3> : sa_bwd_kernel<K, 4>;
+}
+
+// tiles in flight per SM = NG (per CTA, sharing the resident weights) x CTAs per SM: take the combination
+// that keeps the most tiles in flight (the per-tile chain is latency-bound); ties go to the larger NG
+// (fewer CTAs: fewer prologues, weights loaded fewer times).  Decisions are cached per configuration.
+struct Pick { int ng, occ; };
+template <class KernOf, class SmemOf>
+Pick pick_ng(KernOf kern_of, SmemOf smem_of, int gc, int ng_forced = 0)
+{
+    Pick best{0, 0};
+    int best_tiles = 0;
+    for (int ng = 1; ng <= 4; ++ng) {
+        if (ng_forced && ng != ng_forced) continue;
+        const size_t sm = smem_of(ng);
+        if (sm > kSmemPerCtaMax || ng * gc > 512) break;
+        const int occ = ctas_per_sm(kern_of(ng), ng * 160, sm, (int)pow2cols(ng * gc));
+        if (ng * occ >= best_tiles && occ > 0) { best_tiles = ng * occ; best = Pick{ng, occ}; }
+    }
+    return best;
+}
+
+struct PickKey { int dir, K, gpad, n0, n1, n2, cap; };
+struct PickEnt { PickKey k; Pick p; };
+PickEnt g_picks[32];
+int g_npicks = 0;
+int g_ng_forced = 0;
+
+}  // namespace
+
+void psg_sa_force_ng(int ng) { g_ng_forced = ng; g_npicks = 0; }
+
+namespace {
+template <class KernOf, class SmemOf>
+Pick cached_pick(int dir, int K, int gpad, int n0, int n1, int n2, KernOf kern_of, SmemOf smem_of, int gc)
+{
+    const PickKey key{dir, K, gpad, n0, n1, n2, g_psg_sm_cap};
+    for (int i = 0; i < g_npicks; ++i) {
+        const PickKey &q = g_picks[i].k;
+        if (q.dir == dir && q.K == K && q.gpad == gpad && q.n0 == n0 && q.n1 == n1 && q.n2 == n2 && q.cap == key.cap) return g_picks[i].p;
+    }
+    const Pick p = pick_ng(kern_of, smem_of, gc, g_ng_forced);
+    if (g_npicks < 32) g_picks[g_npicks++] = PickEnt{key, p};
+    return p;
+}
 }  // namespace
 
 bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2)
@@ -547,28 +616,6 @@ size_t psg_sa_mask_words(long long rows, int n)
     return (size_t)((rows + 127) / 128) * ((n + 31) / 32) * 128;
 }
 
-// tiles in flight per SM = NG (per CTA, sharing the resident weights) x CTAs per SM: take the
-// combination that keeps the most tiles in flight (the per-tile chain is latency-bound)
-template <class F>
-int pick_ng(F smem_of, int gc, size_t stat)
-{
-    int best = 1, best_tiles = 0;
-    for (int ng = 1; ng <= 4; ++ng) {
-        const size_t sm = smem_of(ng);
-        if (sm > kSmemPerCtaMax || ng * gc > 512) break;
-        const int tiles = ng * ctas_per_sm(sm, (int)pow2cols(ng * gc), stat);
-        if (tiles > best_tiles) { best_tiles = tiles; best = ng; }
-    }
-    return best;
-}
-
-#define SA_LAUNCH(KERN, KK, NGG, ARGS, SMEM, COLS, STAT)                                       \
-    do {                                                                                   \
-        int grid__ = 0, rc__;                                                              \
-        if ((rc__ = launch_cfg(KERN<KK, NGG>, SMEM, ARGS.ntiles, NGG, COLS, &grid__, STAT)) != PSG_OK) return rc__; \
-        if (psg_launch_pdl(KERN<KK, NGG>, dim3(grid__), dim3(NGG * 128 + 32), SMEM, st, 1, ARGS) != cudaSuccess) return PSG_ECUDA; \
-    } while (0)
-
 int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
 {
     SaFwdArgs a;
@@ -579,14 +626,18 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     a.b0 = f.bias[0]; a.b1 = f.bias[1]; a.b2 = f.bias[2];
     a.m0 = f.m0; a.m1 = f.m1; a.out = f.out; a.arg = f.arg;
     a.ntiles = (int)((f.rows + 127) / 128);
+    a.trace = psg_tile_trace_slot();
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.n2 ? a.n0 : a.n2) : (a.n1 > a.n2 ? a.n1 : a.n2));
-    const int ng = pick_ng([&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g); }, gc, kStatFwd);
-    const size_t smem = fwd_smem(a.gpad, a.n0, a.n1, a.n2, ng);
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
-#define SA_FWD_CASE(KK, NGG) if (f.K == KK && ng == NGG) SA_LAUNCH(sa_fwd_kernel, KK, NGG, a, smem, (int)pow2cols(gc * NGG), kStatFwd)
-    SA_FWD_CASE(32, 1); SA_FWD_CASE(32, 2); SA_FWD_CASE(32, 3); SA_FWD_CASE(32, 4);
-    SA_FWD_CASE(16, 1); SA_FWD_CASE(16, 2); SA_FWD_CASE(16, 3); SA_FWD_CASE(16, 4);
-#undef SA_FWD_CASE
+    auto smem_of = [&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g); };
+    const Pick pk = f.K == 32 ? cached_pick(0, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern<32>, smem_of, gc)
+                              : cached_pick(0, 16, a.gpad, a.n0, a.n1, a.n2, fwd_kern<16>, smem_of, gc);
+    if (pk.ng < 1 || pk.occ < 1 || num_sms() < 1) return PSG_EUNSUPPORTED;
+    const int want = (a.ntiles + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
+    const int grid = want < cap ? want : cap;
+    auto kern = f.K == 32 ? fwd_kern<32>(pk.ng) : fwd_kern<16>(pk.ng);
+    { cudaError_t e__ = psg_launch_pdl(kern, dim3(grid), dim3(pk.ng * 160), smem_of(pk.ng), st, 1, a);
+      if (e__ != cudaSuccess) { fprintf(stderr, "sa launch: %s (ng %d occ %d grid %d smem %zu)\n", cudaGetErrorString(e__), pk.ng, pk.occ, grid, smem_of(pk.ng)); return PSG_ECUDA; } }
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
@@ -601,14 +652,18 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float
     a.slab = bwd_slab(f.n[0], f.n[1], f.n[2]);
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
+    a.trace = psg_tile_trace_slot();
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.gpad ? a.n0 : a.gpad) : (a.n1 > a.gpad ? a.n1 : a.gpad));
-    const int ng = pick_ng([&](int g) { return bwd_smem(a.gpad, a.n0, a.n1, a.n2, g); }, gc, kStatBwd);
-    const size_t smem = bwd_smem(a.gpad, a.n0, a.n1, a.n2, ng);
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
-#define SA_BWD_CASE(KK, NGG) if (f.K == KK && ng == NGG) SA_LAUNCH(sa_bwd_kernel, KK, NGG, a, smem, (int)pow2cols(gc * NGG), kStatBwd)
-    SA_BWD_CASE(32, 1); SA_BWD_CASE(32, 2); SA_BWD_CASE(32, 3); SA_BWD_CASE(32, 4);
-    SA_BWD_CASE(16, 1); SA_BWD_CASE(16, 2); SA_BWD_CASE(16, 3); SA_BWD_CASE(16, 4);
-#undef SA_BWD_CASE
+    auto smem_of = [&](int g) { return bwd_smem(a.gpad, a.n0, a.n1, a.n2, g); };
+    const Pick pk = f.K == 32 ? cached_pick(1, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern<32>, smem_of, gc)
+                              : cached_pick(1, 16, a.gpad, a.n0, a.n1, a.n2, bwd_kern<16>, smem_of, gc);
+    if (pk.ng < 1 || pk.occ < 1 || num_sms() < 1) return PSG_EUNSUPPORTED;
+    const int want = (a.ntiles + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
+    const int grid = want < cap ? want : cap;
+    auto kern = f.K == 32 ? bwd_kern<32>(pk.ng) : bwd_kern<16>(pk.ng);
+    { cudaError_t e__ = psg_launch_pdl(kern, dim3(grid), dim3(pk.ng * 160), smem_of(pk.ng), st, 1, a);
+      if (e__ != cudaSuccess) { fprintf(stderr, "sa launch: %s (ng %d occ %d grid %d smem %zu)\n", cudaGetErrorString(e__), pk.ng, pk.occ, grid, smem_of(pk.ng)); return PSG_ECUDA; } }
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=16)
     ap.add_argument("--launches", type=int, default=12)
     ap.add_argument("--dbg", type=int, default=0)
+    ap.add_argument("--raw", action="store_true", help="print the raw stamp deltas of every launch (fused SA kernels included)")
     args = ap.parse_args()
     from pointsecguard_b200 import _lib as L
     from pointsecguard_b200 import synthetic as syn, torchattacks
@@ -44,6 +45,20 @@ def main():
     torch.cuda.synchronize()
     L.psg_debug_trace(None, 0)
     t = buf.cpu().numpy()
+    if args.raw:
+        for li in range(args.launches):
+            for role in range(3):
+                w = t[li, role]
+                n = int((w != 0).sum())
+                if n > 1:
+                    if role == 0:
+                        g = t[li, 3]
+                        if g[0]:
+                            print(f"launch {li} globaltimer ns: cta0 entry->sync {g[1]-g[0]} sync->pdl {g[2]-g[1]} pdl->exit {g[3]-g[2]}; "
+                                  f"last cta: entry(rel cta0) {g[8]-g[0]} entry->sync {g[9]-g[8]} sync->pdl {g[10]-g[9]} pdl->exit {g[11]-g[10]}")
+                    print(f"launch {li} role {role}: {n} stamps, span {(w[n - 1] - w[0]) / 1.9e3:.1f} us; deltas",
+                          [int(w[i + 1] - w[i]) for i in range(n - 1)])
+        return
     for li in range(args.launches):
         w0, w1, mm = t[li, 0], t[li, 1], t[li, 2]
         n0 = int((w0 != 0).sum())
