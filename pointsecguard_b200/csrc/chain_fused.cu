@@ -219,37 +219,16 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
     }
 }
 
-// dY[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0 for columns [col0, col0 + 4*planes)
+// dY[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0 for columns [col0, col0 + 4*planes): the warp fetches
+// each chunk of its neighbourhoods once and shares it through a staging area (psg_scatter_warp, psg_epi.cuh)
 __device__ __forceinline__ void pre_scatter(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r, int col0,
-                                            int planes)
+                                            int planes, float4 *stage_d, uchar4 *stage_a)
 {
     const long long g = (valid ? row : 0) / s.K;
-    const int k = r % s.K;
-    const int c0 = col0 >> 2;
-    const float *db = s.dout.base + tv_off(s.dout, g, c0), *ob = s.outv.base + tv_off(s.outv, g, c0);
-    const unsigned char *ab = s.sarg + g * s.sargC + col0;
-    constexpr int NB = 8;
-    for (int cb = 0; cb < planes; cb += NB) {
-        float4 d[NB], o[NB]; uchar4 am[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const bool in = cb + j < planes;
-            d[j] = in ? *reinterpret_cast<const float4 *>(db + (size_t)(cb + j) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
-            o[j] = in ? *reinterpret_cast<const float4 *>(ob + (size_t)(cb + j) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
-            am[j] = in ? *reinterpret_cast<const uchar4 *>(ab + 4 * (cb + j)) : make_uchar4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            if (cb + j < planes) {
-                float4 q;
-                q.x = (valid && am[j].x == k && o[j].x > 0.f) ? d[j].x : 0.f;
-                q.y = (valid && am[j].y == k && o[j].y > 0.f) ? d[j].y : 0.f;
-                q.z = (valid && am[j].z == k && o[j].z > 0.f) ? d[j].z : 0.f;
-                q.w = (valid && am[j].w == k && o[j].w > 0.f) ? d[j].w : 0.f;
-                *plane_ptr(pA, cb + j, r) = q;
-            }
-        }
-    }
+    const int lane = r & 31;
+    auto put = [&](int c, float4 q) { *plane_ptr(pA, c, r) = q; };
+    if (s.K == 32) psg_scatter_warp<32>(s.dout, s.outv, s.sarg, s.sargC, g, valid, lane, col0 >> 2, planes, stage_d, stage_a, put);
+    else psg_scatter_warp<16>(s.dout, s.outv, s.sarg, s.sargC, g, valid, lane, col0 >> 2, planes, stage_d, stage_a, put);
 }
 
 // CS > 1: a cluster of CS CTAs works on ONE tile (NG == 1); CTA q computes columns [q n/CS, (q+1) n/CS)
@@ -277,6 +256,8 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
     unsigned char *pA0 = base;
     unsigned *pMask = reinterpret_cast<unsigned *>(base + (size_t)NG * a.abytes + (size_t)kStages * a.stage_bytes);
     float *sbias = reinterpret_cast<float *>(pMask + (size_t)NG * (a.mbytes / 4));
+    float4 *stage_d = reinterpret_cast<float4 *>(sbias + a.bias_floats);          // [NG * 4 warps][32]
+    uchar4 *stage_a = reinterpret_cast<uchar4 *>(stage_d + NG * 4 * 32);           // [NG * 4 warps][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ncols = (uint32_t)(a.tcols * NG);
@@ -442,7 +423,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                 if (op.pre == PRE_GROUP) pre_group(a.src, pA, row, valid, r);
                 else if (op.pre == PRE_FP) { if (a.src.lcols) pre_load(a.src, pA, row, valid, r); pre_interp(a.src, pA, row, valid, r); }
                 else if (op.pre == PRE_LOAD) pre_load(a.src, pA, row, valid, r);
-                else if (op.pre == PRE_SCATTER) pre_scatter(a.src, pA, row, valid, r, op.pre_a, op.planes);
+                else if (op.pre == PRE_SCATTER) pre_scatter(a.src, pA, row, valid, r, op.pre_a, op.planes, stage_d + warp * 32, stage_a + warp * 32);
                 tc::fence_before_sync();
                 if (CS > 1) {
                     tc::fence_async_all();
@@ -720,8 +701,10 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     a.mbytes = nslots * a.mwords * 128 * 4;
     for (int o = 0; o < a.nops; ++o)
         if (a.ops[o].epi == EPI_MAXPOOL && a.mbytes < 16384) a.mbytes = 16384;     // pool scratch: 4 KB per worker warp
+    bool scatters = false;
+    for (int o = 0; o < a.nops; ++o) scatters = scatters || a.ops[o].pre == PRE_SCATTER;
     auto need = [&](int ng, int stg) {
-        return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * a.mbytes + (size_t)a.bias_floats * 4 + 128;
+        return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * a.mbytes + (size_t)a.bias_floats * 4 + (scatters ? (size_t)ng * 4 * 32 * 20 : 0) + 128;
     };
     // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
     int ng = (cs == 1 && a.ntiles > sms && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;

@@ -15,29 +15,30 @@
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 12;
 constexpr int kBlk = 8;                       // chunk planes (4 floats of K each) per stage
 constexpr int kBNMax = 128;
 constexpr int kABytes = kBlk * 2048;          // 16 KB
-constexpr int kBBytes = kBlk * kBNMax * 16;   // 16 KB
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024;
+constexpr int kRingBytes = 200 * 1024;        // operand ring: as many stages as fit (the K loop is a latency chain)
+constexpr int kSmemBytes = kRingBytes + 1024;
 
 template <int EPI>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g)
+__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn_tile, int kStages)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bar_full[kStages], bar_empty[kStages], bar_acc;
+    __shared__ __align__(8) unsigned long long bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc;
     __shared__ uint32_t tmem_slot;
 
     // 1024-byte aligned operand staging area
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int kBBytes = kBlk * bn_tile * 16;
     const uint32_t sA = sbase, sB = sbase + kStages * kABytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row0 = (long long)blockIdx.x * 128;
-    const int n0 = blockIdx.y * kBNMax;
-    const int BN = min(kBNMax, g.nout_pad - n0);
+    const int n0 = blockIdx.y * bn_tile;
+    const int BN = min(bn_tile, g.nout_pad - n0);
     const uint32_t ncols = tc::next_pow2_cols(BN);
 
     if (threadIdx.x == 0) {
@@ -49,6 +50,8 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g)
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();                  // launched with programmatic stream serialization: the prologue overlapped the predecessor
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
@@ -144,8 +147,14 @@ int launch(const PsgGemmArgs &g, cudaStream_t st)
             return PSG_ECUDA;
         attr_done = true;
     }
-    dim3 grid((unsigned)g.mtiles, (unsigned)((g.nout_pad + kBNMax - 1) / kBNMax));
-    gemm_tc_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(g);
+    // few row tiles (the deep levels): narrower column tiles spread the layer over more SMs, and the smaller
+    // B stages let more of the K loop be in flight at once
+    int bn = kBNMax;
+    while (bn > 32 && g.mtiles * ((g.nout_pad + bn - 1) / bn) < 96) bn >>= 1;
+    int nst = kRingBytes / (kABytes + kBlk * bn * 16);
+    if (nst > kMaxStages) nst = kMaxStages;
+    dim3 grid((unsigned)g.mtiles, (unsigned)((g.nout_pad + bn - 1) / bn));
+    if (psg_launch_pdl(gemm_tc_kernel<EPI>, grid, dim3(kThreads), (size_t)kSmemBytes, st, 1, g, bn, nst) != cudaSuccess) return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

@@ -59,6 +59,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// busy polling (no hardware suspend): for single-thread roles whose wake-up latency is on the critical path
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_test_wait(bar, parity)) {}
+}
 
 // ---- thread-block clusters: peer shared memory, remote barrier arrives -------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank()

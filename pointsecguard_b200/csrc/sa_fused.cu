@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             for (int tile = blockIdx.x * NG + g; tile < a.ntiles; tile += tstride) {
 #pragma unroll 1
                 for (int layer = 0; layer < 3; ++layer) {
-                    tc::mbar_wait(b_in, ph); ph ^= 1u;
+                    tc::mbar_spin(b_in, ph); ph ^= 1u;
                     tc::fence_after_sync();
                     if (layer == 0) issue_layer(tm, sA, sW0, a.gpad / 4, a.n0);
                     else if (layer == 1) issue_layer(tm, sA, sW1, a.n0 / 4, a.n1);
@@ -363,6 +363,8 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float4 stg_d[NG * 4][32];      // per-warp staging of the arg-max scatter (psg_epi.cuh)
+    __shared__ uchar4 stg_a[NG * 4][32];
 
     const uint32_t s0 = tc::smem_u32(smem_raw);
     const uint32_t sbase = (s0 + 1023u) & ~1023u;
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             for (int tile = blockIdx.x * NG + g; tile < a.ntiles; tile += tstride) {
 #pragma unroll 1
                 for (int L = 0; L < nslab + 2; ++L) {
-                    tc::mbar_wait(b_in, ph); ph ^= 1u;
+                    tc::mbar_spin(b_in, ph); ph ^= 1u;
                     tc::fence_after_sync();
                     if (L < nslab)                                                        // dY1 (+)= dY2[:, slab L] W2[slab L]
                         issue_layer(tm, sD, sW2 + (uint32_t)L * (a.slab / 4) * a.n1 * 16, a.slab / 4, a.n1, L > 0 ? 1u : 0u);
@@ -427,7 +429,6 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
         unsigned char *pD2 = pG + (size_t)grp * szG, *pD1 = pD2, *pD0 = pD2;
         const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
         const uint32_t tl = tmem + grp * gcols + ((uint32_t)(wq * 32) << 16);
-        const int k = r % K;
         const int w0words = (a.n0 + 31) / 32, w1words = (a.n1 + 31) / 32;
         uint32_t ph = 0;
         long long *tr = (a.trace && blockIdx.x == 0 && r == 0 && grp < 2) ? a.trace + grp * 512 : nullptr;
@@ -440,19 +441,8 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             // ---- dY2[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0, one slab of columns at a
             // time: the operand buffer stays small (more tiles in flight), the MMA accumulates over slabs ----
             for (int sl = 0; sl < nslab; ++sl) {
-                const int c0 = sl * (a.slab / 4);
-#pragma unroll 8
-                for (int c = 0; c < a.slab / 4; ++c) {
-                    const float4 d = tv_ld(a.dout, g, c0 + c);
-                    const float4 o = tv_ld(a.outv, g, c0 + c);
-                    const uchar4 am = *reinterpret_cast<const uchar4 *>(a.arg + g * a.n2 + 4 * (c0 + c));
-                    float4 q;
-                    q.x = (valid && am.x == k && o.x > 0.f) ? d.x : 0.f;
-                    q.y = (valid && am.y == k && o.y > 0.f) ? d.y : 0.f;
-                    q.z = (valid && am.z == k && o.z > 0.f) ? d.z : 0.f;
-                    q.w = (valid && am.w == k && o.w > 0.f) ? d.w : 0.f;
-                    *plane_ptr(pD2, c, r) = q;
-                }
+                psg_scatter_warp<K>(a.dout, a.outv, a.arg, a.n2, g, valid, lane, sl * (a.slab / 4), a.slab / 4,
+                                    stg_d[warp], stg_a[warp], [&](int c, float4 q) { *plane_ptr(pD2, c, r) = q; });
                 tc::fence_before_sync();
                 tc::fence_async_smem();
                 tc::mbar_arrive(b_in);
@@ -518,10 +508,21 @@ inline int bwd_slab(int n0, int n1, int n2)
         if (n2 % sl == 0) return sl;
     return n2;
 }
-inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng)
+inline size_t bwd_smem_slab(int gpad, int n0, int n1, int n2, int ng, int slab)
 {
     return (size_t)n2 * n1 * 4 + (size_t)n1 * n0 * 4 + r1k((size_t)n0 * gpad * 4) +
-           (size_t)ng * (size_t)max3(bwd_slab(n0, n1, n2), n1, n0) * 512 + 1024;
+           (size_t)ng * (size_t)max3(slab, n1, n0) * 512 + 1024;
+}
+// The register file, not shared memory, limits a SM to about four tiles in flight, so when four whole-width
+// operand buffers fit the scatter goes in ONE pass: every extra slab is one more MMA round trip (~1 us) per tile.
+inline int bwd_slab_for(int gpad, int n0, int n1, int n2)
+{
+    if (bwd_smem_slab(gpad, n0, n1, n2, 4, n2) <= kSmemPerCtaMax) return n2;
+    return bwd_slab(n0, n1, n2);
+}
+inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng)
+{
+    return bwd_smem_slab(gpad, n0, n1, n2, ng, bwd_slab_for(gpad, n0, n1, n2));
 }
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
@@ -532,7 +533,11 @@ template <class Kern>
 int ctas_per_sm(Kern kern, int threads, size_t smem, int tmem_cols)
 {
     // one kernel instantiation serves several levels: raise the opt-in limit to the file's maximum once, never lower it
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax) != cudaSuccess) return 0;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return 0;
+    const size_t dyn_max = (size_t)232448 - fa.sharedSizeBytes;          // 227 KB per CTA, static part included
+    if (smem > dyn_max) return 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max) != cudaSuccess) { cudaGetLastError(); return 0; }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) return 0;
     occ = occ < 512 / tmem_cols ? occ : 512 / tmem_cols;
@@ -649,7 +654,7 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float
     a.wb0 = f.wb[0]; a.wb1 = f.wb[1]; a.wb2 = f.wb[2]; a.nwb0 = f.nwb[0]; a.nwb1 = f.nwb[1]; a.nwb2 = f.nwb[2];
     a.dG = dG; a.gcols = gcols; a.rows = f.rows;
     a.dG_rm = dG_rm; a.rm_only = (dG_rm && rm_only) ? 1 : 0;
-    a.slab = bwd_slab(f.n[0], f.n[1], f.n[2]);
+    a.slab = bwd_slab_for(f.gpad, f.n[0], f.n[1], f.n[2]);
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
     a.trace = psg_tile_trace_slot();
