@@ -335,13 +335,13 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
                             if (g > glast) continue;
-                            tc::mbar_wait(tc::smem_u32(&bar_in[g]), ph_in[g]); ph_in[g] ^= 1u;
+                            tc::mbar_spin(tc::smem_u32(&bar_in[g]), ph_in[g]); ph_in[g] ^= 1u;
                             if (tr && tn < 510) tr[tn++] = clock64();
                             for (int si = 0; si < nst; ++si) {
                                 const int pl = si * op.pps;
                                 const int np = min(op.pps, op.planes - pl);
                                 const int slot = (it + si) % kStages;
-                                if (g == 0) tc::mbar_wait(tc::smem_u32(&bar_full[slot]), (uint32_t)((it + si) / kStages) & 1u);
+                                if (g == 0) tc::mbar_spin(tc::smem_u32(&bar_full[slot]), (uint32_t)((it + si) / kStages) & 1u);
                                 tc::fence_after_sync();
                                 const uint32_t sA = sA0 + g * a.abytes + (uint32_t)(op.aplane0 + pl) * 2048u;
                                 const uint32_t sB = sW + slot * a.stage_bytes;
@@ -362,13 +362,13 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         const int np = min(op.pps, op.planes - pl);
                         const int slot = it % kStages;
                         const bool last = pl + op.pps >= op.planes;
-                        tc::mbar_wait(tc::smem_u32(&bar_full[slot]), (uint32_t)(it / kStages) & 1u);
+                        tc::mbar_spin(tc::smem_u32(&bar_full[slot]), (uint32_t)(it / kStages) & 1u);
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
                             if (tile0 + g >= a.ntiles) continue;
                             if (pl == 0) {
                                 if (CS > 1) tc::mbar_wait_cluster(tc::smem_u32(&bar_in[g]), ph_in[g]);
-                                else tc::mbar_wait(tc::smem_u32(&bar_in[g]), ph_in[g]);
+                                else tc::mbar_spin(tc::smem_u32(&bar_in[g]), ph_in[g]);
                                 ph_in[g] ^= 1u;
                             }
                             tc::fence_after_sync();

@@ -287,6 +287,69 @@ __global__ void csr_rank_kernel(const int *__restrict__ keys, long long total, i
     perm[p * M + lo + rank] = slot;
 }
 
+// The same four steps for ONE problem per CTA with the bucket counters in shared memory (R <= 8192): one launch
+// instead of two memsets + four kernels, shared-memory instead of L2 atomics.  Same deterministic output.
+__global__ void __launch_bounds__(1024) csr_fused_kernel(const int *__restrict__ keys, int M, int R, int grp,
+                                                         int *__restrict__ offs, int *__restrict__ perm, int *__restrict__ tmp)
+{
+    extern __shared__ int csr_sm[];
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    int *cnt = csr_sm, *cur = csr_sm + R + 1;
+    const long long p = blockIdx.x;
+    const int *kp = keys + p * M;
+    int *tp = tmp + p * M, *pp = perm + p * M;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i <= R; i += 1024) { cnt[i] = 0; if (i < R) cur[i] = 0; }
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < M; e += 1024) {
+        const int key = kp[e];
+        if (key >= 0 && key < R && !csr_is_pad(kp, e, e, key, grp)) atomicAdd(cnt + key, 1);
+    }
+    __syncthreads();
+    for (int base = 0; base < R; base += 1024) {               // exclusive scan, as csr_scan_kernel
+        const int i = base + threadIdx.x;
+        const int v = i < R ? cnt[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int sv = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, sv, o); if (lane >= o) sv += y; }
+            wsum[lane] = sv;
+        }
+        __syncthreads();
+        const int incl = x + (warp ? wsum[warp - 1] : 0) + carry_s;
+        if (i < R) cnt[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cnt[R] = carry_s;
+    __syncthreads();
+    int *op = offs + p * (R + 1);
+    for (int i = threadIdx.x; i <= R; i += 1024) op[i] = cnt[i];
+    for (int e = threadIdx.x; e < M; e += 1024) {
+        const int key = kp[e];
+        if (key < 0 || key >= R || csr_is_pad(kp, e, e, key, grp)) continue;
+        const int pos = atomicAdd(cur + key, 1);
+        tp[cnt[key] + pos] = e;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < M; e += 1024) {
+        const int key = kp[e];
+        if (key < 0 || key >= R || csr_is_pad(kp, e, e, key, grp)) continue;
+        const int lo = cnt[key], hi = cnt[key + 1];
+        int rank = 0;
+        for (int q = lo; q < hi; ++q) rank += (tp[q] < e);
+        pp[lo + rank] = e;
+    }
+}
+
 // ---- ordered segmented sum (backward of group / interp) ---------------------------------------
 // dst[p*R + r][c] (+)= sum over bucket entries e (ascending slot) of scale_e * src[p*rows_per_p + slot_e/div][c]
 // LPR lanes per destination row (narrow rows share a warp); the entry loop issues four independent
@@ -448,6 +511,18 @@ int psg_csr_build(const int *keys, long long P, int M, int R, int grp, int *offs
     int *cursor = (int *)scratch;
     int *tmp = cursor + P * (R + 1);
     const long long total = P * M;
+    if (R <= 8192) {
+        const size_t smem = (size_t)(2 * R + 1) * sizeof(int);
+        static bool attr_done = false;
+        if (!attr_done) {
+            if (cudaFuncSetAttribute(csr_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 8192 + 1) * 4) != cudaSuccess)
+                return PSG_ECUDA;
+            attr_done = true;
+        }
+        csr_fused_kernel<<<(unsigned)P, 1024, smem, st>>>(keys, M, R, grp, offs, perm, tmp);
+        PSG_LAUNCH_CHECK();
+        return PSG_OK;
+    }
     if (cudaMemsetAsync(offs, 0, (size_t)P * (R + 1) * sizeof(int), st) != cudaSuccess) return PSG_ECUDA;
     if (cudaMemsetAsync(cursor, 0, (size_t)P * (R + 1) * sizeof(int), st) != cudaSuccess) return PSG_ECUDA;
     csr_count_kernel<<<nblocks(total, 256), 256, 0, st>>>(keys, total, M, R, grp, offs);
