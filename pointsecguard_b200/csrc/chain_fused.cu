@@ -130,10 +130,10 @@ __device__ __forceinline__ void pre_group(const TileSrc &s, unsigned char *pA, l
     }
 }
 
-__device__ __forceinline__ void pre_load(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r)
+// source chunks [cbeg, cbeg + nch) of the row-local tensor -> A planes [0, nch)
+__device__ __forceinline__ void pre_load(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r, int cbeg, int nch)
 {
-    const float *b = s.lsrc.base + tv_off(s.lsrc, valid ? row : 0, 0);
-    const int nch = s.lcols / 4;
+    const float *b = s.lsrc.base + tv_off(s.lsrc, valid ? row : 0, cbeg);
     constexpr int NB = 16;
     for (int c0 = 0; c0 < nch; c0 += NB) {
         float4 x[NB];
@@ -149,7 +149,9 @@ __device__ __forceinline__ void pre_load(const TileSrc &s, unsigned char *pA, lo
 // (f[i0] w0 + f[i1] w1) + f[i2] w2, products rounded separately as torch does (pointnet_util.py:308).
 // The three gathered rows are 16-byte pieces 2 KB apart: a latency-bound gather, so the loads of eight chunks
 // (24 independent 16-byte requests per thread) are issued before the first one is consumed.
-__device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r)
+// interpolated chunks [cbeg, cbeg + nch) -> A planes [plane0, plane0 + nch)
+__device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r, int cbeg, int nch,
+                                           int plane0)
 {
     const long long rr = valid ? row : 0;
     const long long p = rr / s.iNf;
@@ -157,11 +159,11 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
     const float *ww = s.nn_w + rr * 3;
     const long long r0 = p * s.iS + ii[0], r1 = p * s.iS + ii[1], r2 = p * s.iS + ii[2];
     const float w0 = valid ? ww[0] : 0.f, w1 = valid ? ww[1] : 0.f, w2 = valid ? ww[2] : 0.f;
-    const int nch = s.icols / 4;
     if (s.irm) {
         // row-major mirror: one 32-byte request per two chunks -- half the L1 tag work and only whole sectors
         // from L2 (the T-layout pieces are 16 bytes, 2 KB apart)
-        const float *m0 = s.irm + r0 * s.irm_stride, *m1 = s.irm + r1 * s.irm_stride, *m2 = s.irm + r2 * s.irm_stride;
+        const float *m0 = s.irm + r0 * s.irm_stride + 4 * cbeg, *m1 = s.irm + r1 * s.irm_stride + 4 * cbeg,
+                    *m2 = s.irm + r2 * s.irm_stride + 4 * cbeg;
         constexpr int NP = 4;                         // pairs of chunks per batch
         for (int c0 = 0; c0 < nch; c0 += 2 * NP) {
             float4 x[2 * NP], y[2 * NP], z[2 * NP];
@@ -184,14 +186,14 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
                     q.y = __fadd_rn(__fadd_rn(__fmul_rn(x[j].y, w0), __fmul_rn(y[j].y, w1)), __fmul_rn(z[j].y, w2));
                     q.z = __fadd_rn(__fadd_rn(__fmul_rn(x[j].z, w0), __fmul_rn(y[j].z, w1)), __fmul_rn(z[j].z, w2));
                     q.w = __fadd_rn(__fadd_rn(__fmul_rn(x[j].w, w0), __fmul_rn(y[j].w, w1)), __fmul_rn(z[j].w, w2));
-                    *plane_ptr(pA, s.iplane0 + c0 + j, r) = q;
+                    *plane_ptr(pA, plane0 + c0 + j, r) = q;
                 }
             }
         }
         return;
     }
-    const float *b0 = s.isrc.base + tv_off(s.isrc, r0, 0), *b1 = s.isrc.base + tv_off(s.isrc, r1, 0),
-                *b2 = s.isrc.base + tv_off(s.isrc, r2, 0);
+    const float *b0 = s.isrc.base + tv_off(s.isrc, r0, cbeg), *b1 = s.isrc.base + tv_off(s.isrc, r1, cbeg),
+                *b2 = s.isrc.base + tv_off(s.isrc, r2, cbeg);
     constexpr int NB = 8;
     for (int c0 = 0; c0 < nch; c0 += NB) {
         float4 x[NB], y[NB], z[NB];
@@ -213,7 +215,7 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
                 q.y = __fadd_rn(__fadd_rn(__fmul_rn(x[j].y, w0), __fmul_rn(y[j].y, w1)), __fmul_rn(z[j].y, w2));
                 q.z = __fadd_rn(__fadd_rn(__fmul_rn(x[j].z, w0), __fmul_rn(y[j].z, w1)), __fmul_rn(z[j].z, w2));
                 q.w = __fadd_rn(__fadd_rn(__fmul_rn(x[j].w, w0), __fmul_rn(y[j].w, w1)), __fmul_rn(z[j].w, w2));
-                *plane_ptr(pA, s.iplane0 + c0 + j, r) = q;
+                *plane_ptr(pA, plane0 + c0 + j, r) = q;
             }
         }
     }
@@ -421,8 +423,13 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                 const int nl = op.n / CS, c0l = q * nl;        // this CTA's output columns [c0l, c0l + nl)
                 // ---- refill the A operand, hand it to the MMA thread ----
                 if (op.pre == PRE_GROUP) pre_group(a.src, pA, row, valid, r);
-                else if (op.pre == PRE_FP) { if (a.src.lcols) pre_load(a.src, pA, row, valid, r); pre_interp(a.src, pA, row, valid, r); }
-                else if (op.pre == PRE_LOAD) pre_load(a.src, pA, row, valid, r);
+                else if (op.pre == PRE_FP) {
+                    // chunks [pre_a, pre_a + planes) of the concatenation [skip | interpolation]
+                    const int L = a.src.lcols / 4, kb = op.pre_a, ke = op.pre_a + op.planes;
+                    if (kb < L) pre_load(a.src, pA, row, valid, r, kb, min(ke, L) - kb);
+                    if (ke > L) pre_interp(a.src, pA, row, valid, r, max(kb, L) - L, ke - max(kb, L), max(kb, L) - kb);
+                }
+                else if (op.pre == PRE_LOAD) pre_load(a.src, pA, row, valid, r, 0, a.src.lcols / 4);
                 else if (op.pre == PRE_SCATTER) pre_scatter(a.src, pA, row, valid, r, op.pre_a, op.planes, stage_d + warp * 32, stage_a + warp * 32);
                 tc::fence_before_sync();
                 if (CS > 1) {
@@ -837,15 +844,25 @@ int psg_sa_stream_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, floa
 // -------------------------------------------------------------------------------------------------
 // feature-propagation level (weights streamed)
 // -------------------------------------------------------------------------------------------------
+// does the whole concatenated input of level f fit the operand buffer next to two 16 KB weight stages?
+static bool fp_fits_whole(const PsgFpStream &f)
+{
+    size_t bias = 0;
+    for (int j = 0; j < f.nl; ++j) bias += (size_t)f.n[j] * 4;
+    return (size_t)(f.C1 + f.C2) * 512 + 2 * 16 * 1024 + bias + 128 <= kSmemMax;
+}
+static bool g_fp_slabs = false;
+void psg_tile_set_fp_slabs(bool on) { g_fp_slabs = on; }
+
 bool psg_fp_streamable(const PsgFpStream &f, bool forward)
 {
     if (f.nl < 1 || f.nl > 3 || f.C1 % 16 || f.C2 % 16) return false;
     for (int j = 0; j < f.nl; ++j)
         if (f.n[j] % 32 || f.n[j] > 256) return false;
-    size_t bias = 0;
-    for (int j = 0; j < f.nl; ++j) bias += (size_t)f.n[j] * 4;
-    if (forward) return (size_t)(f.C1 + f.C2) * 512 + 2 * 16 * 1024 + bias + 128 <= kSmemMax;
-    return true;
+    // Inputs wider than the operand buffer CAN be contracted in 256-column slabs (psg_fp_stream_fwd), but for the
+    // levels that need it (FP4: 1024 rows x 768 columns at B = 16) the per-layer GEMMs with their deep operand ring
+    // and 64 column-split CTAs measured faster (fp4 forward 45 us vs 95 us), so slabs stay opt-in ("fp_slabs").
+    return !forward || g_fp_slabs || fp_fits_whole(f);
 }
 
 // [skip | interp] -> nl x (conv + folded BN + ReLU); last layer stored (it is the next level's
@@ -855,9 +872,20 @@ int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st)
     Builder b;
     int kprev = f.C1 + f.C2;
     for (int j = 0; j < f.nl; ++j) {
-        TileOp *o = b.add(f.wf[j], f.nwf[j], 0, 0, f.n[j], kprev / 4, 0);
+        TileOp *o = nullptr;
+        if (j == 0 && !fp_fits_whole(f)) {
+            // the concatenated input is wider than the operand buffer: contract it in 256-column slabs, each slab
+            // refilled (skip rows / interpolation) while the accumulator carries over (FP4: 768 columns)
+            for (int k0 = 0; k0 < kprev; k0 += 256) {
+                const int ks = kprev - k0 < 256 ? kprev - k0 : 256;
+                o = b.add(f.wf[0], f.nwf[0], 0, k0 / 4, f.n[0], ks / 4, 0);
+                o->pre = PRE_FP; o->pre_a = k0 / 4; o->accumulate = k0 > 0 ? 1 : 0; o->epi = EPI_NONE;
+            }
+        } else {
+            o = b.add(f.wf[j], f.nwf[j], 0, 0, f.n[j], kprev / 4, 0);
+            if (j == 0) { o->pre = PRE_FP; o->pre_a = 0; }
+        }
         o->bias = f.bias[j];
-        if (j == 0) o->pre = PRE_FP;
         if (j + 1 < f.nl) { o->epi = EPI_RELU; o->mglobal = f.m[j]; }
         else { o->epi = EPI_STORE; o->relu = 1; o->out = f.y_last; o->rm = f.y_last_rm; o->rm_stride = f.n[j]; }
         kprev = f.n[j];

@@ -23,6 +23,7 @@
 
 long long g_psg_launch_count = 0;
 int g_psg_sm_cap = 0;
+static int g_fp_min_tiles = 0;      // FP levels with fewer 128-row tiles run per layer (psg_set_option "fp_min_tiles")
 
 // ------------------------------------------------------------------------------------------------
 // per-kernel-family device timing (bench.py's live roofline measurement).  When enabled, every
@@ -374,6 +375,8 @@ extern "C" int psg_set_option(const char *name, int value)
 {
     if (!name) return PSG_EINVAL;
     if (!strcmp(name, "clusters")) { psg_tile_use_clusters(value != 0); return PSG_OK; }
+    if (!strcmp(name, "fp_min_tiles")) { g_fp_min_tiles = value; return PSG_OK; }
+    if (!strcmp(name, "fp_slabs")) { psg_tile_set_fp_slabs(value != 0); return PSG_OK; }
     if (!strcmp(name, "sa_ng")) { psg_sa_force_ng(value); return PSG_OK; }
     if (!strcmp(name, "dbg")) { psg_tile_set_dbg(value); return PSG_OK; }
     if (!strcmp(name, "sm_cap")) { g_psg_sm_cap = value > 0 ? value : 0; return PSG_OK; }
@@ -461,7 +464,7 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
         for (int j = 0; j < 3; ++j) F.m[j] = nullptr;
         if (f > 0) {
             PsgFpStream q = fp_stream_desc(n, f, 0, TView{nullptr, 0, 0});
-            F.streamed = psg_fp_streamable(q, true) && psg_fp_streamable(q, false);
+            F.streamed = psg_fp_streamable(q, true) && psg_fp_streamable(q, false) && (rows + 127) / 128 >= g_fp_min_tiles;
             if (F.streamed)
                 for (int j = 0; j + 1 < F.nl; ++j) F.m[j] = bp.take<unsigned>(psg_sa_mask_words(rows, F.mlp[j]->npad));
         }
