@@ -23,7 +23,10 @@
 
 long long g_psg_launch_count = 0;
 int g_psg_sm_cap = 0;
-static int g_fp_min_tiles = 0;      // FP levels with fewer 128-row tiles run per layer (psg_set_option "fp_min_tiles")
+// FP levels with fewer 128-row tiles than this run per layer: with a third of the SMs or fewer busy, 64 column-split
+// GEMM CTAs with a deep operand ring beat one cluster per tile (B = 16: fp3 as a tile program 1133 steps/s, per
+// layer 1153; psg_set_option "fp_min_tiles")
+static int g_fp_min_tiles = 48;
 
 // ------------------------------------------------------------------------------------------------
 // per-kernel-family device timing (bench.py's live roofline measurement).  When enabled, every
