@@ -155,6 +155,10 @@ int launch_fps(const float *xyz, long long cloud_stride, int nclouds, int P, int
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return PSG_ECUDA;
     }
+    // several problems share an SM (that is what hides the per-round reduction latency): ask for the largest
+    // shared-memory carve-out so that the clouds of three or four CTAs fit next to each other
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        return PSG_ECUDA;
     kern<<<P, THREADS, smem, st>>>(xyz, cloud_stride, nclouds, N, npoint, start, out_idx, out_xyz);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
