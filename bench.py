@@ -163,7 +163,7 @@ def run_native(args, rank, world, local_rank):
     from pointsecguard_b200.engine import MLP_TF32
     from pointsecguard_b200.models.pointnet2_sem_seg import get_model
 
-    for opt in ("sa_ng", "clusters", "fp_min_tiles", "fp_slabs"):                 # A/B switches of the library (experiments only)
+    for opt in ("sa_ng", "clusters", "fp_min_tiles", "fp_slabs", "ts"):                 # A/B switches of the library (experiments only)
         if os.environ.get("PSG_OPT_" + opt.upper()):
             L.psg_set_option(opt.encode(), int(os.environ["PSG_OPT_" + opt.upper()]))
     model = get_model(13)

@@ -74,6 +74,7 @@ struct TileArgs {
     TileSrc src;
     long long rows; int ntiles;
     int abytes, stage_bytes, tcols;      // A buffer bytes per tile, weight stage bytes, TMEM columns per tile
+    int acols;                           // TS programs: TMEM columns of the A operand (after the accumulator's tcols)
     int bias_floats;                     // size of the shared-memory bias area
     int mwords, mbytes;                  // ReLU-bit words per mask slot; bytes of the per-tile mask / scratch area
     // head / loss (EPI_HEAD)
@@ -89,6 +90,7 @@ __device__ __forceinline__ float4 *plane_ptr(unsigned char *buf, int chunk, int 
 {
     return reinterpret_cast<float4 *>(buf) + (size_t)chunk * 128 + row;
 }
+__device__ __forceinline__ uint32_t pow2cols_dev(uint32_t n) { uint32_t c = 32; while (c < n) c <<= 1; return c; }
 
 // ---- A-operand producers (worker thread r owns tile row r) ----------------------------------------
 __device__ __forceinline__ void pre_group(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r)
@@ -150,8 +152,11 @@ __device__ __forceinline__ void pre_load(const TileSrc &s, unsigned char *pA, lo
 // The three gathered rows are 16-byte pieces 2 KB apart: a latency-bound gather, so the loads of eight chunks
 // (24 independent 16-byte requests per thread) are issued before the first one is consumed.
 // interpolated chunks [cbeg, cbeg + nch) -> A planes [plane0, plane0 + nch)
+// TS: the A operand lives in tensor memory (tA = TMEM address of this thread's lane, column 0 of the operand):
+// eight chunks are collected and written with one tcgen05.st (nch must then be a multiple of 8)
+template <bool TS>
 __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r, int cbeg, int nch,
-                                           int plane0)
+                                           int plane0, uint32_t tA)
 {
     const long long rr = valid ? row : 0;
     const long long p = rr / s.iNf;
@@ -178,17 +183,18 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
                     tc::ldg256(m2 + (size_t)(c0 + 2 * j) * 4, z[2 * j], z[2 * j + 1]);
                 }
             }
+            float v[8 * NP];
 #pragma unroll
             for (int j = 0; j < 2 * NP; ++j) {
-                if (c0 + j < nch) {
-                    float4 q;
-                    q.x = __fadd_rn(__fadd_rn(__fmul_rn(x[j].x, w0), __fmul_rn(y[j].x, w1)), __fmul_rn(z[j].x, w2));
-                    q.y = __fadd_rn(__fadd_rn(__fmul_rn(x[j].y, w0), __fmul_rn(y[j].y, w1)), __fmul_rn(z[j].y, w2));
-                    q.z = __fadd_rn(__fadd_rn(__fmul_rn(x[j].z, w0), __fmul_rn(y[j].z, w1)), __fmul_rn(z[j].z, w2));
-                    q.w = __fadd_rn(__fadd_rn(__fmul_rn(x[j].w, w0), __fmul_rn(y[j].w, w1)), __fmul_rn(z[j].w, w2));
-                    *plane_ptr(pA, plane0 + c0 + j, r) = q;
-                }
+                float4 q;
+                q.x = __fadd_rn(__fadd_rn(__fmul_rn(x[j].x, w0), __fmul_rn(y[j].x, w1)), __fmul_rn(z[j].x, w2));
+                q.y = __fadd_rn(__fadd_rn(__fmul_rn(x[j].y, w0), __fmul_rn(y[j].y, w1)), __fmul_rn(z[j].y, w2));
+                q.z = __fadd_rn(__fadd_rn(__fmul_rn(x[j].z, w0), __fmul_rn(y[j].z, w1)), __fmul_rn(z[j].z, w2));
+                q.w = __fadd_rn(__fadd_rn(__fmul_rn(x[j].w, w0), __fmul_rn(y[j].w, w1)), __fmul_rn(z[j].w, w2));
+                if (TS) { v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w; }
+                else if (c0 + j < nch) *plane_ptr(pA, plane0 + c0 + j, r) = q;
             }
+            if (TS) tc::tmem_st32(tA + (uint32_t)(plane0 + c0) * 4u, v);
         }
         return;
     }
@@ -207,17 +213,18 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
             y[j] = in ? __ldg(reinterpret_cast<const float4 *>(b1 + (size_t)(c0 + j) * 512)) : zero;
             z[j] = in ? __ldg(reinterpret_cast<const float4 *>(b2 + (size_t)(c0 + j) * 512)) : zero;
         }
+        float v[4 * NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-            if (c0 + j < nch) {
-                float4 q;
-                q.x = __fadd_rn(__fadd_rn(__fmul_rn(x[j].x, w0), __fmul_rn(y[j].x, w1)), __fmul_rn(z[j].x, w2));
-                q.y = __fadd_rn(__fadd_rn(__fmul_rn(x[j].y, w0), __fmul_rn(y[j].y, w1)), __fmul_rn(z[j].y, w2));
-                q.z = __fadd_rn(__fadd_rn(__fmul_rn(x[j].z, w0), __fmul_rn(y[j].z, w1)), __fmul_rn(z[j].z, w2));
-                q.w = __fadd_rn(__fadd_rn(__fmul_rn(x[j].w, w0), __fmul_rn(y[j].w, w1)), __fmul_rn(z[j].w, w2));
-                *plane_ptr(pA, plane0 + c0 + j, r) = q;
-            }
+            float4 q;
+            q.x = __fadd_rn(__fadd_rn(__fmul_rn(x[j].x, w0), __fmul_rn(y[j].x, w1)), __fmul_rn(z[j].x, w2));
+            q.y = __fadd_rn(__fadd_rn(__fmul_rn(x[j].y, w0), __fmul_rn(y[j].y, w1)), __fmul_rn(z[j].y, w2));
+            q.z = __fadd_rn(__fadd_rn(__fmul_rn(x[j].z, w0), __fmul_rn(y[j].z, w1)), __fmul_rn(z[j].z, w2));
+            q.w = __fadd_rn(__fadd_rn(__fmul_rn(x[j].w, w0), __fmul_rn(y[j].w, w1)), __fmul_rn(z[j].w, w2));
+            if (TS) { v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w; }
+            else if (c0 + j < nch) *plane_ptr(pA, plane0 + c0 + j, r) = q;
         }
+        if (TS) tc::tmem_st32(tA + (uint32_t)(plane0 + c0) * 4u, v);
     }
 }
 
@@ -240,10 +247,15 @@ __device__ __forceinline__ void pre_scatter(const TileSrc &s, unsigned char *pA,
 // accumulator barriers (nobody overwrites an operand a peer's MMA still reads) and the workers arrive
 // on all CTAs' operand barriers (nobody issues an MMA before every slice landed).  This is what lets
 // the deep levels -- few rows, large weights -- use more than one SM per tile.
-template <int NG, int CS>
+// TS: the A operand of every MMA lives in TENSOR MEMORY (tcgen05.mma with A from TMEM): gathers and epilogues
+// write the next operand with tcgen05.st, there is no operand buffer in shared memory at all.  That removes
+// the two biggest shared-memory streams of a layer (MMA A reads, epilogue stores) -- the SS-mode chain was
+// shared-memory bound at about twice its tensor time -- and leaves room for 64 KB weight stages.
+template <int NG, int CS, bool TS>
 __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_constant__ TileArgs a)
 {
     static_assert(CS == 1 || NG == 1, "cluster programs keep one tile in flight");
+    static_assert(!TS || CS == 1, "peers cannot write each other's tensor memory");
     // no-swizzle UMMA operands and bulk copies need 16-byte alignment only: a 128-byte aligned dynamic
     // segment keeps the static + padding overhead small (every KB decides whether 32 KB weight stages fit)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -262,7 +274,8 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
     uchar4 *stage_a = reinterpret_cast<uchar4 *>(stage_d + NG * 4 * 32);           // [NG * 4 warps][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ncols = (uint32_t)(a.tcols * NG);
+    const uint32_t tper = (uint32_t)(TS ? a.tcols + a.acols : a.tcols);      // TMEM columns per tile in flight
+    const uint32_t ncols = pow2cols_dev(tper * NG);
     if (threadIdx.x == 0) {
         for (int g = 0; g < NG; ++g) { tc::mbar_init(tc::smem_u32(&bar_in[g]), kWorkers * CS); tc::mbar_init(tc::smem_u32(&bar_acc[g]), CS); }
         for (int s = 0; s < kStages; ++s) { tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1); }
@@ -347,10 +360,12 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                                 tc::fence_after_sync();
                                 const uint32_t sA = sA0 + g * a.abytes + (uint32_t)(op.aplane0 + pl) * 2048u;
                                 const uint32_t sB = sW + slot * a.stage_bytes;
+                                const uint32_t tD = tmem + g * tper, tA = tD + a.tcols + (uint32_t)(op.aplane0 + pl) * 4u;
                                 for (int j = 0; j < np; j += 2) {
-                                    const uint64_t ad = tc::smem_desc(sA + j * 2048, 2048, 128);
                                     const uint64_t bd = tc::smem_desc(sB + j * nl * 16, (uint32_t)(nl * 16), 128);
-                                    tc::mma_tf32(tmem + g * a.tcols, ad, bd, idesc, (op.accumulate || pl > 0 || j > 0) ? 1u : 0u);
+                                    const uint32_t acc = (op.accumulate || pl > 0 || j > 0) ? 1u : 0u;
+                                    if (TS) tc::mma_tf32_ts(tD, tA + j * 4, bd, idesc, acc);
+                                    else tc::mma_tf32(tD, tc::smem_desc(sA + j * 2048, 2048, 128), bd, idesc, acc);
                                 }
                                 if (g == glast) tc::mma_commit(tc::smem_u32(&bar_empty[slot]));
                             }
@@ -376,10 +391,12 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                             tc::fence_after_sync();
                             const uint32_t sA = sA0 + g * a.abytes + (uint32_t)(op.aplane0 + pl) * 2048u;
                             const uint32_t sB = sW + slot * a.stage_bytes;
+                            const uint32_t tD = tmem + g * tper, tA = tD + a.tcols + (uint32_t)(op.aplane0 + pl) * 4u;
                             for (int j = 0; j < np; j += 2) {
-                                const uint64_t ad = tc::smem_desc(sA + j * 2048, 2048, 128);
                                 const uint64_t bd = tc::smem_desc(sB + j * nl * 16, (uint32_t)(nl * 16), 128);
-                                tc::mma_tf32(tmem + g * a.tcols, ad, bd, idesc, (op.accumulate || pl > 0 || j > 0) ? 1u : 0u);
+                                const uint32_t acc = (op.accumulate || pl > 0 || j > 0) ? 1u : 0u;
+                                if (TS) tc::mma_tf32_ts(tD, tA + j * 4, bd, idesc, acc);
+                                else tc::mma_tf32(tD, tc::smem_desc(sA + j * 2048, 2048, 128), bd, idesc, acc);
                             }
                             if (last) {
                                 if (CS > 1) tc::mma_commit_mc(tc::smem_u32(&bar_acc[g]), (uint16_t)((1u << CS) - 1u));
@@ -399,7 +416,8 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
         unsigned *mbits = pMask + (size_t)grp * (a.mbytes / 4);
         const int mw = a.mwords;
         const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
-        const uint32_t tl = tmem + grp * a.tcols + ((uint32_t)(wq * 32) << 16);
+        const uint32_t tl = tmem + grp * tper + ((uint32_t)(wq * 32) << 16);
+        const uint32_t tla = tl + a.tcols;                 // TS: this thread's lane of the A operand
         const int K = a.src.K > 0 ? a.src.K : 32;
         uint32_t ph = 0;
         long long *tr = (a.trace && blockIdx.x == 0 && r == 0) ? a.trace + grp * 512 : nullptr;
@@ -415,6 +433,21 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                     if (pr != q) tc::st_cluster_v4(tc::mapa(la, (uint32_t)pr), val);
             }
         };
+        // 32 / 16 consecutive columns of this thread's row, starting at operand column `col`
+        auto put32 = [&](int col, const float *v) {
+            if (TS) tc::tmem_st32(tla + (uint32_t)col, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) put((col >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            }
+        };
+        auto put16 = [&](int col, const float *v) {
+            if (TS) tc::tmem_st16(tla + (uint32_t)col, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) put((col >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            }
+        };
         for (int tile = first_tile + grp; tile < a.ntiles; tile += tstride) {
             const long long row = (long long)tile * 128 + r;
             const bool valid = row < a.rows;
@@ -427,7 +460,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                     // chunks [pre_a, pre_a + planes) of the concatenation [skip | interpolation]
                     const int L = a.src.lcols / 4, kb = op.pre_a, ke = op.pre_a + op.planes;
                     if (kb < L) pre_load(a.src, pA, row, valid, r, kb, min(ke, L) - kb);
-                    if (ke > L) pre_interp(a.src, pA, row, valid, r, max(kb, L) - L, ke - max(kb, L), max(kb, L) - kb);
+                    if (ke > L) pre_interp<TS>(a.src, pA, row, valid, r, max(kb, L) - L, ke - max(kb, L), max(kb, L) - kb, tla);
                 }
                 else if (op.pre == PRE_LOAD) pre_load(a.src, pA, row, valid, r, 0, a.src.lcols / 4);
                 else if (op.pre == PRE_SCATTER) pre_scatter(a.src, pA, row, valid, r, op.pre_a, op.planes, stage_d + warp * 32, stage_a + warp * 32);
@@ -437,7 +470,8 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
 #pragma unroll
                     for (int pr = 0; pr < CS; ++pr) tc::mbar_arrive_cluster(tc::mapa(b_in, (uint32_t)pr));
                 } else {
-                    tc::fence_async_smem();
+                    if (TS) tc::tmem_wait_st();        // the operand written by this thread (gather or previous epilogue) has landed
+                    else tc::fence_async_smem();
                     tc::mbar_arrive(b_in);
                 }
                 if (tr && tn < 510) tr[tn++] = clock64();
@@ -453,9 +487,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         float v[32];
                         tc::tmem_ld32(tl + (uint32_t)c, v);
                         const unsigned w = psg_relu_bias_bits<32>(v, sbias + op.boff + c0l + c);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                        put32(c0l + c, v);
                         if (op.slot >= 0) mbits[((size_t)op.slot * mw + w0l + (c >> 5)) * 128 + r] = w;
                         if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
@@ -463,9 +495,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c, v);
                         const unsigned w = psg_relu_bias_bits<16>(v, sbias + op.boff + c0l + c);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                        put16(c0l + c, v);
                         if (op.slot >= 0) mbits[((size_t)op.slot * mw + w0l + (c >> 5)) * 128 + r] = w;
                         if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
@@ -477,9 +507,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         float v[32];
                         tc::tmem_ld32(tl + (uint32_t)c, v);
                         psg_apply_bits<32>(v, w);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                        put32(c0l + c, v);
                     }
                     if (c < nl) {
                         const unsigned w = op.mglobal ? op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r]
@@ -487,9 +515,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         float v[16];
                         tc::tmem_ld16(tl + (uint32_t)c, v);
                         psg_apply_bits<16>(v, w);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            put(((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                        put16(c0l + c, v);
                     }
                 } else if (op.epi == EPI_STORE) {
                     int c = 0;
@@ -594,12 +620,11 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                             if (valid && a.loss_rows) a.loss_rows[row] = f;
                             if (valid && a.hit) a.hit[row] = (unsigned char)h;
                         }
+                        if (!valid) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float4 qv = make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
-                            if (!valid) qv = make_float4(0.f, 0.f, 0.f, 0.f);
-                            *plane_ptr(pA, c, r) = qv;
+                            for (int i = 0; i < 16; ++i) dz[i] = 0.f;
                         }
+                        put16(0, dz);
                     }
                 }
                 // EPI_NONE: the accumulator is continued by the next op
@@ -661,18 +686,36 @@ int pick_cluster(const TileArgs &a, int ntiles, int sms)
     return 1;
 }
 
-template <int NG, int CS>
+template <int NG, int CS, bool TS = false>
 int launch_tile(const TileArgs &a, int grid, size_t smem, cudaStream_t st)
 {
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(tile_kernel<NG, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
+        if (cudaFuncSetAttribute(tile_kernel<NG, CS, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
             return PSG_ECUDA;
         attr_done = true;
     }
-    if (psg_launch_pdl(tile_kernel<NG, CS>, dim3((unsigned)grid), dim3(NG * 128 + 64), smem, st, CS, a) != cudaSuccess)
+    if (psg_launch_pdl(tile_kernel<NG, CS, TS>, dim3((unsigned)grid), dim3(NG * 128 + 64), smem, st, CS, a) != cudaSuccess)
         return PSG_ECUDA;
     return PSG_OK;
+}
+
+bool g_use_ts = true;
+
+// A-operand-in-tensor-memory mode: row-local chains whose only refill is the interpolation (fp1 + head).  The operand
+// region needs whole 32-column stores and, with the accumulator, has to fit the 512 TMEM columns NG times.
+bool ts_eligible(const Builder &b, int ng)
+{
+    const TileArgs &a = b.a;
+    if (!g_use_ts || b.amax_cols % 32) return false;
+    for (int o = 0; o < a.nops; ++o) {
+        const TileOp &op = a.ops[o];
+        if (op.pre != PRE_NONE && op.pre != PRE_FP) return false;
+        if (op.pre == PRE_FP && (a.src.lcols != 0 || a.src.icols % 32)) return false;
+        if (op.epi == EPI_MAXPOOL) return false;
+        if ((op.epi == EPI_RELU || op.epi == EPI_MASK) && op.n % 16) return false;
+    }
+    return (int)pow2cols(ng * ((int)pow2cols(b.nmax) + b.amax_cols)) <= 512;
 }
 
 // choose cluster size / NG / stage size to fit shared memory, fill the derived fields, launch
@@ -715,7 +758,9 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     };
     // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
     int ng = (cs == 1 && a.ntiles > sms && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
-    int stage = need(ng, 32 * 1024) <= kSmemMax ? 32 * 1024 : 16 * 1024;
+    const bool ts = cs == 1 && ts_eligible(b, ng);
+    if (ts) { a.abytes = 0; a.acols = b.amax_cols; }          // no operand buffer in shared memory: room for 64 KB stages
+    int stage = (ts && need(ng, 64 * 1024) <= kSmemMax) ? 64 * 1024 : need(ng, 32 * 1024) <= kSmemMax ? 32 * 1024 : 16 * 1024;
     if (need(ng, stage) > kSmemMax || a.tcols * ng > 512) return PSG_EUNSUPPORTED;
     a.stage_bytes = stage;
     for (int o = 0; o < a.nops; ++o) {
@@ -730,7 +775,8 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     if (cs == 1) {
         const int want = (a.ntiles + ng - 1) / ng;
         const int grid = want < sms ? want : sms;
-        rc = ng == 2 ? launch_tile<2, 1>(a, grid, smem, st) : launch_tile<1, 1>(a, grid, smem, st);
+        if (ts) rc = ng == 2 ? launch_tile<2, 1, true>(a, grid, smem, st) : launch_tile<1, 1, true>(a, grid, smem, st);
+        else rc = ng == 2 ? launch_tile<2, 1>(a, grid, smem, st) : launch_tile<1, 1>(a, grid, smem, st);
     } else {
         const int grid = a.ntiles * cs;                     // one cluster per tile, all resident in one wave
         rc = cs == 4 ? launch_tile<1, 4>(a, grid, smem, st) : launch_tile<1, 2>(a, grid, smem, st);
@@ -925,6 +971,7 @@ int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dc
 
 // thread-block clusters for the deep levels (on by default; the switch exists for A/B measurements)
 void psg_tile_use_clusters(bool on) { g_use_clusters = on; }
+void psg_tile_use_ts(bool on) { g_use_ts = on; }
 void psg_tile_set_dbg(int v) { g_dbg = v; }
 long long *psg_tile_trace_slot() { return (g_trace && g_trace_n < g_trace_cap) ? g_trace + (size_t)(g_trace_n++) * 2048 : nullptr; }
 void psg_tile_set_trace(long long *buf, int nlaunches) { g_trace = buf; g_trace_cap = nlaunches; g_trace_n = 0; }

@@ -107,6 +107,7 @@ bool psg_fp_streamable(const PsgFpStream &f, bool forward);
 int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st);
 int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dcat_rm, cudaStream_t st);
 void psg_tile_use_clusters(bool on);
+void psg_tile_use_ts(bool on);     // A operand of the row-local chains in tensor memory (default on)
 void psg_tile_set_dbg(int v);
 void psg_tile_set_fp_slabs(bool on);
 long long *psg_tile_trace_slot();   // next [4][512] block of the debug trace buffer, or null
