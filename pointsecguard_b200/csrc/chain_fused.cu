@@ -74,6 +74,7 @@ struct TileArgs {
     TileSrc src;
     long long rows; int ntiles;
     int abytes, stage_bytes, tcols;      // A buffer bytes per tile, weight stage bytes, TMEM columns per tile
+    int rmstage;                         // 1: a 4 KB per-warp staging area for coalesced row-major stores follows the scatter staging
     int acols;                           // TS programs: TMEM columns of the A operand (after the accumulator's tcols)
     int bias_floats;                     // size of the shared-memory bias area
     int mwords, mbytes;                  // ReLU-bit words per mask slot; bytes of the per-tile mask / scratch area
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
     float *sbias = reinterpret_cast<float *>(pMask + (size_t)NG * (a.mbytes / 4));
     float4 *stage_d = reinterpret_cast<float4 *>(sbias + a.bias_floats);          // [NG * 4 warps][32]
     uchar4 *stage_a = reinterpret_cast<uchar4 *>(stage_d + NG * 4 * 32);           // [NG * 4 warps][32]
+    float4 *stage_rm = reinterpret_cast<float4 *>(stage_a + NG * 4 * 32);          // [NG * 4 warps][256] when a.rmstage
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tper = (uint32_t)(TS ? a.tcols + a.acols : a.tcols);      // TMEM columns per tile in flight
@@ -530,11 +532,16 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                                 for (int j = 0; j < 8; ++j)
                                     tv_st(op.out, row, ((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                             }
-                            if (op.rm) {
+                            if (op.rm && !a.rmstage) {
                                 float4 *d = reinterpret_cast<float4 *>(op.rm + row * op.rm_stride + c0l + c);
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                             }
+                        }
+                        if (op.rm && a.rmstage) {             // whole warp: coalesced row-major store through the staging area
+                            const long long row0 = (long long)tile * 128 + wq * 32;
+                            psg_store_rm32(v, stage_rm + warp * 256, lane, op.rm + row0 * op.rm_stride + c0l + c, op.rm_stride,
+                                           [&](int i) { return row0 + i < a.rows; });
                         }
                         if (op.mglobal) op.mglobal[((size_t)tile * words + w0l + (c >> 5)) * 128 + r] = w;
                     }
@@ -751,10 +758,15 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     a.mbytes = nslots * a.mwords * 128 * 4;
     for (int o = 0; o < a.nops; ++o)
         if (a.ops[o].epi == EPI_MAXPOOL && a.mbytes < 16384) a.mbytes = 16384;     // pool scratch: 4 KB per worker warp
-    bool scatters = false;
-    for (int o = 0; o < a.nops; ++o) scatters = scatters || a.ops[o].pre == PRE_SCATTER;
+    bool scatters = false, mirrors = false;
+    for (int o = 0; o < a.nops; ++o) {
+        scatters = scatters || a.ops[o].pre == PRE_SCATTER;
+        mirrors = mirrors || (a.ops[o].epi == EPI_STORE && a.ops[o].rm);
+    }
+    a.rmstage = 0;
     auto need = [&](int ng, int stg) {
-        return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * a.mbytes + (size_t)a.bias_floats * 4 + (scatters ? (size_t)ng * 4 * 32 * 20 : 0) + 128;
+        return (size_t)ng * a.abytes + (size_t)kStages * stg + (size_t)ng * a.mbytes + (size_t)a.bias_floats * 4 +
+               ((scatters || a.rmstage) ? (size_t)ng * 4 * 32 * 20 : 0) + (a.rmstage ? (size_t)ng * 4 * 4096 : 0) + 128;
     };
     // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
     int ng = (cs == 1 && a.ntiles > sms && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
@@ -762,6 +774,10 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     if (ts) { a.abytes = 0; a.acols = b.amax_cols; }          // no operand buffer in shared memory: room for 64 KB stages
     int stage = (ts && need(ng, 64 * 1024) <= kSmemMax) ? 64 * 1024 : need(ng, 32 * 1024) <= kSmemMax ? 32 * 1024 : 16 * 1024;
     if (need(ng, stage) > kSmemMax || a.tcols * ng > 512) return PSG_EUNSUPPORTED;
+    if (mirrors) {                   // staging for coalesced row-major stores, if it fits without shrinking the weight stages
+        a.rmstage = 1;
+        if (need(ng, stage) > kSmemMax) a.rmstage = 0;
+    }
     a.stage_bytes = stage;
     for (int o = 0; o < a.nops; ++o) {
         TileOp &op = a.ops[o];
