@@ -303,29 +303,32 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
     const int tstride = (CS > 1 ? (int)gridDim.x / CS : (int)gridDim.x) * NG;
 
     if (warp == NG * 4 + 1) {
-        // ---------------- weight producer ----------------
-        if (lane == 0) {
-            int it = 0;
-            for (int tile0 = first_tile; tile0 < a.ntiles; tile0 += tstride) {
-                for (int o = 0; o < a.nops; ++o) {
-                    const TileOp &op = a.ops[o];
-                    const int nl = op.n / CS;                     // this CTA's slice of the output columns
-                    for (int pl = 0; pl < op.planes; pl += op.pps, ++it) {
-                        const int np = min(op.pps, op.planes - pl);
-                        const int slot = it % kStages;
-                        const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+        // ---------------- weight producer: the whole warp issues a stage's copies ----------------
+        // (column-sliced weights are one copy per 4-column plane; a single thread issuing them back to back cost
+        // ~80 ns per copy -- 1.3 us per 32 KB stage of a cluster program, more than the copies take to arrive)
+        int it = 0;
+        for (int tile0 = first_tile; tile0 < a.ntiles; tile0 += tstride) {
+            for (int o = 0; o < a.nops; ++o) {
+                const TileOp &op = a.ops[o];
+                const int nl = op.n / CS;                     // this CTA's slice of the output columns
+                for (int pl = 0; pl < op.planes; pl += op.pps, ++it) {
+                    const int np = min(op.pps, op.planes - pl);
+                    const int slot = it % kStages;
+                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                    const uint32_t full = tc::smem_u32(&bar_full[slot]);
+                    const uint32_t dst = sW + slot * a.stage_bytes;
+                    if (lane == 0) {
                         tc::mbar_wait(tc::smem_u32(&bar_empty[slot]), ph ^ 1u);
-                        const uint32_t full = tc::smem_u32(&bar_full[slot]);
-                        const uint32_t dst = sW + slot * a.stage_bytes;
                         tc::mbar_expect_tx(full, (uint32_t)np * nl * 16);
-                        const float4 *wsrc = reinterpret_cast<const float4 *>(op.w) + (size_t)(op.wplane0 + pl) * op.wstride +
-                                             op.wrow0 + q * nl;
-                        if (op.wstride == nl) {
-                            tc::bulk_g2s(dst, wsrc, (uint32_t)np * nl * 16, full);
-                        } else {
-                            for (int j = 0; j < np; ++j)
-                                tc::bulk_g2s(dst + j * nl * 16, wsrc + (size_t)j * op.wstride, (uint32_t)nl * 16, full);
-                        }
+                    }
+                    __syncwarp();
+                    const float4 *wsrc = reinterpret_cast<const float4 *>(op.w) + (size_t)(op.wplane0 + pl) * op.wstride +
+                                         op.wrow0 + q * nl;
+                    if (op.wstride == nl) {
+                        if (lane == 0) tc::bulk_g2s(dst, wsrc, (uint32_t)np * nl * 16, full);
+                    } else {
+                        for (int j = lane; j < np; j += 32)
+                            tc::bulk_g2s(dst + j * nl * 16, wsrc + (size_t)j * op.wstride, (uint32_t)nl * 16, full);
                     }
                 }
             }

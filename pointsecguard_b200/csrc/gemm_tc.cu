@@ -23,9 +23,18 @@ constexpr int kThreads = 192;
 constexpr int kRingBytes = 200 * 1024;        // operand ring: as many stages as fit (the K loop is a latency chain)
 constexpr int kSmemBytes = kRingBytes + 1024;
 
-template <int EPI>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn_tile, int kStages)
+__device__ __forceinline__ long long gtimer()
 {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn_tile, int kStages, long long *trace)
+{
+    long long *tr = (trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) ? trace : nullptr;   // first epilogue thread
+    if (tr) tr[0] = gtimer();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc;
     __shared__ uint32_t tmem_slot;
@@ -50,31 +59,37 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    if (tr) tr[1] = gtimer();
     tc::pdl_launch_dependents();
     tc::pdl_wait();                  // launched with programmatic stream serialization: the prologue overlapped the predecessor
+    if (tr) tr[2] = gtimer();
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---- producer ----
-            int it = 0, kglob = 0;
-            for (int srcI = 0; srcI < 2; ++srcI) {
-                const TView &src = srcI == 0 ? g.A1 : g.A2;
-                const int kch = srcI == 0 ? g.k1chunks : g.k2chunks;
-                for (int c = 0; c < kch; c += kBlk, ++it) {
-                    const int n = min(kBlk, kch - c);
-                    const int s = it % kStages;
-                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+        // ---- producer: the whole warp issues a stage's copies (lane 0: barrier bookkeeping + the A tile, lane j:
+        // weight plane j).  One thread issuing the nine copies of a stage back to back cost ~80 ns per copy and
+        // made the K loop copy-issue bound (5.9 us for K = 256 with every stage in flight). ----
+        int it = 0, kglob = 0;
+        for (int srcI = 0; srcI < 2; ++srcI) {
+            const TView &src = srcI == 0 ? g.A1 : g.A2;
+            const int kch = srcI == 0 ? g.k1chunks : g.k2chunks;
+            for (int c = 0; c < kch; c += kBlk, ++it) {
+                const int n = min(kBlk, kch - c);
+                const int s = it % kStages;
+                const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                const uint32_t full = tc::smem_u32(&bar_full[s]);
+                if (lane == 0) {
                     tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
-                    const uint32_t full = tc::smem_u32(&bar_full[s]);
                     tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + n * BN * 16));
-                    tc::bulk_g2s(sA + s * kABytes, src.base + tv_off(src, row0, c), (uint32_t)(n * 2048), full);
-                    for (int j = 0; j < n; ++j)
-                        tc::bulk_g2s(sB + s * kBBytes + j * BN * 16, g.W + ((size_t)(kglob + c + j) * g.Nw + n0) * 4,
-                                     (uint32_t)(BN * 16), full);
                 }
-                kglob += kch;
+                __syncwarp();
+                if (lane == 0) tc::bulk_g2s(sA + s * kABytes, src.base + tv_off(src, row0, c), (uint32_t)(n * 2048), full);
+                if (lane >= 1 && lane <= n) {
+                    const int j = lane - 1;
+                    tc::bulk_g2s(sB + s * kBBytes + j * BN * 16, g.W + ((size_t)(kglob + c + j) * g.Nw + n0) * 4, (uint32_t)(BN * 16), full);
+                }
             }
+            kglob += kch;
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -107,6 +122,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
         const long long row = row0 + q * 32 + lane;
         tc::mbar_wait(tc::smem_u32(&bar_acc), 0);
         tc::fence_after_sync();
+        if (tr) tr[3] = gtimer();
         for (int c16 = 0; c16 < BN; c16 += 16) {
             float v[16];
             tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c16, v);
@@ -133,8 +149,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
                 tv_st(g.Out, row, (col >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
         }
     }
+    if (tr) tr[4] = gtimer();
     tc::fence_before_sync();
     __syncthreads();
+    if (tr) { tr[5] = gtimer(); tr[6] = g.mtiles; tr[7] = (long long)(g.k1chunks + g.k2chunks) * 4; tr[8] = g.nout_pad; tr[9] = bn_tile; }
     if (warp == 1) tc::tmem_dealloc(tmem, ncols);
 }
 
@@ -154,7 +172,7 @@ int launch(const PsgGemmArgs &g, cudaStream_t st)
     int nst = kRingBytes / (kABytes + kBlk * bn * 16);
     if (nst > kMaxStages) nst = kMaxStages;
     dim3 grid((unsigned)g.mtiles, (unsigned)((g.nout_pad + bn - 1) / bn));
-    if (psg_launch_pdl(gemm_tc_kernel<EPI>, grid, dim3(kThreads), (size_t)kSmemBytes, st, 1, g, bn, nst) != cudaSuccess) return PSG_ECUDA;
+    if (psg_launch_pdl(gemm_tc_kernel<EPI>, grid, dim3(kThreads), (size_t)kSmemBytes, st, 1, g, bn, nst, psg_tile_trace_slot()) != cudaSuccess) return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

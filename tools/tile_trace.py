@@ -47,6 +47,11 @@ def main():
     t = buf.cpu().numpy()
     if args.raw:
         for li in range(args.launches):
+            g0 = t[li, 0]
+            if g0[6] > 0 and g0[9] > 0 and g0[5] > g0[0] and g0[10] == 0:       # a gemm_tc launch (globaltimer ns)
+                print(f"launch {li} gemm_tc mtiles {g0[6]} K {g0[7]} N {g0[8]} bn {g0[9]}: prologue {g0[1]-g0[0]} ns, "
+                      f"pdl wait {g0[2]-g0[1]}, k loop {g0[3]-g0[2]}, epilogue {g0[4]-g0[3]}, tail {g0[5]-g0[4]}")
+                continue
             for role in range(3):
                 w = t[li, role]
                 n = int((w != 0).sum())
