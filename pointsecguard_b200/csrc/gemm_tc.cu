@@ -9,9 +9,11 @@
 // shared-memory stages back through tcgen05.commit -> mbarrier.  Warps 2-5 read the accumulator
 // with tcgen05.ld (thread = row), apply bias / ReLU / ReLU-mask and write T-layout rows as
 // coalesced 16-byte pieces.
+#include <cstring>
 #include "psg_common.cuh"
 #include "psg_internal.h"
 #include "psg_tc.cuh"
+#include "psg_tmap.cuh"
 
 namespace {
 
@@ -31,7 +33,8 @@ __device__ __forceinline__ long long gtimer()
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn_tile, int kStages, long long *trace)
+__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn_tile, int kStages, long long *trace,
+                                                           const __grid_constant__ CUtensorMap wmap, int use_map)
 {
     long long *tr = (trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) ? trace : nullptr;   // first epilogue thread
     if (tr) tr[0] = gtimer();
@@ -84,7 +87,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
                 }
                 __syncwarp();
                 if (lane == 0) tc::bulk_g2s(sA + s * kABytes, src.base + tv_off(src, row0, c), (uint32_t)(n * 2048), full);
-                if (lane >= 1 && lane <= n) {
+                if (use_map && BN == bn_tile) {
+                    // one tiled TMA copy: planes [kglob + c, + n) x columns [n0, n0 + BN), laid down as [plane][BN][4]
+                    if (lane == 1) psg_tmap_load(sB + s * kBBytes, &wmap, n0, kglob + c, full);
+                } else if (lane >= 1 && lane <= n) {
                     const int j = lane - 1;
                     tc::bulk_g2s(sB + s * kBBytes + j * BN * 16, g.W + ((size_t)(kglob + c + j) * g.Nw + n0) * 4, (uint32_t)(BN * 16), full);
                 }
@@ -172,7 +178,13 @@ int launch(const PsgGemmArgs &g, cudaStream_t st)
     int nst = kRingBytes / (kABytes + kBlk * bn * 16);
     if (nst > kMaxStages) nst = kMaxStages;
     dim3 grid((unsigned)g.mtiles, (unsigned)((g.nout_pad + bn - 1) / bn));
-    if (psg_launch_pdl(gemm_tc_kernel<EPI>, grid, dim3(kThreads), (size_t)kSmemBytes, st, 1, g, bn, nst, psg_tile_trace_slot()) != cudaSuccess) return PSG_ECUDA;
+    // weights [K/4][Nw][4] as a tiled TMA source: boxes of kBlk planes x bn columns (K is a multiple of 16, i.e. of
+    // 4 planes; a last short stage reads past the layer's planes only if K % 32 != 0, where the map clips)
+    CUtensorMap wmap;
+    memset(&wmap, 0, sizeof(wmap));
+    const long long planes = g.k1chunks + g.k2chunks;
+    const int use_map = (planes % kBlk == 0 && psg_weight_tmap(&wmap, g.W, planes, g.Nw, kBlk, bn)) ? 1 : 0;
+    if (psg_launch_pdl(gemm_tc_kernel<EPI>, grid, dim3(kThreads), (size_t)kSmemBytes, st, 1, g, bn, nst, psg_tile_trace_slot(), wmap, use_map) != cudaSuccess) return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
