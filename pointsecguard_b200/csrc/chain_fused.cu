@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
     tc::fence_after_sync();
     if (CS > 1) tc::cluster_sync_all();            // peers' barriers exist before anyone arrives on them remotely
     tc::pdl_launch_dependents();
-    tc::pdl_wait();                                // everything above overlapped the previous kernel's tail
+    // everything above overlapped the previous kernel's tail.  The weight producer does not wait at all: it reads only
+    // the network's constant weights, so its first stages land while the predecessor is still draining.
+    if (warp != NG * 4 + 1) tc::pdl_wait();
     const uint32_t tmem = tmem_slot;
     const int q = CS > 1 ? (int)tc::cluster_ctarank() : 0;
     const int first_tile = (CS > 1 ? (int)blockIdx.x / CS : (int)blockIdx.x) * NG;
