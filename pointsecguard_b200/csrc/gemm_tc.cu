@@ -64,38 +64,62 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
     tc::fence_after_sync();
     if (tr) tr[1] = gtimer();
     tc::pdl_launch_dependents();
-    tc::pdl_wait();                  // launched with programmatic stream serialization: the prologue overlapped the predecessor
-    if (tr) tr[2] = gtimer();
+    if (warp != 0) tc::pdl_wait();   // launched with programmatic stream serialization: the prologue overlapped the predecessor
+    if (tr) tr[2] = gtimer();        // (the producer warp waits after it has requested the first weight stages)
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
         // ---- producer: the whole warp issues a stage's copies (lane 0: barrier bookkeeping + the A tile, lane j:
-        // weight plane j).  One thread issuing the nine copies of a stage back to back cost ~80 ns per copy and
-        // made the K loop copy-issue bound (5.9 us for K = 256 with every stage in flight). ----
-        int it = 0, kglob = 0;
-        for (int srcI = 0; srcI < 2; ++srcI) {
-            const TView &src = srcI == 0 ? g.A1 : g.A2;
-            const int kch = srcI == 0 ? g.k1chunks : g.k2chunks;
-            for (int c = 0; c < kch; c += kBlk, ++it) {
-                const int n = min(kBlk, kch - c);
-                const int s = it % kStages;
-                const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-                const uint32_t full = tc::smem_u32(&bar_full[s]);
-                if (lane == 0) {
-                    tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
-                    tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + n * BN * 16));
-                }
-                __syncwarp();
-                if (lane == 0) tc::bulk_g2s(sA + s * kABytes, src.base + tv_off(src, row0, c), (uint32_t)(n * 2048), full);
-                if (use_map && BN == bn_tile) {
-                    // one tiled TMA copy: planes [kglob + c, + n) x columns [n0, n0 + BN), laid down as [plane][BN][4]
-                    if (lane == 1) psg_tmap_load(sB + s * kBBytes, &wmap, n0, kglob + c, full);
-                } else if (lane >= 1 && lane <= n) {
-                    const int j = lane - 1;
-                    tc::bulk_g2s(sB + s * kBBytes + j * BN * 16, g.W + ((size_t)(kglob + c + j) * g.Nw + n0) * 4, (uint32_t)(BN * 16), full);
-                }
+        // weight plane j, or lane 1 one tiled TMA copy).  One thread issuing the nine copies of a stage back to back
+        // cost ~80 ns per copy.  The weights of the first ring-full of stages are requested BEFORE
+        // griddepcontrol.wait (they are constants), the activations after it. ----
+        const int s0n = (g.k1chunks + kBlk - 1) / kBlk, s1n = (g.k2chunks + kBlk - 1) / kBlk, total = s0n + s1n;
+        auto stage_of = [&](int it, int &srcI, int &c, int &kglob, int &n) {
+            srcI = it < s0n ? 0 : 1;
+            c = (srcI == 0 ? it : it - s0n) * kBlk;
+            kglob = srcI == 0 ? 0 : g.k1chunks;
+            n = min(kBlk, (srcI == 0 ? g.k1chunks : g.k2chunks) - c);
+        };
+        auto issue_w = [&](int s, int c, int kglob, int n, uint32_t full) {
+            if (use_map && BN == bn_tile) {
+                if (lane == 1) psg_tmap_load(sB + s * kBBytes, &wmap, n0, kglob + c, full);
+            } else if (lane >= 1 && lane <= n) {
+                const int j = lane - 1;
+                tc::bulk_g2s(sB + s * kBBytes + j * BN * 16, g.W + ((size_t)(kglob + c + j) * g.Nw + n0) * 4, (uint32_t)(BN * 16), full);
             }
-            kglob += kch;
+        };
+        const int pre = min(total, kStages);
+        for (int it = 0; it < pre; ++it) {
+            int srcI, c, kglob, n;
+            stage_of(it, srcI, c, kglob, n);
+            const uint32_t full = tc::smem_u32(&bar_full[it]);
+            if (lane == 0) tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + n * BN * 16));
+            __syncwarp();
+            issue_w(it, c, kglob, n, full);
+        }
+        tc::pdl_wait();
+        if (lane == 0) {
+            for (int it = 0; it < pre; ++it) {
+                int srcI, c, kglob, n;
+                stage_of(it, srcI, c, kglob, n);
+                const TView &src = srcI == 0 ? g.A1 : g.A2;
+                tc::bulk_g2s(sA + it * kABytes, src.base + tv_off(src, row0, c), (uint32_t)(n * 2048), tc::smem_u32(&bar_full[it]));
+            }
+        }
+        for (int it = pre; it < total; ++it) {
+            int srcI, c, kglob, n;
+            stage_of(it, srcI, c, kglob, n);
+            const TView &src = srcI == 0 ? g.A1 : g.A2;
+            const int s = it % kStages;
+            const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+            const uint32_t full = tc::smem_u32(&bar_full[s]);
+            if (lane == 0) {
+                tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
+                tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + n * BN * 16));
+            }
+            __syncwarp();
+            if (lane == 0) tc::bulk_g2s(sA + s * kABytes, src.base + tv_off(src, row0, c), (uint32_t)(n * 2048), full);
+            issue_w(s, c, kglob, n, full);
         }
     } else if (warp == 1) {
         if (lane == 0) {
