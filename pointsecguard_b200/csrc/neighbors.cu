@@ -164,6 +164,168 @@ three_nn_kernel(const float *__restrict__ xyz1, long long stride1, int nclouds1,
     }
 }
 
+
+// ---- 3-NN through a uniform grid over the coarse cloud ---------------------------------------------------
+// Same results as three_nn_kernel, bit for bit: every candidate's distance is computed with the same
+// expansion-form arithmetic and the top-3 is kept under the total order (distance, index), so the order in
+// which candidates are visited does not matter.  The grid only decides WHICH candidates are visited: rings of
+// cells around the query's cell, until the third-best distance found so far is below the squared distance to
+// everything not visited yet -- minus a margin that covers the rounding error of the expansion formula
+// (|computed - true| <= ~1e-6 * max|p|^2; a query that cannot prove the bound simply visits more rings, up to
+// the whole grid).  ~70 candidates per query instead of 1024 at fp1.
+constexpr int kNgMaxS = 2048, kNgMaxCells = 2048, kNgQ = 1024;     // coarse points, cells, queries per CTA
+
+__device__ __forceinline__ bool nn_less(float d, int j, float D, int I) { return I < 0 || d < D || (d == D && j < I); }
+__device__ __forceinline__ void top3_push_lex(float d, int jj, float &d0, float &d1, float &d2, int &i0, int &i1, int &i2)
+{
+    if (nn_less(d, jj, d2, i2)) {
+        if (nn_less(d, jj, d1, i1)) {
+            d2 = d1; i2 = i1;
+            if (nn_less(d, jj, d0, i0)) { d1 = d0; i1 = i0; d0 = d; i0 = jj; }
+            else { d1 = d; i1 = jj; }
+        } else { d2 = d; i2 = jj; }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+three_nn_grid_kernel(const float *__restrict__ xyz1, long long stride1, int nclouds1, int N,
+                     const float *__restrict__ xyz2, int S,
+                     int *__restrict__ idx, float *__restrict__ wout, float *__restrict__ d2out)
+{
+    extern __shared__ __align__(16) unsigned char nn_sm[];
+    float4 *sp = reinterpret_cast<float4 *>(nn_sm);                  // [S] points sorted by cell (x, y, z, |p|^2)
+    int *sid = reinterpret_cast<int *>(sp + S);                      // [S] their original indices
+    int *cstart = sid + S;                                           // [cells + 1]
+    int *ccnt = cstart + kNgMaxCells + 1;                            // [cells] fill cursors
+    __shared__ float red[6][8];
+    __shared__ float sb[8];                                          // bbox min (3), cell size, margin
+    __shared__ int sdim[4];
+
+    const int p = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *fine = xyz1 + (long long)(p % nclouds1) * stride1;
+    const float *coarse = xyz2 + (long long)p * S * 3;
+
+    // ---- bounding box of the coarse cloud ----
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int j = t; j < S; j += 256) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = coarse[3 * j + a]; mn[a] = fminf(mn[a], v); mx[a] = fmaxf(mx[a], v); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) { red[a][warp] = mn[a]; red[3 + a][warp] = mx[a]; }
+    }
+    __syncthreads();
+    if (t == 0) {
+        float lo[3], hi[3], ext[3];
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = red[a][0]; hi[a] = red[3 + a][0];
+            for (int w = 1; w < 8; ++w) { lo[a] = fminf(lo[a], red[a][w]); hi[a] = fmaxf(hi[a], red[3 + a][w]); }
+            ext[a] = fmaxf(hi[a] - lo[a], 1e-6f);
+        }
+        // about two points per cell; at most 16 cells per axis and kNgMaxCells in total
+        float h = cbrtf(ext[0] * ext[1] * ext[2] * 2.0f / (float)S);
+        h = fmaxf(h, fmaxf(ext[0], fmaxf(ext[1], ext[2])) / 16.0f);
+        int d[3];
+        for (int a = 0; a < 3; ++a) { d[a] = (int)(ext[a] / h) + 1; d[a] = d[a] > 16 ? 16 : d[a]; }
+        while (d[0] * d[1] * d[2] > kNgMaxCells) { h *= 1.26f; for (int a = 0; a < 3; ++a) { d[a] = (int)(ext[a] / h) + 1; d[a] = d[a] > 16 ? 16 : d[a]; } }
+        float m2 = 0.f;
+        for (int a = 0; a < 3; ++a) { const float v = fmaxf(fabsf(lo[a]), fabsf(hi[a])); m2 += v * v; }
+        sb[0] = lo[0]; sb[1] = lo[1]; sb[2] = lo[2]; sb[3] = h; sb[4] = m2;            // m2 >= |p|^2 of every coarse point
+        sdim[0] = d[0]; sdim[1] = d[1]; sdim[2] = d[2]; sdim[3] = d[0] * d[1] * d[2];
+    }
+    __syncthreads();
+    const float lox = sb[0], loy = sb[1], loz = sb[2], h = sb[3], m2c = sb[4], inv_h = 1.0f / h;
+    const int nx = sdim[0], ny = sdim[1], nz = sdim[2], ncell = sdim[3];
+    auto cell_of = [&](float x, float y, float z, int &cx, int &cy, int &cz) {
+        cx = min(max((int)floorf((x - lox) * inv_h), 0), nx - 1);
+        cy = min(max((int)floorf((y - loy) * inv_h), 0), ny - 1);
+        cz = min(max((int)floorf((z - loz) * inv_h), 0), nz - 1);
+    };
+    // ---- counting sort of the coarse points by cell ----
+    for (int c = t; c <= ncell; c += 256) { cstart[c] = 0; if (c < ncell) ccnt[c] = 0; }
+    __syncthreads();
+    for (int j = t; j < S; j += 256) {
+        int cx, cy, cz;
+        cell_of(coarse[3 * j], coarse[3 * j + 1], coarse[3 * j + 2], cx, cy, cz);
+        atomicAdd(&cstart[(cz * ny + cy) * nx + cx + 1], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {                                     // inclusive scan of cstart[1..ncell] by one warp
+        int carry = 0;
+        for (int base = 1; base <= ncell; base += 32) {
+            const int c = base + lane;
+            int v = c <= ncell ? cstart[c] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
+            if (c <= ncell) cstart[c] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    for (int j = t; j < S; j += 256) {
+        const float x = coarse[3 * j], y = coarse[3 * j + 1], z = coarse[3 * j + 2];
+        int cx, cy, cz;
+        cell_of(x, y, z, cx, cy, cz);
+        const int c = (cz * ny + cy) * nx + cx;
+        const int pos = cstart[c] + atomicAdd(&ccnt[c], 1);
+        sp[pos] = make_float4(x, y, z, psg_sqnorm(x, y, z));
+        sid[pos] = j;
+    }
+    __syncthreads();
+    // ---- queries ----
+    const int q0 = blockIdx.x * kNgQ;
+    for (int qi = q0 + t; qi < min(q0 + kNgQ, N); qi += 256) {
+        const float qx = fine[3 * qi], qy = fine[3 * qi + 1], qz = fine[3 * qi + 2];
+        const float qn = psg_sqnorm(qx, qy, qz);
+        // rounding error of the expansion formula <= ~2.4e-6 * max(|q|^2, |p|^2): a 16x safety factor
+        const float margin = 4e-5f * (1.0f + fmaxf(qn, m2c));
+        int cx, cy, cz;
+        cell_of(qx, qy, qz, cx, cy, cz);
+        float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY;
+        int i0 = -1, i1 = -1, i2 = -1;
+        const int rmax = max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz));
+        for (int r = 0; r <= rmax; ++r) {
+            for (int dz = -r; dz <= r; ++dz) {
+                const int z = cz + dz;
+                if (z < 0 || z >= nz) continue;
+                for (int dy = -r; dy <= r; ++dy) {
+                    const int y = cy + dy;
+                    if (y < 0 || y >= ny) continue;
+                    const bool shell = (dz == -r || dz == r || dy == -r || dy == r);
+                    const int step = shell ? 1 : 2 * r;             // interior rows of the cube: only the two end cells
+                    for (int dx = -r; dx <= r; dx += (step > 0 ? step : 1)) {
+                        const int x = cx + dx;
+                        if (x < 0 || x >= nx) continue;
+                        const int c = (z * ny + y) * nx + x;
+                        for (int e = cstart[c]; e < cstart[c + 1]; ++e) {
+                            const float4 cp = sp[e];
+                            const float d = psg_sqdist(qx, qy, qz, qn, cp.x, cp.y, cp.z, cp.w);
+                            top3_push_lex(d, sid[e], d0, d1, d2, i0, i1, i2);
+                        }
+                    }
+                }
+            }
+            // everything not visited yet is farther than r cells away along some axis
+            const float bound = (float)r * h;
+            if (i2 >= 0 && d2 < bound * bound - margin) break;
+        }
+        const long long o = ((long long)p * N + qi) * 3;
+        idx[o] = i0; idx[o + 1] = i1; idx[o + 2] = i2;
+        const float r0 = __fdiv_rn(1.0f, __fadd_rn(d0, 1e-8f));
+        const float r1 = __fdiv_rn(1.0f, __fadd_rn(d1, 1e-8f));
+        const float r2 = __fdiv_rn(1.0f, __fadd_rn(d2, 1e-8f));
+        const float nrm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        if (wout) { wout[o] = __fdiv_rn(r0, nrm); wout[o + 1] = __fdiv_rn(r1, nrm); wout[o + 2] = __fdiv_rn(r2, nrm); }
+        if (d2out) { d2out[o] = d0; d2out[o + 1] = d1; d2out[o + 2] = d2; }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 square_distance_kernel(const float *__restrict__ src, const float *__restrict__ dst, int N, int M,
                        float *__restrict__ out)
@@ -211,10 +373,30 @@ int psg_ball_query_launch(const float *xyz, long long cloud_stride, int nclouds,
     return PSG_OK;
 }
 
+static int g_nn_grid_mode = 0;      // 0 automatic, 1 never, 2 whenever the coarse cloud fits (tests)
+void psg_three_nn_grid_mode(int m) { g_nn_grid_mode = m; }
+
 int psg_three_nn_launch(const float *xyz1, long long stride1, int nclouds1, int P, int N,
                         const float *xyz2, int S, int *idx, float *w, float *d2, cudaStream_t st)
 {
     if (P <= 0 || N <= 0 || S < 3) return PSG_EINVAL;
+    const bool want_grid = g_nn_grid_mode == 2 ? S <= kNgMaxS
+                         : g_nn_grid_mode == 1 ? false : (S >= 256 && S <= kNgMaxS && N >= 1024 && (long long)P * N >= 32768);
+    if (want_grid) {
+        // many queries against a cloud worth binning: uniform grid (bit-identical results)
+        const size_t smem = (size_t)S * 20 + (size_t)(2 * kNgMaxCells + 1) * 4 + 16;
+        static bool attr_done = false;
+        if (!attr_done) {
+            if (cudaFuncSetAttribute(three_nn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kNgMaxS * 20 + (2 * kNgMaxCells + 1) * 4 + 16) != cudaSuccess)
+                return PSG_ECUDA;
+            attr_done = true;
+        }
+        dim3 ggrid((N + kNgQ - 1) / kNgQ, P);
+        three_nn_grid_kernel<<<ggrid, 256, smem, st>>>(xyz1, stride1, nclouds1, N, xyz2, S, idx, w, d2);
+        PSG_LAUNCH_CHECK();
+        return PSG_OK;
+    }
     dim3 grid((N + 256 * kNnQ - 1) / (256 * kNnQ), P);
     three_nn_kernel<<<grid, 256, 0, st>>>(xyz1, stride1, nclouds1, N, xyz2, S, idx, w, d2);
     PSG_LAUNCH_CHECK();

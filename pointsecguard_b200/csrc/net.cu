@@ -377,6 +377,7 @@ static PsgFpStream fp_stream_desc(psg_net *n, int f, int t, TView coarse);
 extern "C" int psg_set_option(const char *name, int value)
 {
     if (!name) return PSG_EINVAL;
+    if (!strcmp(name, "nn_grid")) { psg_three_nn_grid_mode(value); return PSG_OK; }
     if (!strcmp(name, "ts")) { psg_tile_use_ts(value != 0); return PSG_OK; }
     if (!strcmp(name, "clusters")) { psg_tile_use_clusters(value != 0); return PSG_OK; }
     if (!strcmp(name, "fp_min_tiles")) { g_fp_min_tiles = value; return PSG_OK; }

@@ -29,6 +29,7 @@ int psg_ball_query_launch(const float *xyz, long long cloud_stride, int nclouds,
                           int *out0, int *out1, cudaStream_t st);
 int psg_three_nn_launch(const float *xyz1, long long stride1, int nclouds1, int P, int N,
                         const float *xyz2, int S, int *idx, float *w, float *d2, cudaStream_t st);
+void psg_three_nn_grid_mode(int m);   // 0 automatic, 1 never, 2 always (A/B and tests)
 int psg_square_distance_launch(const float *src, const float *dst, int B, int N, int M, float *out, cudaStream_t st);
 // ballgrid.cu: ball query over a uniform grid (large clouds), same results as psg_ball_query_launch
 size_t psg_ballgrid_workspace_bytes(int nclouds, int N);

@@ -91,6 +91,32 @@ def test_ball_query_and_three_nn_against_oracle(PU, N, S, r, k):
     assert torch.equal(idx.cpu(), ridx) and torch.equal(d2.cpu(), rd2) and torch.equal(w.cpu(), rw)
 
 
+@pytest.mark.parametrize("kind", ["uniform", "surface", "grid", "clustered", "duplicates"])
+def test_three_nn_grid_equals_exhaustive_scan(PU, kind):
+    """The uniform-grid 3-NN (csrc/neighbors.cu) must return exactly what the exhaustive kernel returns -- indices,
+    distances and weights -- on every kind of cloud, including heavy ties (grid / duplicates) and everything in
+    one corner (clustered); queries are all points of the cloud, candidates an FPS subset and a random subset."""
+    from pointsecguard_b200 import _lib as L
+    B, N = 3, 4096
+    xyz = _xyz(kind, B, N, 7).cuda()
+    gcpu = torch.Generator().manual_seed(11)
+    for S, how in ((1024, "fps"), (256, "fps"), (300, "rand"), (2048, "rand"), (5, "rand")):
+        if how == "fps":
+            sel = PU.farthest_point_sample(xyz, S)
+        else:
+            sel = torch.stack([torch.randperm(N, generator=gcpu)[:S] for _ in range(B)]).cuda()
+        new_xyz = PU.index_points(xyz, sel)
+        try:
+            L.psg_set_option(b"nn_grid", 1)
+            ref = [t.clone() for t in torch.ops.psg.three_nn(xyz, new_xyz)]
+            L.psg_set_option(b"nn_grid", 2)
+            out = torch.ops.psg.three_nn(xyz, new_xyz)
+        finally:
+            L.psg_set_option(b"nn_grid", 0)
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b), (kind, S, how)
+
+
 def test_ball_query_far_centroid_pads_with_N(PU):
     """A centroid with no point in range leaves N in every slot, as the reference does."""
     xyz = torch.rand(1, 128, 3).cuda()
