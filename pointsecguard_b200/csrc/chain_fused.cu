@@ -52,6 +52,7 @@ struct TileOp {
     TView out;                 // EPI_STORE / EPI_MAXPOOL destination (column offset folded into c0)
     float *rm; int rm_stride;  // EPI_STORE: optional row-major mirror of `out` (floats per row), or null
     int rm_only;               // ... and skip the T-layout store
+    TView out2; int out2_cols; // EPI_STORE: columns (absolute, of this op's range) below out2_cols are also written here
     unsigned char *arg; int argC, arg0;   // EPI_MAXPOOL
 };
 
@@ -543,6 +544,11 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                                 for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                             }
                         }
+                        if (valid && op.out2.base && c0l + c + 32 <= op.out2_cols) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                tv_st(op.out2, row, ((c0l + c) >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                        }
                         if (op.rm && a.rmstage) {             // whole warp: coalesced row-major store through the staging area
                             const long long row0 = (long long)tile * 128 + wq * 32;
                             psg_store_rm32(v, stage_rm + warp * 256, lane, op.rm + row0 * op.rm_stride + c0l + c, op.rm_stride,
@@ -965,7 +971,7 @@ int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st)
 }
 
 // dY_last (pre-activation gradient, already masked) -> dgrad chain -> d[skip | interp] stored to dcat
-int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dcat_rm, cudaStream_t st)
+int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dcat_rm, TView dskip, cudaStream_t st)
 {
     Builder b;
     for (int j = f.nl - 1; j >= 0; --j) {
@@ -980,6 +986,7 @@ int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dc
                 TileOp *o = b.add(f.wb[0], f.nwb[0], c0, 0, n, f.n[0] / 4, 0);
                 o->epi = EPI_STORE; o->out = dcat; o->out.c0 += c0 / 4;
                 if (dcat_rm) { o->rm = dcat_rm + c0; o->rm_stride = f.C1 + f.C2; }
+                if (dskip.base && c0 == 0 && f.C1 % 32 == 0) { o->out2 = dskip; o->out2_cols = f.C1 < n ? f.C1 : n; }
                 if (f.nl == 1 && c0 == 0) o->pre = PRE_LOAD;
             }
         }

@@ -177,6 +177,11 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 tv_st(g.Out, row, (col >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+            if (g.Out2.base && col + 16 <= g.out2_cols) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    tv_st(g.Out2, row, (col >> 2) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+            }
         }
     }
     if (tr) tr[4] = gtimer();

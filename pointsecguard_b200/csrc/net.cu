@@ -153,15 +153,18 @@ static int mlp_fwd(const psg_mlp *m, TView a1, int k1chunks, TView a2, int k2chu
     g.A1 = a1; g.k1chunks = k1chunks; g.A2 = a2; g.k2chunks = k2chunks;
     g.W = m->wf; g.Nw = m->nwf; g.bias = m->bias; g.Out = out; g.nout_pad = m->npad;
     g.Mask = TView{nullptr, 0, 0};
+    g.Out2 = TView{nullptr, 0, 0}; g.out2_cols = 0;
     g.mtiles = (int)(round_up_ll(rows, 128) / 128);
     g.epi = relu ? PSG_EPI_BIAS_RELU : PSG_EPI_BIAS;
     return run_gemm(g, mode, st);
 }
 
 // dgrad of one layer: dX = (dY W) [. (mask > 0)]
-static int mlp_bwd(const psg_mlp *m, TView dy, long long rows, TView dx, const TView *mask, int mode, cudaStream_t st)
+static int mlp_bwd(const psg_mlp *m, TView dy, long long rows, TView dx, const TView *mask, int mode, cudaStream_t st,
+                   const TView *out2 = nullptr, int out2_cols = 0)
 {
     PsgGemmArgs g;
+    g.Out2 = out2 ? *out2 : TView{nullptr, 0, 0}; g.out2_cols = out2 ? out2_cols : 0;
     g.A1 = dy; g.k1chunks = m->npad / 4; g.A2 = TView{nullptr, 0, 0}; g.k2chunks = 0;
     g.W = m->wb; g.Nw = m->nwb; g.bias = nullptr; g.Out = dx; g.nout_pad = m->kpad;
     g.Mask = mask ? *mask : TView{nullptr, 0, 0};
@@ -765,7 +768,7 @@ extern "C" int psg_net_loss_grad(psg_net *n, int kind, const float *dlogp, const
 // the last layer; Ys[j] the forward output of layer j.  Ping-pongs between the two scratch buffers,
 // starting with the one `top` does not live in; returns the buffer index holding dIn.
 static int chain_bwd(psg_net *n, psg_mlp *const *mlps, float *const *Ys, int nl, long long rows, TView top, int top_buf,
-                     int *out_buf, cudaStream_t st)
+                     int *out_buf, cudaStream_t st, const TView *out2 = nullptr, int out2_cols = 0)
 {
     TView cur = top;
     int dstb = top_buf == 0 ? 1 : 0;
@@ -775,7 +778,7 @@ static int chain_bwd(psg_net *n, psg_mlp *const *mlps, float *const *Ys, int nl,
             TView mk = tv(Ys[j - 1], mlps[j - 1]->npad);
             PSG_RUN(PF_GEMM_BWD, mlp_bwd(mlps[j], cur, rows, dx, &mk, n->mode, st));
         } else {
-            PSG_RUN(PF_GEMM_BWD, mlp_bwd(mlps[j], cur, rows, dx, nullptr, n->mode, st));
+            PSG_RUN(PF_GEMM_BWD, mlp_bwd(mlps[j], cur, rows, dx, nullptr, n->mode, st, out2, out2_cols));
         }
         cur = dx;
         *out_buf = dstb;
@@ -804,6 +807,7 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
         if (f == 0) { mlps[nl] = n->conv1; Ys[nl] = n->H; ++nl; mlps[nl] = n->conv2; Ys[nl] = n->Z; ++nl; }
         int cat_buf = 0;
         const float *rm_src = nullptr; int rm_stride = 0;      // row-major copy of d[interp] when a fused kernel produced it
+        bool skip_done = false;                                 // d[skip] already written into dfeat[f] by the producing kernel
         if (f == 0 && n->mode == 1 && n->head_fused) {
             if (!n->loss.set) return PSG_EINVAL;
             FpLevel &C = n->fp[1];
@@ -818,12 +822,18 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
         } else if (f > 0 && n->mode == 1 && F.streamed) {
             PsgFpStream q = fp_stream_desc(n, f, t, TView{nullptr, 0, 0});
             cat_buf = top_buf == 0 ? 1 : 0;
-            PSG_RUN(PF_FP_BWD, psg_fp_stream_bwd(q, top, tv(n->S[cat_buf], F.C1 + F.C2), n->Srm, st));
+            // the skip part of the gradient goes straight into dfeat[f] (no copy kernel)
+            PSG_RUN(PF_FP_BWD, psg_fp_stream_bwd(q, top, tv(n->S[cat_buf], F.C1 + F.C2), n->Srm, tv(n->dfeat[f], n->wfeat[f]), st));
             rm_src = n->Srm + F.C1; rm_stride = F.C1 + F.C2;
+            skip_done = true;
+        } else if (f > 0 && n->mode == 1 && F.C1) {
+            TView dsk = tv(n->dfeat[f], n->wfeat[f]);
+            PSG_TRY(chain_bwd(n, mlps, Ys, nl, rows, top, top_buf, &cat_buf, st, &dsk, F.C1));
+            skip_done = true;
         } else
         PSG_TRY(chain_bwd(n, mlps, Ys, nl, rows, top, top_buf, &cat_buf, st));
         const int catw = F.C1 + F.C2;
-        if (F.C1) PSG_RUN(PF_COPY, psg_copy_cols(tv(n->S[cat_buf], catw), tv(n->dfeat[f], n->wfeat[f]), rows, F.C1, 0, st));
+        if (F.C1 && !skip_done) PSG_RUN(PF_COPY, psg_copy_cols(tv(n->S[cat_buf], catw), tv(n->dfeat[f], n->wfeat[f]), rows, F.C1, 0, st));
         // interpolation backward: scatter the three weighted copies to the coarse level, in CSR order
         const size_t go = (size_t)t * B;
         if (n->xyz_grad) {

@@ -17,6 +17,7 @@ struct PsgGemmArgs {
     TView Mask;                 // PSG_EPI_MASK: forward activation of the layer below
     int mtiles;                 // padded rows / 128
     int epi;
+    TView Out2; int out2_cols;  // optional: columns [0, out2_cols) are ALSO written here (tcgen05 path; FP skip-gradient)
 };
 
 // fps.cu
@@ -106,7 +107,7 @@ struct PsgFpStream {
 };
 bool psg_fp_streamable(const PsgFpStream &f, bool forward);
 int psg_fp_stream_fwd(const PsgFpStream &f, cudaStream_t st);
-int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dcat_rm, cudaStream_t st);
+int psg_fp_stream_bwd(const PsgFpStream &f, TView dy_last, TView dcat, float *dcat_rm, TView dskip, cudaStream_t st);
 void psg_tile_use_clusters(bool on);
 void psg_tile_use_ts(bool on);     // A operand of the row-local chains in tensor memory (default on)
 void psg_tile_set_dbg(int v);
