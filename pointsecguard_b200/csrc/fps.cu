@@ -24,6 +24,44 @@ __device__ __forceinline__ void warp_argmax(unsigned &bits, int &idx)
     bits = m;
 }
 
+// Packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100a): two points per instruction for the three subtractions and
+// the three squares, each half rounded exactly like the scalar op.  The two ADDS stay scalar on purpose: ptxas
+// contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in SASS, even with explicit .rn), which would change
+// the rounding; a scalar FADD of one half of a packed product is never contracted (checked in SASS: no FFMA2 with
+// a non-zero addend in this file).
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi)
+{
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b)
+{
+    unsigned long long v;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b));
+    return v;
+}
+__device__ __forceinline__ unsigned long long f2_sq(unsigned long long a)
+{
+    unsigned long long v;
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(v) : "l"(a));
+    return v;
+}
+// distances of two points (lo, hi halves) to the centroid, op order of psg_fpsdist
+__device__ __forceinline__ void fpsdist2(unsigned long long px, unsigned long long py, unsigned long long pz,
+                                         unsigned long long cx, unsigned long long cy, unsigned long long cz, float &d0, float &d1)
+{
+    const unsigned long long sx = f2_sq(f2_sub(px, cx)), sy = f2_sq(f2_sub(py, cy)), sz = f2_sq(f2_sub(pz, cz));
+    float x0, x1, y0, y1, z0, z1;
+    f2_unpack(sx, x0, x1); f2_unpack(sy, y0, y1); f2_unpack(sz, z0, z1);
+    d0 = __fadd_rn(__fadd_rn(x0, y0), z0);
+    d1 = __fadd_rn(__fadd_rn(x1, y1), z1);
+}
+
 // MODE 0: coordinates in registers (+ shared copy for the centroid broadcast), N <= THREADS*PPT
 // MODE 1: coordinates only in shared memory (N <= 16384), min-distance in registers
 // EXACT:  N == THREADS*PPT, no bounds checks in the round loop (the common 4096 / 1024 / 256 / 64 case)
@@ -48,7 +86,9 @@ fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, i
     constexpr int NW = THREADS / 32;
     const float *cloud = xyz + (long long)(p % nclouds) * cloud_stride;
 
+    constexpr bool PK = (MODE == 0 && PPT % 2 == 0);     // two points per packed register pair
     float px[MODE == 0 ? PPT : 1], py[MODE == 0 ? PPT : 1], pz[MODE == 0 ? PPT : 1];
+    unsigned long long qx[PK ? PPT / 2 : 1], qy[PK ? PPT / 2 : 1], qz[PK ? PPT / 2 : 1];
     float mind[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
@@ -60,6 +100,12 @@ fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, i
             sx[i] = x; sy[i] = y; sz[i] = z;
             if (MODE == 0) { px[k] = x; py[k] = y; pz[k] = z; }
         } else if (MODE == 0) { px[k] = py[k] = pz[k] = 0.f; }
+    }
+    if (PK) {
+#pragma unroll
+        for (int k = 0; k < PPT / 2; ++k) {
+            qx[k] = f2_pack(px[2 * k], px[2 * k + 1]); qy[k] = f2_pack(py[2 * k], py[2 * k + 1]); qz[k] = f2_pack(pz[2 * k], pz[2 * k + 1]);
+        }
     }
     int far = start[p];
     __syncthreads();
@@ -74,6 +120,19 @@ fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, i
             if (ox) { ox[3 * it] = cx; ox[3 * it + 1] = cy; ox[3 * it + 2] = cz; }
         }
         float bestv = -2.f; int bestk = 0;
+        if (PK) {
+            // slots past the end of a ragged cloud hold (0, 0, 0) and the -1 sentinel: fminf(-1, d >= 0) keeps it
+            const unsigned long long c2x = f2_pack(cx, cx), c2y = f2_pack(cy, cy), c2z = f2_pack(cz, cz);
+#pragma unroll
+            for (int k = 0; k < PPT / 2; ++k) {
+                float d0, d1;
+                fpsdist2(qx[k], qy[k], qz[k], c2x, c2y, c2z, d0, d1);
+                mind[2 * k] = fminf(mind[2 * k], d0);
+                mind[2 * k + 1] = fminf(mind[2 * k + 1], d1);
+                if (mind[2 * k] > bestv) { bestv = mind[2 * k]; bestk = 2 * k; }
+                if (mind[2 * k + 1] > bestv) { bestv = mind[2 * k + 1]; bestk = 2 * k + 1; }
+            }
+        } else
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int i = k * THREADS + t;
