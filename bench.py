@@ -155,6 +155,9 @@ def run_native(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from pointsecguard_b200 import _lib as L
     from pointsecguard_b200 import distributed as D
@@ -298,7 +301,7 @@ def run_native(args, rank, world, local_rank):
                 "frac_of_hbm": byt[k] * B_PER_GPU / (fam[k]["ms_per_step"] / 1e3) / 1e9 / pk["hbm_gbs"]}
             for k in byt if k in fam}
         # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
-        if args.no_cpu:
+        if args.no_cpu or world > 1:          # the CPU leg runs on rank 0 at N = 1 only
             cpu = None
         else:
             sps, cores, sample, _ = cpu_reference(40, 1, sample_blocks=4)
