@@ -214,6 +214,35 @@ int psg_confusion_matrix(const float *logp, const int32_t *labels, const uint8_t
 int psg_add_vote(const float *logp, const int64_t *point_idx, const float *weight, int64_t rows, int ncls, float *pool,
                  int64_t pool_rows, psg_stream_t stream);
 
+/* ---- whole-scene block slicer: ScannetDatasetWholeScene.__getitem__,
+ * data_utils/S3DISDataLoader.py:124-175.  `points` is the room, float64 [P][ld] row-major with x, y, z, r, g, b in
+ * columns 0..5 and the label in column label_col; it stays resident on the device.  Columns ("cells") are the
+ * reference's grid_y x grid_x loop in row-major order; their padded bounds (lo_x, hi_x, lo_y, hi_y), their centres
+ * (s_x + block_size / 2, s_y + block_size / 2) and the random positions are computed by the host mirror
+ * (pointsecguard_b200/data_utils/S3DISDataLoader.py) with the reference's float64 expressions and numpy draws. ---- */
+
+/* room bounding box, :128: out6 = (min x, y, z, max x, y, z).  The workspace must be zero-filled once by the caller. */
+size_t psg_scene_minmax_workspace(void);
+int psg_scene_minmax(const double *points, int64_t P, int ld, double *out6, void *workspace, size_t workspace_bytes,
+                     psg_stream_t stream);
+/* number of 1024-point chunks the passes below split P points into */
+int64_t psg_scene_chunks(int64_t P);
+/* np.where of :143-145, pass 1: counts [ncell][chunks] receives, per column, the EXCLUSIVE scan over chunks of its
+ * member counts; totals [ncell] the members per column (= point_idxs.size of :146, what the host's draws depend on) */
+int psg_scene_cell_counts(const double *points, int64_t P, int ld, const double *cell_bounds, int ncell, int32_t *counts,
+                          int32_t *totals, psg_stream_t stream);
+/* pass 2: sel[cell_offset[c] + k] = k-th smallest member index of column c (cell_offset = exclusive sum of totals) */
+int psg_scene_cell_fill(const double *points, int64_t P, int ld, const double *cell_bounds, int ncell,
+                        const int32_t *counts, const int64_t *cell_offset, int32_t *sel, psg_stream_t stream);
+/* :155-166 for all blocks at once.  Output row r belongs to block r / block_points of column block_cell[block] and
+ * takes member number row_pos[r] of that column (the host's choice + shuffle).  data [rows][9] float64 (optional),
+ * data32 the same rounded to float32 as torch.Tensor(ndarray) does (optional), label int64, smpw float64 =
+ * labelweights[label], index int64 = the point's row in the room (each optional). */
+int psg_scene_gather(const double *points, int ld, int label_col, const int32_t *sel, const int64_t *cell_offset,
+                     const int32_t *block_cell, const int32_t *row_pos, const double *centre, const double *room_max,
+                     const float *labelweights, int ncls, int64_t rows, int block_points, double *data, float *data32,
+                     int64_t *label, double *smpw, int64_t *index, psg_stream_t stream);
+
 /* library-wide switches for A/B measurements: "clusters" (default 1) = run the deep levels' tile programs on
  * thread-block clusters (N split across CTAs, activations exchanged through distributed shared memory);
  * "sm_cap" (default 0 = all) = spread persistent launches over at most that many SMs, so that sub-batches

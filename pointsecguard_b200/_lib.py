@@ -98,6 +98,12 @@ _PROTOS = {
     "psg_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "psg_confusion_matrix": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
     "psg_debug_trace": (_i, [_vp, _i]),
+    "psg_scene_minmax_workspace": (_sz, []),
+    "psg_scene_minmax": (_i, [_vp, _i64, _i, _vp, _vp, _sz, _vp]),
+    "psg_scene_chunks": (_i64, [_i64]),
+    "psg_scene_cell_counts": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp]),
+    "psg_scene_cell_fill": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "psg_scene_gather": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTS = tuple(_PROTOS)

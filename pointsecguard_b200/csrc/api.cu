@@ -148,3 +148,42 @@ extern "C" int psg_add_vote(const float *logp, const int64_t *point_idx, const f
     if (!logp || !point_idx || !pool || rows <= 0 || ncls < 1 || pool_rows <= 0) return PSG_EINVAL;
     return psg_add_vote_k(logp, (const long long *)point_idx, weight, rows, ncls, pool, pool_rows, (cudaStream_t)stream);
 }
+
+// ---- whole-scene block slicer (slicer.cu) ----
+extern "C" size_t psg_scene_minmax_workspace(void) { return psg_scene_minmax_ws_bytes(); }
+
+extern "C" int psg_scene_minmax(const double *points, int64_t P, int ld, double *out6, void *workspace, size_t workspace_bytes,
+                                psg_stream_t stream)
+{
+    if (!points || !out6 || P <= 0 || ld < 3) return PSG_EINVAL;
+    if (!workspace || workspace_bytes < psg_scene_minmax_ws_bytes()) return PSG_EWORKSPACE;
+    return psg_scene_minmax_k(points, P, ld, out6, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int64_t psg_scene_chunks(int64_t P) { return (P + 1023) / 1024; }
+
+extern "C" int psg_scene_cell_counts(const double *points, int64_t P, int ld, const double *cell_bounds, int ncell,
+                                     int32_t *counts, int32_t *totals, psg_stream_t stream)
+{
+    if (!points || !cell_bounds || !counts || !totals || P <= 0 || ld < 2 || ncell <= 0) return PSG_EINVAL;
+    return psg_scene_count_k(points, P, ld, cell_bounds, ncell, counts, totals, (cudaStream_t)stream);
+}
+
+extern "C" int psg_scene_cell_fill(const double *points, int64_t P, int ld, const double *cell_bounds, int ncell,
+                                   const int32_t *counts, const int64_t *cell_offset, int32_t *sel, psg_stream_t stream)
+{
+    if (!points || !cell_bounds || !counts || !cell_offset || !sel || P <= 0 || ld < 2 || ncell <= 0) return PSG_EINVAL;
+    return psg_scene_fill_k(points, P, ld, cell_bounds, ncell, counts, (const long long *)cell_offset, sel, (cudaStream_t)stream);
+}
+
+extern "C" int psg_scene_gather(const double *points, int ld, int label_col, const int32_t *sel, const int64_t *cell_offset,
+                                const int32_t *block_cell, const int32_t *row_pos, const double *centre, const double *room_max,
+                                const float *labelweights, int ncls, int64_t rows, int block_points, double *data, float *data32,
+                                int64_t *label, double *smpw, int64_t *index, psg_stream_t stream)
+{
+    if (!points || !sel || !cell_offset || !block_cell || !row_pos || !centre || !room_max || !labelweights) return PSG_EINVAL;
+    if (ld < 6 || label_col < 0 || label_col >= ld || rows <= 0 || block_points <= 0 || ncls <= 0) return PSG_EINVAL;
+    return psg_scene_gather_k(points, ld, label_col, sel, (const long long *)cell_offset, block_cell, row_pos, centre, room_max,
+                              labelweights, ncls, rows, block_points, data, data32, (long long *)label, smpw, (long long *)index,
+                              (cudaStream_t)stream);
+}

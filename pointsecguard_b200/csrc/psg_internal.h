@@ -20,6 +20,18 @@ struct PsgGemmArgs {
     TView Out2; int out2_cols;  // optional: columns [0, out2_cols) are ALSO written here (tcgen05 path; FP skip-gradient)
 };
 
+// slicer.cu (whole-scene block slicer)
+size_t psg_scene_minmax_ws_bytes();
+int psg_scene_minmax_k(const double *pts, long long P, int ld, double *out6, void *ws, cudaStream_t st);
+int psg_scene_count_k(const double *pts, long long P, int ld, const double *bounds, int ncell, int *counts, int *totals,
+                      cudaStream_t st);
+int psg_scene_fill_k(const double *pts, long long P, int ld, const double *bounds, int ncell, const int *counts,
+                     const long long *cell_off, int *sel, cudaStream_t st);
+int psg_scene_gather_k(const double *pts, int ld, int label_col, const int *sel, const long long *cell_off, const int *block_cell,
+                       const int *row_pos, const double *centre, const double *room_max, const float *labelweights, int ncls,
+                       long long rows, int block_points, double *data, float *data32, long long *label, double *smpw,
+                       long long *index, cudaStream_t st);
+
 // fps.cu
 size_t psg_fps_workspace_bytes(int P, int N);
 int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P, int N, int npoint,

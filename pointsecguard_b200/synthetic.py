@@ -13,6 +13,7 @@ from __future__ import annotations
 import math
 from collections import OrderedDict
 
+import numpy as np
 import torch
 
 NUM_CLASSES = 13
@@ -168,3 +169,36 @@ def make_state_dict(arch: str = "ssg", seed: int = 1234, randomize_bn: bool = Tr
             bound = 1.0 / math.sqrt(kind)
             sd[key] = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
     return sd
+
+
+def make_room(P: int, seed: int = 0, kind: str = "box") -> np.ndarray:
+    """Synthetic S3DIS-shaped room: float64 [P, 7] = (x, y, z in metres, r, g, b in 0..255, label 0..12), the layout
+    of the reference's ``stanford_indoor3d/Area_*.npy`` files (data_utils/S3DISDataLoader.py:105-108).
+
+    kinds: ``box``     uniform in a 3.3 x 2.4 x 2.8 m room, random point order;
+           ``objects`` the same points stored object by object (sorted into 0.4 m tiles), as S3DIS rooms are;
+           ``lshape``  an L-shaped 4.1 x 3.6 m room: one quadrant is empty (empty grid columns) and one strip is
+                       thinly populated (columns that need sampling WITH replacement);
+           ``tiny``    a room barely larger than one block with fewer points than one block holds.
+    """
+    rng = np.random.RandomState(1000 + seed)
+    if kind in ("box", "objects"):
+        xy = rng.rand(P, 2) * np.array([3.3, 2.4]) + np.array([-1.7, 0.4])
+    elif kind == "lshape":
+        xy = rng.rand(P, 2) * np.array([4.1, 3.6])
+        dead = (xy[:, 0] > 2.3) & (xy[:, 1] > 2.0)
+        xy[dead, 0] -= 2.3                                  # fold the empty quadrant back into the room
+        thin = rng.rand(P) < 0.01
+        xy[thin] = rng.rand(int(thin.sum()), 2) * np.array([0.55, 0.9]) + np.array([2.45, 2.6])   # a thin strip inside it
+    elif kind == "tiny":
+        xy = rng.rand(P, 2) * np.array([1.2, 1.1]) + np.array([5.0, -3.0])
+    else:
+        raise ValueError(kind)
+    z = rng.rand(P) * 2.8
+    rgb = np.floor(rng.rand(P, 3) * 256.0)
+    label = np.minimum(12, np.floor(13.0 * z / 2.8))
+    room = np.concatenate([xy, z[:, None], rgb, label[:, None]], axis=1).astype(np.float64)
+    if kind == "objects":
+        tile = np.floor(room[:, 0] / 0.4) * 100 + np.floor(room[:, 1] / 0.4)
+        room = room[np.argsort(tile, kind="stable")]
+    return np.ascontiguousarray(room)
