@@ -108,6 +108,7 @@ class ScannetDatasetWholeScene:
         self.semantic_labels_list = []
         self.room_coord_min, self.room_coord_max = [], []
         self._rooms = []                       # device copies [P,7] float64, uploaded once
+        self.stage_events = None               # set to [] to collect (name, start, end) CUDA events of the device stages
         ws = torch.zeros(L.psg_scene_minmax_workspace(), dtype=torch.uint8, device=self.device)
         self._ws = ws
         for file in self.file_list:
@@ -131,13 +132,23 @@ class ScannetDatasetWholeScene:
                                self._ws.numel(), _stream())
         return out.cpu().numpy()
 
+    def _timed(self, name, fn):
+        if self.stage_events is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.stage_events.append((name, e0, e1))
+        return out
+
     def _slice(self, index, want_f64, want_f32):
         room = self._rooms[index]
         P, ld = room.shape
         dev = self.device
         with torch.cuda.device(dev):
             st = _stream()
-            mm = self._minmax(room)                                  # :128 (recomputed per call, as the reference does)
+            mm = self._timed("minmax", lambda: self._minmax(room))     # :128 (recomputed per call, as the reference does)
             coord_min, coord_max = mm[:3], mm[3:]
             bounds, centre = grid_columns(coord_min, coord_max, self.block_size, self.stride, self.padding)
             ncell = bounds.shape[0]
@@ -149,7 +160,8 @@ class ScannetDatasetWholeScene:
             nchunk = L.psg_scene_chunks(P)
             counts = torch.empty(ncell * nchunk, dtype=torch.int32, device=dev)
             totals = torch.empty(ncell, dtype=torch.int32, device=dev)
-            L.psg_scene_cell_counts(room.data_ptr(), P, ld, d_bounds.data_ptr(), ncell, counts.data_ptr(), totals.data_ptr(), st)
+            self._timed("cell_counts", lambda: L.psg_scene_cell_counts(room.data_ptr(), P, ld, d_bounds.data_ptr(), ncell,
+                                                                        counts.data_ptr(), totals.data_ptr(), st))
             tot = totals.cpu().numpy().astype(np.int64)              # the only sync: the draws depend on these counts
             pos_parts, block_cell = draw_positions(tot, self.block_points)
             bp = self.block_points
@@ -159,8 +171,8 @@ class ScannetDatasetWholeScene:
             off[1:] = np.cumsum(tot)[:-1]
             d_off = torch.from_numpy(off).to(dev)
             sel = torch.empty(int(tot.sum()), dtype=torch.int32, device=dev)
-            L.psg_scene_cell_fill(room.data_ptr(), P, ld, d_bounds.data_ptr(), ncell, counts.data_ptr(), d_off.data_ptr(),
-                                  sel.data_ptr(), st)
+            self._timed("cell_fill", lambda: L.psg_scene_cell_fill(room.data_ptr(), P, ld, d_bounds.data_ptr(), ncell,
+                                                                    counts.data_ptr(), d_off.data_ptr(), sel.data_ptr(), st))
             d_pos = torch.from_numpy(row_pos).to(dev)
             d_bc = torch.tensor(block_cell, dtype=torch.int32, device=dev)
             nb = rows // bp
@@ -169,11 +181,11 @@ class ScannetDatasetWholeScene:
             label = torch.empty(nb, bp, dtype=torch.int64, device=dev)
             smpw = torch.empty(nb, bp, dtype=torch.float64, device=dev)
             idx = torch.empty(nb, bp, dtype=torch.int64, device=dev)
-            L.psg_scene_gather(room.data_ptr(), ld, 6, sel.data_ptr(), d_off.data_ptr(), d_bc.data_ptr(), d_pos.data_ptr(),
+            self._timed("gather", lambda: L.psg_scene_gather(room.data_ptr(), ld, 6, sel.data_ptr(), d_off.data_ptr(), d_bc.data_ptr(), d_pos.data_ptr(),
                                d_centre.data_ptr(), d_max.data_ptr(), self._lw_dev.data_ptr(), 13, rows, bp,
                                data.data_ptr() if data is not None else None,
                                data32.data_ptr() if data32 is not None else None,
-                               label.data_ptr(), smpw.data_ptr(), idx.data_ptr(), st)
+                               label.data_ptr(), smpw.data_ptr(), idx.data_ptr(), st))
         return data, data32, label, smpw, idx
 
     def __getitem__(self, index):
