@@ -73,3 +73,7 @@ def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
 
 def world_size() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
