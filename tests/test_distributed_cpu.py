@@ -108,3 +108,23 @@ def test_two_rank_counters_equal_the_single_rank_result():
     torch.manual_seed(5)
     full = D.draw_starts([512, 128], 2, D.Shard(6, 0, 6)).numpy()
     assert np.array_equal(np.concatenate([res[0][1], res[1][1]], axis=2), full)
+
+
+def test_bulk_start_draws_equal_the_reference_call_sequence():
+    """draw_starts takes the mt19937 outputs in bulk; values and the generator state afterwards must equal the
+    reference's per-level torch.randint calls (pointnet_util.py:75), across state-regeneration boundaries."""
+    import torch
+    from pointsecguard_b200 import distributed as D
+    assert D._bulk_selftest()
+    for seed, sizes, T, Bg, off, size in ((0, [4096, 1024, 256, 64], 50, 16, 0, 16), (1, [4096, 1024, 256, 64], 7, 128, 48, 16),
+                                          (2, [65536, 16384, 4096, 1024], 3, 9, 2, 5), (3, [1000, 333, 77, 5], 11, 4, 0, 4)):
+        torch.manual_seed(seed)
+        ref = D._draw_starts_loop(sizes, T, Bg)
+        tail_ref = torch.rand(5)
+        torch.manual_seed(seed)
+        got = D.draw_starts(sizes, T, D.Shard(Bg, off, size))
+        tail = torch.rand(5)
+        assert got.dtype == torch.int32 and tuple(got.shape) == (4, T, size)
+        assert torch.equal(got, ref[:, :, off:off + size].permute(1, 0, 2).to(torch.int32))
+        assert torch.equal(tail, tail_ref)
+    assert D._bulk_ok is True
