@@ -310,6 +310,11 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             }
             SA_STAMP();
             tc::fence_before_sync();
+            // The transposed pool borrows WHOLE planes of the tile's operand buffer as per-warp scratch, and the next
+            // tile's gather writes this warp's rows of EVERY plane: a warp that ran ahead would scribble over the scratch
+            // of a sibling still pooling (seen as a rare run-to-run difference of a 50-step attack).  The four warps of
+            // a tile meet here first (named barrier per tile in flight; they meet again at the next MMA hand-off anyway).
+            if (szG >= 16384) asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
         }
     }
     tc::fence_before_sync();

@@ -146,6 +146,34 @@ def test_attack_is_deterministic():
     assert torch.equal(outs[0], outs[1])            # no float atomics anywhere on the path
 
 
+def test_tf32_attack_is_run_to_run_deterministic_at_bench_size():
+    """The fused tcgen05 path at the bench configuration (16 x 4096, 50 steps), eight runs: bit-identical.  A race
+    between the warps of one tile (the pooled scratch of a slow warp overwritten by a fast warp's next gather) used to
+    flip a few hundred values in about one run out of three; differences grow over the steps, so the long attack is
+    the sensitive probe."""
+    from pointsecguard_b200 import torchattacks
+    from pointsecguard_b200.engine import MLP_FP32, MLP_TF32
+    from pointsecguard_b200.models.pointnet2_sem_seg import get_model
+    m = get_model(13)
+    m.load_state_dict(syn.make_state_dict("ssg", init="he"))
+    m = m.cuda().eval()
+    m.set_mlp_mode(MLP_TF32)
+    x = syn.make_blocks(16, 4096, 0)
+    labels = syn.zband_labels(x)
+    mask = labels == 11
+    lab = labels.numpy().astype(np.float64)
+    xd = x.cuda()
+    first = None
+    for _ in range(8):
+        torch.manual_seed(0)
+        adv = torchattacks.tar_NB_attack(m, eps=0.5, alpha=0.1, iters=50, target=7, mask=mask)(xd, lab)
+        if first is None:
+            first = adv.clone()
+        else:
+            assert int((adv != first).sum()) == 0
+    m.set_mlp_mode(MLP_FP32)
+
+
 def test_sharded_attack_equals_full_batch_attack():
     """Two 'ranks' (run one after the other on this GPU) that each attack their shard of a global batch
     -- FPS starts drawn for the GLOBAL batch and sliced (distributed.py) -- reproduce the full-batch
