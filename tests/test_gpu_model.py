@@ -174,6 +174,29 @@ def test_tf32_attack_is_run_to_run_deterministic_at_bench_size():
     m.set_mlp_mode(MLP_FP32)
 
 
+def test_tf32_msg_attack_is_run_to_run_deterministic():
+    """Same probe for the multi-radius network (K = 16 and K = 32 branches of the fused kernels, wide tile programs)."""
+    from pointsecguard_b200 import torchattacks
+    from pointsecguard_b200.engine import MLP_FP32, MLP_TF32
+    from pointsecguard_b200.models.pointnet2_sem_seg_msg import get_model
+    m = get_model(13)
+    m.load_state_dict(syn.make_state_dict("msg", init="he"))
+    m = m.cuda().eval()
+    m.set_mlp_mode(MLP_TF32)
+    x = syn.make_blocks(8, 4096, 5)
+    lab = syn.zband_labels(x).numpy().astype(np.float64)
+    xd = x.cuda()
+    first = None
+    for _ in range(5):
+        torch.manual_seed(0)
+        adv = torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=12)(xd, lab)
+        if first is None:
+            first = adv.clone()
+        else:
+            assert int((adv != first).sum()) == 0
+    m.set_mlp_mode(MLP_FP32)
+
+
 def test_sharded_attack_equals_full_batch_attack():
     """Two 'ranks' (run one after the other on this GPU) that each attack their shard of a global batch
     -- FPS starts drawn for the GLOBAL batch and sliced (distributed.py) -- reproduce the full-batch
