@@ -27,3 +27,31 @@ x2 = xd.clone().requires_grad_(True)
 torch.manual_seed(1); g1 = torch.autograd.grad(m(x2)[0][..., 3].sum(), x2)[0].cpu()
 torch.manual_seed(1); g2 = torch.autograd.grad(m(x2)[0][..., 3].sum(), x2)[0].cpu()
 print("grad equal:", torch.equal(g1, g2), float((g1 - g2).abs().max()))
+
+# ---- the other BASELINE configurations: repeated runs must be bit-identical ----
+def repeat(name, make, x, lab, runs=4):
+    first, diff = None, []
+    for _ in range(runs):
+        torch.manual_seed(0)
+        a = make()(x, lab).detach().cpu()
+        if first is None:
+            first = a
+        else:
+            diff.append(int((a != first).sum()))
+    print(f"{name}: differing elements per repeat {diff}")
+
+x = syn.make_blocks(32, 4096, 0).cuda()
+torch.manual_seed(5); labc = m(x)[0].argmax(2).cpu().numpy().astype(np.float64)
+repeat("NU colour B=32 x 100", lambda: torchattacks.NU_attack(m, c=0.1, kappa=0, steps=100, lr=0.01), x, labc)
+repeat("NU coords+colour B=32 x 40", lambda: torchattacks.NU_attack(m, c=0.1, kappa=0, steps=40, lr=0.01, field=(0, 6)), x, labc, runs=3)
+for N in (16384, 65536):
+    x = syn.make_blocks(8, N, 0).cuda()
+    torch.manual_seed(5); labn = m(x)[0].argmax(2).cpu().numpy().astype(np.float64)
+    repeat(f"NB N={N} B=8 x 10", lambda: torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=10), x, labn, runs=3)
+from pointsecguard_b200.models.pointnet2_sem_seg_msg import get_model as get_msg
+mm = get_msg(13); mm.load_state_dict(syn.make_state_dict("msg", init="he")); mm = mm.cuda().eval(); mm.set_mlp_mode(MLP_TF32)
+x = syn.make_blocks(64, 4096, 0).cuda()
+torch.manual_seed(5); labm = mm(x)[0].argmax(2).cpu().numpy().astype(np.float64)
+repeat("MSG NB B=64 x 10", lambda: torchattacks.NB_attack(mm, eps=0.1, alpha=0.05, iters=10), x, labm, runs=4)
+x1 = syn.make_blocks(1, 4096, 3).cuda(); l1 = syn.zband_labels(x1.cpu()); mk1 = (l1 == 11)[0].numpy()
+repeat("tar-NU B=1 x 60", lambda: torchattacks.tar_NU_attack(m, c=0.1, kappa=0, steps=60, lr=0.01, target=7, mask=mk1), x1, l1.numpy().astype(np.float64), runs=3)
