@@ -262,6 +262,36 @@ def test_coordinate_gradient_vs_reference_golden(golden_dir, arch):
     assert rel_all < 2e-2 and sign_all > 0.998
 
 
+def test_coordinate_gradient_with_repeated_fps_indices_vs_oracle():
+    """A cloud with fewer distinct points than SA1 samples: FPS runs out of distinct points and selects one index many
+    times, so xyz_l = xyz_{l-1}[fps_idx] scatters many gradient rows into ONE source point -- the ordered multi-add
+    path of fps_xyz_back_kernel -- checked against the CPU autograd of the oracle model."""
+    from oracle import pointnet2_oracle as PO
+    sd = syn.make_state_dict("ssg")
+    m = _model("ssg")
+    m.xyz_grad = True
+    gen = torch.Generator().manual_seed(3)
+    base = syn.make_blocks(1, 1024, 4, "uniform")                       # [1,9,1024]
+    pick = torch.randint(0, 600, (1, 1024), generator=gen)              # 1024 points, at most 600 distinct
+    x0 = torch.gather(base, 2, pick.unsqueeze(1).expand(1, 9, 1024)).contiguous()
+    y = syn.zband_labels(x0).long()
+    xo = x0.clone().requires_grad_(True)
+    torch.manual_seed(0)
+    lo, _ = PO.OracleModel(sd, "ssg")(xo)
+    (torch.nn.functional.cross_entropy(lo.reshape(-1, 13), y.view(-1), reduction="sum") / lo.size(1)).backward()
+    xg = x0.clone().cuda().requires_grad_(True)
+    torch.manual_seed(0)
+    lg, _ = m(xg)
+    (torch.nn.functional.cross_entropy(lg.reshape(-1, 13), y.view(-1).cuda(), reduction="sum") / lg.size(1)).backward()
+    # the engine really saw repeated indices at SA1 (1024 samples out of <= 600 distinct points)
+    rel, sign, close = _grad_report(xg.grad.cpu().numpy()[:, :3], xo.grad.numpy()[:, :3])
+    print(f"repeated fps indices: xyz grad rel={rel:.2e} sign={sign:.5f} within-rtol-1e-3={close:.4f}")
+    # coincident points make many coordinate gradients cancel to ~0 (random sign there), so the gate is the relative error
+    assert rel < 1e-3 and sign > 0.95
+    rel_all, sign_all, _ = _grad_report(xg.grad.cpu().numpy(), xo.grad.numpy())
+    assert rel_all < 1e-3 and sign_all > 0.95
+
+
 def test_attack_metrics_vs_oracle_within_half_a_point():
     """north_star gate: accuracy and mIoU after N attack iterations agree with the CPU oracle within
     +-0.5 pt.  Uses the input-sensitive synthetic checkpoint (init="he"), on which the attack really
