@@ -72,6 +72,7 @@ def _draw_starts_loop(level_sizes, T: int, global_batch: int) -> torch.Tensor:
 # is not used if that check fails.
 _STATE_BYTES = 5056          # at::CPUGeneratorImplState: seed u64, left i32, seeded i32, next u64, state u64[624], normal cache
 _bulk_ok = None
+_bulk_bg = None              # one numpy MT19937 instance, re-pointed at torch's state per call (constructing one seeds it from the OS: 0.2 ms)
 
 
 def _bulk_raw32(count: int):
@@ -83,7 +84,10 @@ def _bulk_raw32(count: int):
     if not (1 <= left <= 624):
         raise RuntimeError("unexpected mt19937 position")
     key = st[24:24 + 624 * 8].view(np.uint64)
-    bg = np.random.MT19937()
+    global _bulk_bg
+    if _bulk_bg is None:
+        _bulk_bg = np.random.MT19937(0)
+    bg = _bulk_bg
     bg.state = {"bit_generator": "MT19937", "state": {"key": key.astype(np.uint32), "pos": 625 - left}}
     raw = bg.random_raw(count)
     ns = bg.state["state"]

@@ -90,12 +90,13 @@ class SemSegBase(nn.Module):
             self._sub_engines = []
         return self._engine
 
-    def sub_engines(self, device, count: int):
+    def sub_engines(self, device, count: int, primary=None):
         """``count`` engines (same folded weights, own workspace) with one CUDA stream each.  The
         attacks split a batch into independent sub-batches and enqueue them round-robin: the deep
         levels of the network are latency-bound chains of small launches, and blocks are independent
         in every op of the path, so sub-batches overlap on the GPU."""
-        primary = self.engine(device)
+        if primary is None:                     # (the parameter walk of engine() costs ~0.5 ms: callers that just made it pass it in)
+            primary = self.engine(device)
         if count <= 1:
             return [primary], [None]
         while len(self._sub_engines) < count - 1:

@@ -52,7 +52,7 @@ def _nb_loop(atk, images, labels, target, mask):
     # one sub-batch overlap the others.  FPS starts are drawn ONCE for the whole batch (the
     # reference's draw, pointnet_util.py:75) and sliced.
     nsub = _sub_batches(atk.model, B)
-    engs, streams = atk.model.sub_engines(dev, nsub)
+    engs, streams = atk.model.sub_engines(dev, nsub, primary=eng)
     if nsub > 1:
         # each sub-batch's persistent kernels take an equal share of the SMs, so the streams really overlap
         from pointsecguard_b200 import _lib as L
