@@ -159,6 +159,118 @@ fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, i
     }
 }
 
+// Large clouds (16384 < N <= CS * 1024 * PPT): one thread-block CLUSTER per problem.  CTA q of the cluster keeps its
+// share of the cloud in registers (running min-distance, packed coordinates) and in shared memory (for the look-up of
+// its winner's coordinates); per round every CTA finds its local first arg-max exactly as fps_kernel does, publishes
+// (distance bits, index, x, y, z) into a slot of EVERY peer's shared memory (distributed shared memory stores), and
+// after one cluster barrier every CTA reduces the CS records itself -- no global memory on the round's critical path.
+// The records are double-buffered by round parity: a CTA that runs ahead writes the other buffer, and cannot reach the
+// round after that before every peer has passed this round's barrier.  The single-CTA fallback below re-reads the whole
+// cloud from L2 every round (measured L2-bound at ~7 TB/s with 80 problems of 65536 points in flight).
+template <int CS, int PPT>
+__global__ void __launch_bounds__(1024, 1)
+fps_cluster_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, int N, int npoint,
+                   const int *__restrict__ start, int *__restrict__ out_idx, float *__restrict__ out_xyz)
+{
+    static_assert(PPT % 2 == 0, "points are processed in packed pairs");
+    constexpr int T = 1024, NW = T / 32;
+    extern __shared__ float smem[];
+    float *sx = smem, *sy = smem + T * PPT, *sz = smem + 2 * T * PPT;        // this CTA's points, slot = k * T + t
+    __shared__ unsigned red_v[2][32];
+    __shared__ int red_i[2][32];
+    __shared__ __align__(16) float rec[2][CS][8];                            // per parity, per source CTA: bits, idx, x, y, z
+    unsigned q;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(q));
+    const int p = blockIdx.x / CS;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *cloud = xyz + (long long)(p % nclouds) * cloud_stride;
+
+    float mind[PPT];
+    unsigned long long qx[PPT / 2], qy[PPT / 2], qz[PPT / 2];
+    {
+        float px[PPT], py[PPT], pz[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int i = k * (CS * T) + (int)q * T + t;          // global point index of slot (k, t) of CTA q
+            const bool in = i < N;
+            px[k] = in ? cloud[3 * i] : 0.f; py[k] = in ? cloud[3 * i + 1] : 0.f; pz[k] = in ? cloud[3 * i + 2] : 0.f;
+            mind[k] = in ? 1e10f : -1.f;                          // -1: below every real distance, never selected
+            sx[k * T + t] = px[k]; sy[k * T + t] = py[k]; sz[k * T + t] = pz[k];
+        }
+#pragma unroll
+        for (int k = 0; k < PPT / 2; ++k) {
+            qx[k] = f2_pack(px[2 * k], px[2 * k + 1]); qy[k] = f2_pack(py[2 * k], py[2 * k + 1]); qz[k] = f2_pack(pz[2 * k], pz[2 * k + 1]);
+        }
+    }
+    int far = start[p];
+    float cx = cloud[3 * far], cy = cloud[3 * far + 1], cz = cloud[3 * far + 2];
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // every CTA of the cluster is resident before
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // anyone writes into a peer's shared memory
+
+    int *oi = out_idx + (long long)p * npoint;
+    float *ox = out_xyz ? out_xyz + (long long)p * npoint * 3 : nullptr;
+    for (int it = 0; it < npoint; ++it) {
+        const int par = it & 1;
+        if (q == 0 && t == 0) {
+            oi[it] = far;
+            if (ox) { ox[3 * it] = cx; ox[3 * it + 1] = cy; ox[3 * it + 2] = cz; }
+        }
+        float bestv = -2.f; int bestk = 0;
+        const unsigned long long c2x = f2_pack(cx, cx), c2y = f2_pack(cy, cy), c2z = f2_pack(cz, cz);
+#pragma unroll
+        for (int k = 0; k < PPT / 2; ++k) {
+            float d0, d1;
+            fpsdist2(qx[k], qy[k], qz[k], c2x, c2y, c2z, d0, d1);
+            mind[2 * k] = fminf(mind[2 * k], d0);
+            mind[2 * k + 1] = fminf(mind[2 * k + 1], d1);
+            // slots ascend with the global index inside a thread (k major), so strict '>' keeps the first maximum
+            if (mind[2 * k] > bestv) { bestv = mind[2 * k]; bestk = 2 * k; }
+            if (mind[2 * k + 1] > bestv) { bestv = mind[2 * k + 1]; bestk = 2 * k + 1; }
+        }
+        unsigned best = bestv < 0.f ? 0u : __float_as_uint(bestv);
+        int besti = bestv < 0.f ? kIntMax : bestk * (CS * T) + (int)q * T + t;
+        warp_argmax(best, besti);
+        if (lane == 0) { red_v[par][warp] = best; red_i[par][warp] = besti; }
+        __syncthreads();
+        if (warp == 0) {
+            best = red_v[par][lane]; besti = red_i[par][lane];
+            warp_argmax(best, besti);
+            // the CTA's candidate and its coordinates -> slot q of every CTA's record table
+            float bx = 0.f, by = 0.f, bz = 0.f;
+            if (besti != kIntMax) {
+                const int slot = (besti / (CS * T)) * T + (besti % T);
+                bx = sx[slot]; by = sy[slot]; bz = sz[slot];
+            }
+            if (lane < CS) {
+                const uint32_t local = (uint32_t)__cvta_generic_to_shared(&rec[par][q][0]);
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)lane));
+                asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(__uint_as_float(best)),
+                             "f"(__int_as_float(besti)), "f"(bx), "f"(by) : "memory");
+                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 16u), "f"(bz) : "memory");
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        // every warp reduces the CS records redundantly (first maximum = smallest index among equal distances)
+        {
+            const float4 r4 = lane < CS ? *reinterpret_cast<const float4 *>(&rec[par][lane][0]) : make_float4(0.f, __int_as_float(kIntMax), 0.f, 0.f);
+            const float rz = lane < CS ? rec[par][lane][4] : 0.f;
+            unsigned b = __float_as_uint(r4.x); int bi = __float_as_int(r4.y);
+            const int mine = bi;
+            warp_argmax(b, bi);
+            const unsigned win = __ballot_sync(0xffffffffu, mine == bi && lane < CS);
+            const int src = __ffs(win) - 1;
+            far = bi;
+            cx = __shfl_sync(0xffffffffu, r4.z, src); cy = __shfl_sync(0xffffffffu, r4.w, src); cz = __shfl_sync(0xffffffffu, rz, src);
+        }
+    }
+    // no CTA may exit while a peer can still write into its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // Fallback for clouds that fit neither registers nor shared memory (N > 16384): coordinates are
 // re-read from L2 every round and the min-distance lives in a caller-provided workspace.
 template <int THREADS>
@@ -245,6 +357,26 @@ int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P,
         return launch_fps<256, 16, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 4096) return launch_fps<1024, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 16384) return launch_fps<1024, 16, 1>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    if (N <= 8 * 1024 * 8) {
+        // one 8-CTA cluster per problem; the per-thread share is 4 or 8 points
+        constexpr int CS = 8;
+        const bool small = N <= CS * 1024 * 4;
+        auto kern = small ? fps_cluster_kernel<CS, 4> : fps_cluster_kernel<CS, 8>;
+        const size_t smem = (size_t)3 * 1024 * (small ? 4 : 8) * sizeof(float);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
+        cudaLaunchConfig_t cfg;
+        cfg.gridDim = dim3((unsigned)P * CS); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, kern, xyz, cloud_stride, nclouds, N, npoint, start, out_idx, out_xyz) != cudaSuccess) {
+            cudaGetLastError();
+            return PSG_ECUDA;
+        }
+        PSG_LAUNCH_CHECK();
+        return PSG_OK;
+    }
     if (ws_bytes < psg_fps_workspace_bytes(P, N) || !ws) return PSG_EWORKSPACE;
     fps_global_kernel<1024><<<P, 1024, 0, st>>>(xyz, cloud_stride, nclouds, N, npoint, start, out_idx, out_xyz,
                                                 (float *)ws);

@@ -60,7 +60,8 @@ def test_primitives_match_reference_goldens(golden_dir, PU, case):
         assert dn[b, i, mine[b, i, k]] == dn[b, i, ref[b, i, k]]
 
 
-@pytest.mark.parametrize("N,S", [(64, 16), (256, 64), (1024, 256), (4096, 1024), (6000, 300), (16384, 512), (20000, 64)])
+@pytest.mark.parametrize("N,S", [(64, 16), (256, 64), (1024, 256), (4096, 1024), (6000, 300), (16384, 512), (20000, 64), (40000, 48),
+                                 (65536, 96), (70000, 24)])
 def test_fps_sizes_against_oracle(PU, N, S):
     from oracle import geom as G
     B = 3
