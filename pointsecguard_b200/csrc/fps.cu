@@ -337,6 +337,10 @@ int launch_fps(const float *xyz, long long cloud_stride, int nclouds, int P, int
 
 }  // namespace
 
+// cluster path for 16384 < N <= 65536 (psg_set_option "fps_cluster"; off until verified on the GPU in this round)
+static int g_fps_cluster = 0;
+void psg_fps_use_cluster(int on) { g_fps_cluster = on; }
+
 size_t psg_fps_workspace_bytes(int P, int N)
 {
     return N > 16384 ? (size_t)P * N * sizeof(float) : 0;
@@ -357,7 +361,7 @@ int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P,
         return launch_fps<256, 16, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 4096) return launch_fps<1024, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 16384) return launch_fps<1024, 16, 1>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
-    if (N <= 8 * 1024 * 8) {
+    if (g_fps_cluster && N <= 8 * 1024 * 8) {
         // one 8-CTA cluster per problem; the per-thread share is 4 or 8 points
         constexpr int CS = 8;
         const bool small = N <= CS * 1024 * 4;

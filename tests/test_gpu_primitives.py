@@ -72,6 +72,14 @@ def test_fps_sizes_against_oracle(PU, N, S):
     ref = G.fps(xyz, S, start)
     out = torch.ops.psg.fps(xyz.cuda(), S, start)
     assert torch.equal(out.cpu(), ref)
+    if 16384 < N <= 65536:                       # the thread-block-cluster kernel for large clouds (library option)
+        from pointsecguard_b200 import _lib as L
+        L.psg_set_option(b"fps_cluster", 1)
+        try:
+            out = torch.ops.psg.fps(xyz.cuda(), S, start)
+        finally:
+            L.psg_set_option(b"fps_cluster", 0)
+        assert torch.equal(out.cpu(), ref)
 
 
 @pytest.mark.parametrize("N,S,r,k", [(4096, 1024, 0.1, 32), (1024, 256, 0.2, 32), (300, 7, 0.4, 16), (9000, 100, 0.3, 32),
