@@ -173,7 +173,7 @@ fps_cluster_kernel(const float *__restrict__ xyz, long long cloud_stride, int nc
                    const int *__restrict__ start, int *__restrict__ out_idx, float *__restrict__ out_xyz)
 {
     static_assert(PPT % 2 == 0, "points are processed in packed pairs");
-    constexpr int T = 1024, NW = T / 32;
+    constexpr int T = 1024;
     extern __shared__ float smem[];
     float *sx = smem, *sy = smem + T * PPT, *sz = smem + 2 * T * PPT;        // this CTA's points, slot = k * T + t
     __shared__ unsigned red_v[2][32];
