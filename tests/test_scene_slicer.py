@@ -159,3 +159,17 @@ def test_gpu_slicer_room_scale_properties():
     members = np.where((room[:, 0] >= b[0]) & (room[:, 0] <= b[1]) & (room[:, 1] >= b[2]) & (room[:, 1] <= b[3]))[0]
     blocks_of_col = [k for k in range(idx.shape[0]) if set(idx[k]) <= set(members)]
     assert len(blocks_of_col) >= int(np.ceil(members.size / bp))
+
+
+def test_scatter_last_wins_matches_numpy_assignment_on_cpu():
+    """scene_eval scatters the perturbed points back into the scene with numpy's semantics for repeated indices
+    (the last row wins, NB_nontarget_test_semseg.py:175-176); the helper is device-agnostic torch, checked here on CPU."""
+    from pointsecguard_b200.scene_eval import _scatter_last_wins
+    rng = np.random.default_rng(1)
+    idx = rng.integers(0, 300, 2500)
+    rows = rng.random((2500, 6)).astype(np.float32)
+    ref = np.full((400, 6), -1.0, np.float32)
+    ref[idx] = rows
+    dst = torch.full((400, 6), -1.0)
+    _scatter_last_wins(dst, torch.from_numpy(idx), torch.from_numpy(rows))
+    assert np.array_equal(dst.numpy(), ref)
