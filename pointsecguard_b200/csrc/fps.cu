@@ -338,7 +338,7 @@ int launch_fps(const float *xyz, long long cloud_stride, int nclouds, int P, int
 }  // namespace
 
 // cluster path for 16384 < N <= 65536 (psg_set_option "fps_cluster"; off until verified on the GPU in this round)
-static int g_fps_cluster = 0;
+static int g_fps_cluster = 1;
 void psg_fps_use_cluster(int on) { g_fps_cluster = on; }
 
 size_t psg_fps_workspace_bytes(int P, int N)
