@@ -147,3 +147,45 @@ def test_index_points_shapes(PU):
 def test_cpu_tensors_are_refused(PU):
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.psg.square_distance(torch.rand(1, 4, 3), torch.rand(1, 4, 3))
+
+
+@pytest.mark.parametrize("M,R,grp", [(32768, 4096, 32), (12288, 1024, 0), (196608, 1024, 0), (3000, 7, 0), (32768, 16384, 32),
+                                     (5000, 9000, 0)])
+def test_csr_by_source_is_a_stable_counting_sort(M, R, grp):
+    """psg_csr_build_by_source (the deterministic backward of index_points / interpolation): offsets = exclusive counts
+    per source point, perm = the slots of every bucket in ASCENDING order; padded ball-query slots (copies of the
+    group's first hit, pointnet_util.py:104-106) are left out.  Covers the one-CTA shared-memory kernel (chunk-ordered
+    fill, large buckets: 196608 entries on 1024 keys) and the multi-kernel path (R > 8192)."""
+    from pointsecguard_b200 import _lib as L
+    P = 3
+    rng = np.random.default_rng(M + R)
+    keys = rng.integers(0, R, (P, M)).astype(np.int32)
+    if grp:
+        k3 = keys.reshape(P, M // grp, grp)
+        nreal = rng.integers(1, grp + 1, (P, M // grp))
+        for p in range(P):
+            for g in range(M // grp):
+                row = np.sort(rng.choice(R, nreal[p, g], replace=False)) if nreal[p, g] <= R else k3[p, g, :nreal[p, g]]
+                k3[p, g, :nreal[p, g]] = row
+                k3[p, g, nreal[p, g]:] = row[0]                    # padding = copies of the first hit
+        keys = k3.reshape(P, M)
+    kd = torch.from_numpy(keys).cuda()
+    offs = torch.empty(P * (R + 1), dtype=torch.int32, device="cuda")
+    perm = torch.full((P * M,), -1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(max(L.psg_csr_workspace(P, M, R), 16), dtype=torch.uint8, device="cuda")
+    L.psg_csr_build_by_source(kd.data_ptr(), P, M, R, grp, offs.data_ptr(), perm.data_ptr(), ws.data_ptr(),
+                              torch.cuda.current_stream().cuda_stream)
+    offs, perm = offs.cpu().numpy().reshape(P, R + 1), perm.cpu().numpy().reshape(P, M)
+    for p in range(P):
+        slots = np.arange(M)
+        keep = np.ones(M, bool)
+        if grp:
+            k = slots % grp
+            first = keys[p, slots - k]
+            keep = ~((k > 0) & (keys[p] == first))
+        ks, sl = keys[p][keep], slots[keep]
+        order = np.argsort(ks, kind="stable")
+        counts = np.bincount(ks, minlength=R)
+        assert np.array_equal(offs[p, 1:] - offs[p, :-1], counts)
+        assert offs[p, 0] == 0 and offs[p, R] == keep.sum()
+        assert np.array_equal(perm[p, : keep.sum()], sl[order])
