@@ -162,10 +162,12 @@ fps_kernel(const float *__restrict__ xyz, long long cloud_stride, int nclouds, i
 // Large clouds (16384 < N <= CS * 1024 * PPT): one thread-block CLUSTER per problem.  CTA q of the cluster keeps its
 // share of the cloud in registers (running min-distance, packed coordinates) and in shared memory (for the look-up of
 // its winner's coordinates); per round every CTA finds its local first arg-max exactly as fps_kernel does, publishes
-// (distance bits, index, x, y, z) into a slot of EVERY peer's shared memory (distributed shared memory stores), and
-// after one cluster barrier every CTA reduces the CS records itself -- no global memory on the round's critical path.
-// The records are double-buffered by round parity: a CTA that runs ahead writes the other buffer, and cannot reach the
-// round after that before every peer has passed this round's barrier.  The single-CTA fallback below re-reads the whole
+// (distance bits, index, x, y, z) into a slot of EVERY CTA's shared memory with st.async stores that complete
+// transaction bytes on the DESTINATION's mbarrier, and every CTA waits on its own mbarrier only and reduces the CS
+// records itself -- no global memory and no cluster-wide barrier on the round's critical path (a barrier.cluster per
+// round measured ~1400 of the round's 2400 cycles).  Records and mbarriers are double-buffered by round parity: a CTA
+// can run at most one round ahead of a peer (it needs the peer's record of the previous round to finish it), so it
+// never writes a buffer the peer still reads.  The single-CTA fallback below re-reads the whole
 // cloud from L2 every round (measured L2-bound at ~7 TB/s with 80 problems of 65536 points in flight).
 template <int CS, int PPT>
 __global__ void __launch_bounds__(1024, 1)
@@ -179,6 +181,7 @@ fps_cluster_kernel(const float *__restrict__ xyz, long long cloud_stride, int nc
     __shared__ unsigned red_v[2][32];
     __shared__ int red_i[2][32];
     __shared__ __align__(16) float rec[2][CS][8];                            // per parity, per source CTA: bits, idx, x, y, z
+    __shared__ __align__(8) unsigned long long rbar[2];                      // per parity: 1 arrival + CS * 32 transaction bytes
     unsigned q;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(q));
     const int p = blockIdx.x / CS;
@@ -204,6 +207,12 @@ fps_cluster_kernel(const float *__restrict__ xyz, long long cloud_stride, int nc
     }
     int far = start[p];
     float cx = cloud[3 * far], cy = cloud[3 * far + 1], cz = cloud[3 * far + 2];
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&rbar[0]);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // every CTA of the cluster is resident before
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // anyone writes into a peer's shared memory
@@ -242,17 +251,28 @@ fps_cluster_kernel(const float *__restrict__ xyz, long long cloud_stride, int nc
                 const int slot = (besti / (CS * T)) * T + (besti % T);
                 bx = sx[slot]; by = sy[slot]; bz = sz[slot];
             }
+            if (lane == 0)            // this round's phase of OUR barrier completes when this arrival and all CS records are in
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * par), "r"((uint32_t)CS * 32u) : "memory");
             if (lane < CS) {
                 const uint32_t local = (uint32_t)__cvta_generic_to_shared(&rec[par][q][0]);
-                uint32_t remote;
+                uint32_t remote, rbar_remote;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)lane));
-                asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(__uint_as_float(best)),
-                             "f"(__int_as_float(besti)), "f"(bx), "f"(by) : "memory");
-                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 16u), "f"(bz) : "memory");
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar_remote) : "r"(bar0 + 8u * par), "r"((uint32_t)lane));
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote),
+                             "r"(best), "r"((unsigned)besti), "r"(__float_as_uint(bx)), "r"(__float_as_uint(by)), "r"(rbar_remote) : "memory");
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote + 16u),
+                             "r"(__float_as_uint(bz)), "r"(0u), "r"(0u), "r"(0u), "r"(rbar_remote) : "memory");
             }
         }
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        {
+            // wait for this round's CS records (phase parity of barrier `par` flips every second round)
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u, bar = bar0 + 8u * par;
+            uint32_t ok;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar), "r"(ph) : "memory");
+            } while (!ok);
+        }
         // every warp reduces the CS records redundantly (first maximum = smallest index among equal distances)
         {
             const float4 r4 = lane < CS ? *reinterpret_cast<const float4 *>(&rec[par][lane][0]) : make_float4(0.f, __int_as_float(kIntMax), 0.f, 0.f);
@@ -337,6 +357,28 @@ int launch_fps(const float *xyz, long long cloud_stride, int nclouds, int P, int
 
 }  // namespace
 
+// one CS-CTA cluster per problem; the per-thread share is 2, 4 or 8 points
+template <int CS>
+static int launch_fps_cluster(int ppt, const float *xyz, long long cloud_stride, int nclouds, int P, int N, int npoint,
+                              const int *start, int *out_idx, float *out_xyz, cudaStream_t st)
+{
+    auto kern = ppt == 2 ? fps_cluster_kernel<CS, 2> : (ppt == 4 ? fps_cluster_kernel<CS, 4> : fps_cluster_kernel<CS, 8>);
+    const size_t smem = (size_t)3 * 1024 * ppt * sizeof(float);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = dim3((unsigned)P * CS); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, xyz, cloud_stride, nclouds, N, npoint, start, out_idx, out_xyz) != cudaSuccess) {
+        cudaGetLastError();
+        return PSG_ECUDA;
+    }
+    PSG_LAUNCH_CHECK();
+    return PSG_OK;
+}
+
 // cluster path for 16384 < N <= 65536 (psg_set_option "fps_cluster"; off until verified on the GPU in this round)
 static int g_fps_cluster = 1;
 void psg_fps_use_cluster(int on) { g_fps_cluster = on; }
@@ -360,26 +402,15 @@ int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P,
     if (N <= 4096 && N > 2048 && P >= 128)
         return launch_fps<256, 16, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 4096) return launch_fps<1024, 4, 0>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
+    // few problems of a medium cloud: a cluster per problem (all resident at once) beats one CTA walking 16 points per
+    // thread out of shared memory (1.0 vs 1.5 us per round); with many problems in flight the single CTAs fill the GPU
+    if (g_fps_cluster && N > 8192 && N <= 16384 && P * 8 <= 128)
+        return launch_fps_cluster<8>(2, xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (N <= 16384) return launch_fps<1024, 16, 1>(xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     if (g_fps_cluster && N <= 8 * 1024 * 8) {
-        // one 8-CTA cluster per problem; the per-thread share is 4 or 8 points
         constexpr int CS = 8;
-        const bool small = N <= CS * 1024 * 4;
-        auto kern = small ? fps_cluster_kernel<CS, 4> : fps_cluster_kernel<CS, 8>;
-        const size_t smem = (size_t)3 * 1024 * (small ? 4 : 8) * sizeof(float);
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSG_ECUDA;
-        cudaLaunchConfig_t cfg;
-        cfg.gridDim = dim3((unsigned)P * CS); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, kern, xyz, cloud_stride, nclouds, N, npoint, start, out_idx, out_xyz) != cudaSuccess) {
-            cudaGetLastError();
-            return PSG_ECUDA;
-        }
-        PSG_LAUNCH_CHECK();
-        return PSG_OK;
+        const int ppt = N <= CS * 1024 * 2 ? 2 : (N <= CS * 1024 * 4 ? 4 : 8);
+        return launch_fps_cluster<CS>(ppt, xyz, cloud_stride, nclouds, P, N, npoint, start, out_idx, out_xyz, st);
     }
     if (ws_bytes < psg_fps_workspace_bytes(P, N) || !ws) return PSG_EWORKSPACE;
     fps_global_kernel<1024><<<P, 1024, 0, st>>>(xyz, cloud_stride, nclouds, N, npoint, start, out_idx, out_xyz,

@@ -60,7 +60,7 @@ def test_primitives_match_reference_goldens(golden_dir, PU, case):
         assert dn[b, i, mine[b, i, k]] == dn[b, i, ref[b, i, k]]
 
 
-@pytest.mark.parametrize("N,S", [(64, 16), (256, 64), (1024, 256), (4096, 1024), (6000, 300), (16384, 512), (20000, 64), (40000, 48),
+@pytest.mark.parametrize("N,S", [(64, 16), (256, 64), (1024, 256), (4096, 1024), (6000, 300), (12000, 100), (16384, 512), (20000, 64), (40000, 48),
                                  (65536, 96), (70000, 24)])
 def test_fps_sizes_against_oracle(PU, N, S):
     from oracle import geom as G
@@ -72,13 +72,13 @@ def test_fps_sizes_against_oracle(PU, N, S):
     ref = G.fps(xyz, S, start)
     out = torch.ops.psg.fps(xyz.cuda(), S, start)
     assert torch.equal(out.cpu(), ref)
-    if 16384 < N <= 65536:                       # the thread-block-cluster kernel for large clouds (library option)
+    if 8192 < N <= 65536:                        # cluster kernel (default) above; the single-CTA kernels it replaces here
         from pointsecguard_b200 import _lib as L
-        L.psg_set_option(b"fps_cluster", 1)
+        L.psg_set_option(b"fps_cluster", 0)
         try:
             out = torch.ops.psg.fps(xyz.cuda(), S, start)
         finally:
-            L.psg_set_option(b"fps_cluster", 0)
+            L.psg_set_option(b"fps_cluster", 1)
         assert torch.equal(out.cpu(), ref)
 
 
