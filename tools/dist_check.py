@@ -66,6 +66,35 @@ def main():
             print(f"{name}: shards == full batch: {same}; counters equal: {csame}; acc {MT.summarize(rc.cpu())['acc']:.4f}", flush=True)
             ok = ok and same and csame
         dist.barrier()
+    # ---- whole-scene evaluation (slicer -> attack -> votes -> IoU): scenes strided over the ranks, counters all-reduced ----
+    import tempfile
+    from pointsecguard_b200 import scene_eval
+    from pointsecguard_b200.data_utils.S3DISDataLoader import ScannetDatasetWholeScene
+    nscenes = 2 * world + 1
+    box = [None]
+    if rank == 0:                                             # one directory for all ranks: the same os.listdir order everywhere
+        box[0] = tempfile.mkdtemp()
+        for i in range(nscenes):
+            np.save(os.path.join(box[0], f"Area_5_room_{i:02d}.npy"), syn.make_room(2400 + 100 * i, 40 + i, "tiny"))
+    dist.broadcast_object_list(box, 0)
+    d = box[0]
+    ds = ScannetDatasetWholeScene(d + "/", block_points=1024)
+    mk = lambda: torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=2)
+    res = scene_eval.evaluate_dataset(m, ds, mk, batch_size=4, seed=100)
+    if rank == 0:
+        import pointsecguard_b200.distributed as DD
+        ws, rk = DD.world_size, DD.rank
+        DD.world_size, DD.rank = (lambda: 1), (lambda: 0)
+        saved = DD.all_reduce_sum_
+        DD.all_reduce_sum_ = lambda t: t
+        ref = scene_eval.evaluate_dataset(m, ds, mk, batch_size=4, seed=100)
+        DD.world_size, DD.rank, DD.all_reduce_sum_ = ws, rk, saved
+        same = torch.equal(res["counters"], ref["counters"])
+        mine_ok = all(torch.equal(res["scenes"][i]["pool"].pool, ref["scenes"][i]["pool"].pool) for i in res["scenes"])
+        print(f"scene_eval: {nscenes} scenes over {world} ranks: global counters equal: {same}; this rank's vote pools equal: {mine_ok}; "
+              f"adv scene mIoU {ref['adv_scene']['miou_seen']:.4f} (clean {ref['scene']['miou_seen']:.4f})", flush=True)
+        ok = ok and same and mine_ok
+    dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
