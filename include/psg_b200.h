@@ -42,7 +42,9 @@ int psg_version(void);
 /* farthest_point_sample, pointnet_util.py:63-84.  `start` holds the torch.randint draw of line 75
  * (made by the caller on the CPU generator).  Cloud of problem p is xyz + (p % nclouds) * N * 3, so
  * several problems (attack iterations) may share one cloud.  out_xyz (optional) receives the
- * sampled coordinates = index_points(xyz, fps_idx) of :126. */
+ * sampled coordinates = index_points(xyz, fps_idx) of :126.  Kernels by cloud size: N <= 4096 points in registers
+ * (one CTA per problem), N <= 16384 in shared memory, N <= 65536 one 8-CTA thread-block cluster per problem (candidates
+ * exchanged through distributed shared memory), beyond that a single CTA over a caller-provided min-distance workspace. */
 size_t psg_fps_workspace(int P, int N);
 int psg_fps(const float *xyz, int nclouds, int P, int N, int npoint, const int32_t *start,
             int32_t *out_idx, float *out_xyz, void *workspace, size_t workspace_bytes, psg_stream_t stream);
@@ -243,7 +245,8 @@ int psg_scene_gather(const double *points, int ld, int label_col, const int32_t 
                      const float *labelweights, int ncls, int64_t rows, int block_points, double *data, float *data32,
                      int64_t *label, double *smpw, int64_t *index, psg_stream_t stream);
 
-/* library-wide switches for A/B measurements: "clusters" (default 1) = run the deep levels' tile programs on
+/* library-wide switches for A/B measurements: "fps_cluster" (default 1) = cluster FPS kernel for large clouds;
+ * "clusters" (default 1) = run the deep levels' tile programs on
  * thread-block clusters (N split across CTAs, activations exchanged through distributed shared memory);
  * "sm_cap" (default 0 = all) = spread persistent launches over at most that many SMs, so that sub-batches
  * enqueued on different streams share the GPU instead of queueing behind each other */
