@@ -195,6 +195,7 @@ def run_native(args, rank, world, local_rank):
     x_host, labels, mask = shard.slice(x_all), shard.slice(labels_all), shard.slice(mask_all)
     x_pin = x_host.contiguous().pin_memory()                      # [B,9,N] contiguous pinned host copy
     x_dev = x_host.to(dev)
+    adv_host = torch.empty(x_pin.shape, dtype=torch.float32).pin_memory()      # e2e: the perturbed blocks land here
     lab_np = labels.numpy().astype(np.float64)
     K, W = args.steps, args.warmup
     mk = lambda iters: torchattacks.tar_NB_attack(model, eps=EPS, alpha=ALPHA, iters=iters, target=TARGET, mask=mask)
@@ -239,7 +240,7 @@ def run_native(args, rank, world, local_rank):
     e0.record()
     xd = x_pin.to(dev, non_blocking=True)
     adv2 = atk(xd, lab_np)
-    adv_host = adv2.to("cpu", non_blocking=False)
+    adv_host.copy_(adv2, non_blocking=True)          # result read back into pinned host memory
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
