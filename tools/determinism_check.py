@@ -1,3 +1,5 @@
+"""Run-to-run determinism of the tcgen05 path: repeats the bench attack and the attacks of every BASELINE configuration
+and prints how many output elements differ between repeats (must be 0 everywhere; there are no float atomics on the path)."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.getcwd())
 import bench

@@ -1,3 +1,4 @@
+"""cProfile of the HOST side of one 50-step attack at the bench configuration (what runs before / between the launches)."""
 import os, sys, time, cProfile, pstats, numpy as np, torch
 sys.path.insert(0, os.getcwd())
 import bench
