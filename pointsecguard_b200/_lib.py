@@ -139,3 +139,26 @@ def _wrap(name, restype, argtypes):
 
 for _n, (_r, _a) in _PROTOS.items():
     globals()[_n] = _wrap(_n, _r, _a)
+
+
+# ---- device discipline -----------------------------------------------------------------------------
+# The C library launches on the CURRENT CUDA device and on the stream it is handed.  Every Python entry point of the
+# package therefore runs with the device of its tensors made current, and asks torch for that device's current stream
+# (a model on cuda:1 while cuda:0 is current would otherwise launch on cuda:0's stream with cuda:1's pointers).
+def on_device_of(fn):
+    """Decorator: run ``fn`` with the CUDA device of its first CUDA-tensor argument made current."""
+    import functools
+
+    import torch
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+
+    return wrapped

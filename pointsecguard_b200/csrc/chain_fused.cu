@@ -707,11 +707,11 @@ int pick_cluster(const TileArgs &a, int ntiles, int sms)
 template <int NG, int CS, bool TS = false>
 int launch_tile(const TileArgs &a, int grid, size_t smem, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PsgDeviceOnce attr_once;
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(tile_kernel<NG, CS, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
             return PSG_ECUDA;
-        attr_done = true;
+        attr_once.mark();
     }
     if (psg_launch_pdl(tile_kernel<NG, CS, TS>, dim3((unsigned)grid), dim3(NG * 128 + 64), smem, st, CS, a) != cudaSuccess)
         return PSG_ECUDA;

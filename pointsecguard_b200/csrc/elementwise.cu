@@ -87,14 +87,15 @@ __global__ void pgd_update_kernel(float *__restrict__ adv, const float *__restri
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (long long)B * N) return;
     const int b = (int)(row / N), n = (int)(row % N);
-    const bool step = mask ? mask[row] != 0 : true;
+    // target.py:41-43 reads and writes the masked points only: everything else keeps its input value, unclamped
+    if (mask && mask[row] == 0) return;
     for (int j = 0; j < nc; ++j) {
         const int ch = c0 + j;
         float *fp = feats0.base + tv_off(feats0, row, ch >> 2) + (ch & 3);
         const float cur = *fp;
         const float g = grad.base[tv_off(grad, row, ch >> 2) + (ch & 3)];
         const float sg = g > 0.f ? 1.f : (g < 0.f ? -1.f : 0.f);
-        const float a = step ? __fadd_rn(cur, __fmul_rn(alpha_signed, sg)) : cur;
+        const float a = __fadd_rn(cur, __fmul_rn(alpha_signed, sg));
         const float o = ori[((long long)b * nc + j) * N + n];
         adv[((long long)b * C + ch) * N + n] = a;
         const float eta = fminf(fmaxf(__fsub_rn(a, o), -eps), eps);

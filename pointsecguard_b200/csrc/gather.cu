@@ -533,11 +533,11 @@ int psg_csr_build(const int *keys, long long P, int M, int R, int grp, int *offs
     const long long total = P * M;
     if (R <= 8192) {
         const size_t smem = (size_t)(2 * R + 1) * sizeof(int);
-        static bool attr_done = false;
-        if (!attr_done) {
+        static PsgDeviceOnce attr_once;
+        if (attr_once.need()) {
             if (cudaFuncSetAttribute(csr_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 8192 + 1) * 4) != cudaSuccess)
                 return PSG_ECUDA;
-            attr_done = true;
+            attr_once.mark();
         }
         csr_fused_kernel<<<(unsigned)P, 1024, smem, st>>>(keys, M, R, grp, offs, perm, tmp);
         PSG_LAUNCH_CHECK();

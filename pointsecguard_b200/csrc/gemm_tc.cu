@@ -194,11 +194,11 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
 template <int EPI>
 int launch(const PsgGemmArgs &g, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PsgDeviceOnce attr_once;
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
             return PSG_ECUDA;
-        attr_done = true;
+        attr_once.mark();
     }
     // few row tiles (the deep levels): narrower column tiles spread the layer over more SMs, and the smaller
     // B stages let more of the K loop be in flight at once

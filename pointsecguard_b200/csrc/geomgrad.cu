@@ -217,11 +217,11 @@ int psg_fps_xyz_backward(const float *dxyz_l, const int *fps_idx, int S, int R, 
 {
     const size_t smem = (size_t)2 * R * sizeof(int);
     if (smem <= 200 * 1024) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static PsgDeviceOnce attr_once;
+        if (attr_once.need()) {
             if (cudaFuncSetAttribute(fps_xyz_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
                 return PSG_ECUDA;
-            attr_done = true;
+            attr_once.mark();
         }
         fps_xyz_back_kernel<<<P, S < 1024 ? ((S + 31) / 32) * 32 : 1024, smem, st>>>(dxyz_l, fps_idx, S, R, dxyz_src);
     } else {

@@ -354,12 +354,12 @@ int psg_ball_query_launch(const float *xyz, long long cloud_stride, int nclouds,
     // pointnet_util.py:102 compares the float32 tensor against radius**2 (a Python double, cast to
     // the tensor dtype by the comparison)
     const float r2a = (float)(radius[0] * radius[0]);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PsgDeviceOnce attr_once;
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(ball_query_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(ball_query_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return PSG_ECUDA;
-        attr_done = true;
+        attr_once.mark();
     }
     if (nr == 1) {
         ball_query_kernel<1><<<grid, warps * 32, smem, st>>>(xyz, cloud_stride, nclouds, N, new_xyz, S, r2a, 0.f,
@@ -385,12 +385,12 @@ int psg_three_nn_launch(const float *xyz1, long long stride1, int nclouds1, int 
     if (want_grid) {
         // many queries against a cloud worth binning: uniform grid (bit-identical results)
         const size_t smem = (size_t)S * 20 + (size_t)(2 * kNgMaxCells + 1) * 4 + 16;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static PsgDeviceOnce attr_once;
+        if (attr_once.need()) {
             if (cudaFuncSetAttribute(three_nn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kNgMaxS * 20 + (2 * kNgMaxCells + 1) * 4 + 16) != cudaSuccess)
                 return PSG_ECUDA;
-            attr_done = true;
+            attr_once.mark();
         }
         dim3 ggrid((N + kNgQ - 1) / kNgQ, P);
         three_nn_grid_kernel<<<ggrid, 256, smem, st>>>(xyz1, stride1, nclouds1, N, xyz2, S, idx, w, d2);

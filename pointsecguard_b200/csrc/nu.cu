@@ -277,12 +277,12 @@ int psg_nu_smooth_k(const float *adv0, const float *images0, int C, int N, int k
 {
     const size_t smem = (size_t)4 * N * sizeof(float);
     if (smem > 200 * 1024) return PSG_EUNSUPPORTED;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PsgDeviceOnce attr_once;
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(nu_smooth_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(nu_smooth_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return PSG_ECUDA;
-        attr_done = true;
+        attr_once.mark();
     }
     const unsigned grid = nb((long long)N * kSmoothTPR, 256);
     if (k == 5) nu_smooth_kernel<5><<<grid, 256, smem, st>>>(adv0, images0, C, N, rows_out, grad_out);

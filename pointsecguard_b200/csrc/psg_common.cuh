@@ -47,6 +47,24 @@ static inline size_t tl_bytes(long long rows, int cpad) { return (size_t)round_u
 extern long long g_psg_launch_count;   // kernels launched by this library (net.cu)
 extern int g_psg_sm_cap;               // > 0: persistent launches spread over at most this many SMs (net.cu)
 
+// Function attributes (the opt-in to > 48 KB of dynamic shared memory) are per device: one flag per kernel, one bit
+// per device ordinal; setting an attribute twice from racing threads is harmless, so an atomic bit mask is enough.
+struct PsgDeviceOnce {
+    unsigned long long done[2] = {0, 0};          // device ordinals 0..127
+    bool need() const
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        return !((__atomic_load_n(&done[(d >> 6) & 1], __ATOMIC_ACQUIRE) >> (d & 63)) & 1ull);
+    }
+    void mark()
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        __atomic_fetch_or(&done[(d >> 6) & 1], 1ull << (d & 63), __ATOMIC_RELEASE);
+    }
+};
+
 #define PSG_LAUNCH_CHECK()                                      \
     do {                                                        \
         cudaError_t e__ = cudaGetLastError();                   \

@@ -588,9 +588,9 @@ Pick pick_ng(KernOf kern_of, SmemOf smem_of, int gc, int ng_forced = 0)
     return best;
 }
 
-struct PickKey { int dir, K, gpad, n0, n1, n2, cap; };
+struct PickKey { int dir, K, gpad, n0, n1, n2, cap, dev; };
 struct PickEnt { PickKey k; Pick p; };
-PickEnt g_picks[32];
+PickEnt g_picks[128];
 int g_npicks = 0;
 int g_ng_forced = 0;
 
@@ -602,13 +602,16 @@ namespace {
 template <class KernOf, class SmemOf>
 Pick cached_pick(int dir, int K, int gpad, int n0, int n1, int n2, KernOf kern_of, SmemOf smem_of, int gc)
 {
-    const PickKey key{dir, K, gpad, n0, n1, n2, g_psg_sm_cap};
+    // the pick also carries a side effect of ctas_per_sm (the per-device shared-memory opt-in), so it is keyed by device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const PickKey key{dir, K, gpad, n0, n1, n2, g_psg_sm_cap, dev};
     for (int i = 0; i < g_npicks; ++i) {
         const PickKey &q = g_picks[i].k;
-        if (q.dir == dir && q.K == K && q.gpad == gpad && q.n0 == n0 && q.n1 == n1 && q.n2 == n2 && q.cap == key.cap) return g_picks[i].p;
+        if (q.dir == dir && q.K == K && q.gpad == gpad && q.n0 == n0 && q.n1 == n1 && q.n2 == n2 && q.cap == key.cap && q.dev == dev) return g_picks[i].p;
     }
     const Pick p = pick_ng(kern_of, smem_of, gc, g_ng_forced);
-    if (g_npicks < 32) g_picks[g_npicks++] = PickEnt{key, p};
+    if (g_npicks < 128) g_picks[g_npicks++] = PickEnt{key, p};
     return p;
 }
 }  // namespace

@@ -8,6 +8,7 @@ level per forward).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Dict, List, Sequence
 
@@ -15,6 +16,20 @@ import numpy as np
 import torch
 
 from . import _lib as L
+
+def _on_engine_device(fn):
+    """Engine methods launch on the engine's device whatever device is current in the caller."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        if self.device.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapped
+
 
 MLP_FP32 = 0     # CUDA-core fp32 GEMMs (parity mode)
 MLP_TF32 = 1     # tcgen05 TF32 tensor-core GEMMs
@@ -48,6 +63,8 @@ class Engine:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("pointsecguard_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self._keep: List[np.ndarray] = []
         d = L.NetDesc()
         d.in_channels = layers["in_channels"]
@@ -84,6 +101,7 @@ class Engine:
         self.mlp_mode = mlp_mode
         self.shard = None           # distributed.Shard when the bound batch is a slice of a global batch
         self._stream_handle = None
+        self._stream_obj = None
 
     def _fill(self, m: L.MlpDesc, w: np.ndarray, b: np.ndarray):
         w = np.ascontiguousarray(w, dtype=np.float32)
@@ -104,6 +122,7 @@ class Engine:
         L.psg_net_set_mlp_mode(self._net, mode)
         self.mlp_mode = mode
 
+    @_on_engine_device
     def bind(self, B: int, N: int, T: int):
         """(Re)allocate the workspace for B blocks of N points and T forwards' worth of geometry."""
         if (B, N) == (self.B, self.N) and T <= self.T:
@@ -120,7 +139,7 @@ class Engine:
     def _stream(self):
         """Stream the C library enqueues on: the one set with ``use_stream`` (sub-batch pipelining,
         torchattacks/attacks/nontarget.py) or torch's current stream."""
-        return self._stream_handle if self._stream_handle is not None else torch.cuda.current_stream().cuda_stream
+        return self._stream_handle if self._stream_handle is not None else torch.cuda.current_stream(self.device).cuda_stream
 
     def set_xyz_grad(self, on: bool):
         """Also produce the geometric gradient w.r.t. coordinates (csrc/geomgrad.cu) in backward()."""
@@ -129,6 +148,7 @@ class Engine:
     def use_stream(self, stream):
         """Pin this engine to a torch.cuda.Stream (None = follow torch's current stream)."""
         self._stream_handle = stream.cuda_stream if stream is not None else None
+        self._stream_obj = stream
 
     def draw_starts(self, T: int) -> torch.Tensor:
         """FPS start indices for T forwards, drawn on the global CPU generator in the reference's
@@ -147,6 +167,7 @@ class Engine:
         generator like the single-GPU run does."""
         self.shard = shard
 
+    @_on_engine_device
     def set_input(self, x: torch.Tensor):
         if x.dim() != 3 or x.shape[0] != self.B or x.shape[1] != self.in_channels or x.shape[2] != self.N:
             raise ValueError(f"expected [{self.B},{self.in_channels},{self.N}], got {tuple(x.shape)}")
@@ -155,14 +176,19 @@ class Engine:
         sb, sc, sn = x.stride()
         L.psg_net_set_input(self._net, x.data_ptr(), sb, sc, sn, self._stream())
 
+    @_on_engine_device
     def geometry(self, starts: torch.Tensor):
         """starts: int32 [4, T, B] (CPU or device)."""
         T = starts.shape[1]
         if T > self.T or starts.shape[2] != self.B:
             raise ValueError("geometry: starts do not match the bound problem")
-        self._starts_dev = starts.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+        # the upload is enqueued on the stream the FPS kernels read it on (a pinned engine's side stream: the block then
+        # belongs to that stream in the caching allocator, so replacing the previous chunk's starts is stream-ordered too)
+        with torch.cuda.stream(self._stream_obj) if self._stream_obj is not None else contextlib.nullcontext():
+            self._starts_dev = starts.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         L.psg_net_geometry(self._net, self._starts_dev.data_ptr(), T, self._stream())
 
+    @_on_engine_device
     def forward(self, t: int = 0, want_logp: bool = True, want_l4: bool = False):
         logp = torch.empty(self.B, self.N, self.num_classes, dtype=torch.float32, device=self.device) if want_logp else None
         l4 = torch.empty(self.B, self.c4, self.npoints[3], dtype=torch.float32, device=self.device) if want_l4 else None
@@ -170,28 +196,34 @@ class Engine:
                           self._stream())
         return logp, l4
 
+    @_on_engine_device
     def loss_grad_generic(self, dlogp: torch.Tensor):
         dlogp = dlogp.contiguous()
         self._dlogp_keep = dlogp      # read by the kernels psg_net_backward launches (deferred loss, tcgen05 mode)
         L.psg_net_loss_grad(self._net, 0, dlogp.data_ptr(), None, -1, 1.0, 0.0, None, self._stream())
 
+    @_on_engine_device
     def loss_grad_ce(self, labels: torch.Tensor | None, target: int, scale: float):
         L.psg_net_loss_grad(self._net, 1, None, labels.data_ptr() if labels is not None else None, target, scale, 0.0,
                             None, self._stream())
 
+    @_on_engine_device
     def loss_grad_cw(self, labels: torch.Tensor | None, target: int, sign: float, kappa: float, loss_rows=None):
         L.psg_net_loss_grad(self._net, 2, None, labels.data_ptr() if labels is not None else None, target, sign, kappa,
                             loss_rows.data_ptr() if loss_rows is not None else None, self._stream())
 
+    @_on_engine_device
     def backward(self, t: int = 0, want_grad: bool = True):
         g = torch.empty(self.B, self.in_channels, self.N, dtype=torch.float32, device=self.device) if want_grad else None
         L.psg_net_backward(self._net, t, g.data_ptr() if want_grad else None, self._stream())
         return g
 
+    @_on_engine_device
     def pgd_update(self, adv, ori, mask, c0, nc, alpha_signed, eps, lo=0.0, hi=1.0):
         L.psg_net_pgd_update(self._net, adv.data_ptr(), ori.data_ptr(), mask.data_ptr() if mask is not None else None,
                              c0, nc, alpha_signed, eps, lo, hi, self._stream())
 
+    @_on_engine_device
     def nb_attack(self, adv, ori, mask, labels, target, iters, t0, alpha, eps, scale):
         L.psg_nb_attack(self._net, adv.data_ptr(), ori.data_ptr(), mask.data_ptr() if mask is not None else None,
                         labels.data_ptr() if labels is not None else None, target, iters, t0, alpha, eps, scale,

@@ -13,6 +13,7 @@ import torch
 from . import _lib as L
 
 
+@L.on_device_of
 def attack_counters(logp: torch.Tensor, labels: torch.Tensor, mask: torch.Tensor | None = None, target: int = -1,
                     out: torch.Tensor | None = None) -> torch.Tensor:
     """logp [B,N,C] float32 (CUDA), labels [B,N] -> int64 [C*C + 4] counters (accumulated into ``out``)."""
@@ -60,7 +61,11 @@ class VotePool:
     def __init__(self, num_points: int, num_classes: int = 13, device="cuda"):
         self.pool = torch.zeros(num_points, num_classes, dtype=torch.float32, device=device)
 
-    def add(self, logp: torch.Tensor, point_idx: torch.Tensor, weight: torch.Tensor | None = None):
+    def add(self, logp, point_idx, weight=None):
+        with torch.cuda.device(self.pool.device):
+            return self._add(logp, point_idx, weight)
+
+    def _add(self, logp: torch.Tensor, point_idx: torch.Tensor, weight: torch.Tensor | None = None):
         """logp [B,N,C] (CUDA), point_idx [B,N] scene indices, weight [B,N] or None."""
         if not logp.is_cuda:
             raise RuntimeError("VotePool needs CUDA tensors; there is no CPU fallback")

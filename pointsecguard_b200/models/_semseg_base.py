@@ -7,6 +7,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from pointsecguard_b200._lib import on_device_of
 from pointsecguard_b200.engine import Engine, MLP_FP32, fold_conv_bn
 
 
@@ -19,6 +20,7 @@ class _NetFn(torch.autograd.Function):
     of an engine can be back-propagated (its activations live in the engine workspace)."""
 
     @staticmethod
+    @on_device_of
     def forward(ctx, x, model, starts):
         eng = model.engine(x.device)
         eng.bind(x.shape[0], x.shape[2], 1)
@@ -31,6 +33,7 @@ class _NetFn(torch.autograd.Function):
         return logp, l4
 
     @staticmethod
+    @on_device_of
     def backward(ctx, dlogp, dl4):
         if ctx.model._generation != ctx.gen:
             raise RuntimeError("pointsecguard_b200: the activations of this forward were overwritten by a later "
@@ -153,6 +156,7 @@ class SemSegBase(nn.Module):
         }
 
     # ---- forward ------------------------------------------------------------------------------
+    @on_device_of
     def forward(self, xyz):
         if xyz.dim() != 3 or xyz.shape[1] != 9:
             raise ValueError(f"expected [B, 9, N] input, got {tuple(xyz.shape)}")

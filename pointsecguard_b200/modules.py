@@ -149,6 +149,7 @@ class _SetAbstractionFn(torch.autograd.Function):
         return out.to_channels_first(B, S, ctot)
 
     @staticmethod
+    @L.on_device_of
     def backward(ctx, dout):
         saved, out, B, N, S, D, mode = ctx.saved
         if D == 0:
@@ -194,6 +195,7 @@ def _ball_i32(xyz_t, new_xyz, radii, ks):
     return outs
 
 
+@L.on_device_of
 def set_abstraction_forward(module, xyz, points):
     """PointNetSetAbstraction.forward, pointnet_util.py:181-207: xyz [B,3,N], points [B,D,N] ->
     (new_xyz [B,3,S], new_points [B,Cout,S])."""
@@ -210,6 +212,7 @@ def set_abstraction_forward(module, xyz, points):
     return new_xyz.permute(0, 2, 1), new_points
 
 
+@L.on_device_of
 def set_abstraction_msg_forward(module, xyz, points):
     """PointNetSetAbstractionMsg.forward, pointnet_util.py:229-267 (features first, xyz last, :253)."""
     _need_cuda_eval(module, xyz, points)
@@ -261,6 +264,7 @@ class _FeaturePropagationFn(torch.autograd.Function):
         return ys[-1].to_channels_first(B, N, chain.cout[-1])
 
     @staticmethod
+    @L.on_device_of
     def backward(ctx, dout):
         chain, ys, nn_idx, nn_w, B, N, S, D1, D2, two_source, mode, c1pad = ctx.saved
         dev = dout.device
@@ -285,6 +289,7 @@ class _FeaturePropagationFn(torch.autograd.Function):
         return d1, d2.to_channels_first(B, S, D2), None, None, None, None
 
 
+@L.on_device_of
 def feature_propagation_forward(module, xyz1, xyz2, points1, points2):
     """PointNetFeaturePropagation.forward, pointnet_util.py:281-320: xyz1 [B,3,N], xyz2 [B,3,S],
     points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,Cout,N]."""
@@ -312,6 +317,7 @@ def feature_propagation_forward(module, xyz1, xyz2, points1, points2):
 # --------------------------------------------------------------------------------------------------
 # index_points backward (autograd of pointnet_util.py:43-60), deterministic
 # --------------------------------------------------------------------------------------------------
+@L.on_device_of
 def index_points_backward(g, idx, shape):
     """g [B,S,(K,)C] -> d points [B,N,C]: ordered segmented sum over a source-sorted CSR instead of
     index_put_(accumulate=True)'s float atomics."""

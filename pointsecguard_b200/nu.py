@@ -135,8 +135,10 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
             starts_dev = starts.to(device=dev, dtype=torch.int32).contiguous()     # [4, 1, B]: rebuilt inside the step
         else:
             eng.geometry(starts)
+        lr_at = []                       # learning rate in force when each step of the chunk started
         for i in range(T):
             s = step + i
+            lr_at.append(lr)
             adam_k += 1
             step_size = lr / (1.0 - 0.9 ** adam_k)
             bc2 = math.sqrt(1.0 - 0.999 ** adam_k)
@@ -155,11 +157,14 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
             host_cost[last] = gcost
             acc = hits / denom
             if (acc > thr) if above else (acc < thr):
+                atk.lr = lr_at[-1]       # the reference returns before the halving of the exit step (target.py:118-125)
                 break
         else:
             stat = status.cpu()                                       # the chunk's only host sync
             if int(stat[0]):
                 torch.set_rng_state(states[int(stat[1]) - step])      # un-draw the steps the reference never ran
+                if tar_variant:
+                    atk.lr = lr_at[int(stat[1]) - step]               # ... and un-halve the rate (target.py:118-125)
                 break
         if tar_variant and last > 10 and last % 10 == 0:              # target.py:127-132
             c2 = [host_cost[last], host_cost[last - 10]] if sharded else cost[[last, last - 10]].cpu().tolist()

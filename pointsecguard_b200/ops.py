@@ -46,7 +46,7 @@ def _fps_cuda(xyz, npoint, start):
     return out.to(torch.int64)
 
 
-_LIB.impl("fps", _fps_cuda, "CUDA")
+_LIB.impl("fps", L.on_device_of(_fps_cuda), "CUDA")
 
 # ---- square_distance -------------------------------------------------------------------------------
 _LIB.define("square_distance(Tensor src, Tensor dst) -> Tensor")
@@ -61,7 +61,7 @@ def _sqd_cuda(src, dst):
     return out
 
 
-_LIB.impl("square_distance", _sqd_cuda, "CUDA")
+_LIB.impl("square_distance", L.on_device_of(_sqd_cuda), "CUDA")
 
 # ---- ball query (one or two radii sharing a scan) --------------------------------------------------
 _LIB.define("ball_query(float radius, int nsample, Tensor xyz, Tensor new_xyz) -> Tensor")
@@ -107,8 +107,8 @@ def _ball2_cuda(r0, k0, r1, k1, xyz, new_xyz):
     return o0.to(torch.int64), o1.to(torch.int64)
 
 
-_LIB.impl("ball_query", _ball_cuda, "CUDA")
-_LIB.impl("ball_query2", _ball2_cuda, "CUDA")
+_LIB.impl("ball_query", L.on_device_of(_ball_cuda), "CUDA")
+_LIB.impl("ball_query2", L.on_device_of(_ball2_cuda), "CUDA")
 
 # ---- 3-NN + inverse-distance weights ---------------------------------------------------------------
 _LIB.define("three_nn(Tensor xyz1, Tensor xyz2) -> (Tensor, Tensor, Tensor)")
@@ -125,7 +125,7 @@ def _three_nn_cuda(xyz1, xyz2):
     return idx.to(torch.int64), d2, w
 
 
-_LIB.impl("three_nn", _three_nn_cuda, "CUDA")
+_LIB.impl("three_nn", L.on_device_of(_three_nn_cuda), "CUDA")
 
 # ---- index_points ----------------------------------------------------------------------------------
 _LIB.define("index_points(Tensor points, Tensor idx) -> Tensor")
@@ -141,4 +141,4 @@ def _index_points_cuda(points, idx):
     return out
 
 
-_LIB.impl("index_points", _index_points_cuda, "CUDA")
+_LIB.impl("index_points", L.on_device_of(_index_points_cuda), "CUDA")

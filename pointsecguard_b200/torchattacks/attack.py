@@ -62,6 +62,10 @@ class Attack(object):
         return self.attack + "(" + ", ".join("{}={}".format(k, v) for k, v in info.items()) + ")"
 
     def __call__(self, *input, **kwargs):
+        # run on the images' device (the C library launches on the current device)
+        if input and torch.is_tensor(input[0]) and input[0].is_cuda and input[0].device.index != torch.cuda.current_device():
+            with torch.cuda.device(input[0].device):
+                return self.__call__(*input, **kwargs)
         if self.model.training:
             self.model.eval()
         images = self.forward(*input, **kwargs)

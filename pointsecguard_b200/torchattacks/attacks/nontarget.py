@@ -45,6 +45,11 @@ def _nb_loop(atk, images, labels, target, mask):
     src = images.detach()
     lab = atk._labels_i32(labels, dev) if target < 0 else None
     msk = atk._mask_u8(mask, B, N, dev) if mask is not None else None
+    if msk is not None and B > 1 and getattr(mask, "ndim", 2) == 1:
+        # target.py:26,36 with a batch: the cost reads outputs[0] only, so the gradient of every other block is zero and
+        # sign(0) = 0 leaves it where it is -- the reference attacks block 0 alone.  A [B,N] mask attacks every block.
+        msk = msk.clone()
+        msk[1:] = 0
     # nontarget.py:34: sum-CE / N;  target.py:38: mean CE over the B*N points
     scale = 1.0 / N if target < 0 else 1.0 / (B * N)
     # Blocks are independent in every op of the path: split the batch into sub-batches, one engine and

@@ -1,8 +1,10 @@
 """Targeted / masked colour attacks -- drop-in for PointNet/attacks/torchattacks/attacks/target.py.
 
 tar_NB_attack (:7-45): sign *descent* on the mean CE to ``target`` over all points, only masked
-points' colours move.  The reference handles B == 1 with a [N] mask; a [B,N] mask generalises it to
-batches with identical per-block arithmetic (the step is a sign).
+points' colours move (unmasked points are neither stepped nor clamped, target.py:41-43).  The reference handles
+B == 1 with a [N] mask; handed a batch it still attacks block 0 only (its cost reads ``outputs[0]``, :36), and so does
+this class for a 1-D mask.  A [B,N] mask is the generalisation to batches with identical
+per-block arithmetic (the step is a sign, so the loss normalisation does not matter).
 """
 from __future__ import annotations
 
