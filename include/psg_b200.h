@@ -140,6 +140,13 @@ int psg_net_bind(psg_net *net, int B, int N, int T, void *workspace, size_t work
 int psg_net_set_input(psg_net *net, const float *x, int64_t sb, int64_t sc, int64_t sn, psg_stream_t stream);
 /* starts int32 [4][T][B]: FPS start index per level / forward / block (pointnet_util.py:75 draws) */
 int psg_net_geometry(psg_net *net, const int32_t *starts, int T, psg_stream_t stream);
+/* Copy one resident geometry buffer of forward slot t into dst (device memory, dst_bytes large enough; enqueued on
+ * stream): what 0 = FPS indices of SA level (int32 [B][S]; pointnet_util.py:84), 1 = ball-query indices of SA level /
+ * branch (int32 [B][S][K]; :87-107), 2 = 3-NN indices of FP level (int32 [B][Nf][3]; :302-303, level 0 = fp1 ... 3 = fp4),
+ * 3 = their inverse-distance weights (float [B][Nf][3]; :304-306), 4 = coordinates of SA level (float [B][S][3]).
+ * SA levels count 1..4.  These are the indices the network forward itself consumes (parity tests read them). */
+int psg_net_read_geometry(const psg_net *net, int what, int level, int branch, int t, void *dst, size_t dst_bytes,
+                          psg_stream_t stream);
 /* forward pass t: logp [B,N,ncls] and l4_points [B,C4,16] (either may be null) */
 int psg_net_forward(psg_net *net, int t, float *logp, float *l4_points, psg_stream_t stream);
 /* gradient of a cost w.r.t. the logits of the last forward:

@@ -29,13 +29,16 @@ def _labels(labels):
         else labels.to(torch.int64)
 
 
-def nb_attack(model, images, labels, eps=0.3, alpha=2 / 255, iters=40, field=slice(3, 6)):
-    """nontarget.py:18-42: L-inf sign ascent on sum-CE / N; returns the un-projected last step."""
+def nb_attack(model, images, labels, eps=0.3, alpha=2 / 255, iters=40, field=slice(3, 6), snapshots=None):
+    """nontarget.py:18-42: L-inf sign ascent on sum-CE / N; returns the un-projected last step.
+    ``snapshots``: optional list that receives the projected colours entering every iteration (test hook)."""
     col = images[:, field].clone().detach()
     ori = col.clone()
     adv = images.clone().detach()
     y = _labels(labels)
     for _ in range(iters):
+        if snapshots is not None:
+            snapshots.append(col.detach().clone())
         col.requires_grad_(True)
         adv[:, field] = col
         logp, _ = model(adv)
@@ -49,7 +52,7 @@ def nb_attack(model, images, labels, eps=0.3, alpha=2 / 255, iters=40, field=sli
 
 
 def tar_nb_attack(model, images, labels, eps=0.3, alpha=2 / 255, iters=40, target=None, mask=None,
-                  field=slice(3, 6)):
+                  field=slice(3, 6), snapshots=None):
     """target.py:18-45: masked sign *descent* on mean CE to ``target`` over all points.
     mask: bool [N] (reference, B == 1) or bool [B,N] (generalised, per-block masks)."""
     m = torch.as_tensor(np.asarray(mask)) if not torch.is_tensor(mask) else mask
@@ -61,6 +64,8 @@ def tar_nb_attack(model, images, labels, eps=0.3, alpha=2 / 255, iters=40, targe
     adv = images.clone().detach()
     tgt = torch.full((B * N,), int(target), dtype=torch.int64)
     for _ in range(iters):
+        if snapshots is not None:
+            snapshots.append(col.detach().clone())
         col.requires_grad_(True)
         adv[:, field] = torch.where(m3, col, adv[:, field])
         logp, _ = model(adv)

@@ -93,13 +93,23 @@ def three_nn(xyz1, xyz2):
 
 
 # --------------------------------------------------------------------------------------------
-# layers  (pointnet_util.py:166-320), eval mode only
+# layers  (pointnet_util.py:166-320).  Eval mode unless TRAIN is set (oracle/train_oracle.py): then BatchNorm
+# normalises with the batch statistics and updates the running ones in place in ``sd`` (momentum TRAIN["momentum"]),
+# as nn.BatchNorm{1,2}d.train() does, and the head's Dropout(0.5) is active.
 # --------------------------------------------------------------------------------------------
+TRAIN = None
+
+
 def _conv_bn_relu(sd, cp, bp, x):
     w, b = sd[cp + ".weight"], sd[cp + ".bias"]
     y = F.conv2d(x, w, b) if w.dim() == 4 else F.conv1d(x, w, b)
-    y = F.batch_norm(y, sd[bp + ".running_mean"], sd[bp + ".running_var"],
-                     sd[bp + ".weight"], sd[bp + ".bias"], False, 0.0, 1e-5)
+    if TRAIN is not None:
+        sd[bp + ".num_batches_tracked"] += 1
+        y = F.batch_norm(y, sd[bp + ".running_mean"], sd[bp + ".running_var"],
+                         sd[bp + ".weight"], sd[bp + ".bias"], True, TRAIN["momentum"], 1e-5)
+    else:
+        y = F.batch_norm(y, sd[bp + ".running_mean"], sd[bp + ".running_var"],
+                         sd[bp + ".weight"], sd[bp + ".bias"], False, 0.0, 1e-5)
     return F.relu(y)
 
 
@@ -184,6 +194,11 @@ def model_forward(sd, x, arch="ssg", trace=None):
     up = feature_propagation(sd, "fp2", 2, xyzs[1], xyzs[2], feats[1], up, trace)
     up = feature_propagation(sd, "fp1", 3, xyzs[0], xyzs[1], None, up, trace)
     h = _conv_bn_relu(sd, "conv1", "bn1", up)          # dropout is the identity in eval mode
+    if TRAIN is not None:
+        if TRAIN.get("dropout_mask") is not None:      # injected keep-mask [B,128,N] (0/1), scaled like F.dropout
+            h = h * TRAIN["dropout_mask"] * 2.0
+        else:
+            h = F.dropout(h, 0.5, True)                # pointnet2_sem_seg.py:18,35
     z = F.conv1d(h, sd["conv2.weight"], sd["conv2.bias"])
     logp = F.log_softmax(z, dim=1).permute(0, 2, 1)
     return logp, l4_points

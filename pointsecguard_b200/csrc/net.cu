@@ -588,6 +588,36 @@ extern "C" int psg_net_geometry(psg_net *n, const int32_t *starts, int T, psg_st
     return PSG_OK;
 }
 
+extern "C" int psg_net_read_geometry(const psg_net *n, int what, int level, int branch, int t, void *dst, size_t dst_bytes,
+                                     psg_stream_t stream)
+{
+    if (!n || !n->bound || !dst || t < 0 || t >= n->T) return PSG_EINVAL;
+    const size_t B = n->B;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    if (what == 0 || what == 4) {
+        if (level < 1 || level > 4) return PSG_EINVAL;
+        const size_t S = n->npts[level];
+        if (what == 0) { src = n->fps_idx[level] + (size_t)t * B * S; bytes = B * S * sizeof(int); }
+        else { src = n->xyz[level] + (size_t)t * B * S * 3; bytes = B * S * 3 * sizeof(float); }
+    } else if (what == 1) {
+        if (level < 1 || level > 4 || branch < 0 || branch >= n->sa[level - 1].nbr) return PSG_EINVAL;
+        const Branch &Br = n->sa[level - 1].br[branch];
+        const size_t M = (size_t)n->npts[level] * Br.K;
+        src = Br.ball + (size_t)t * B * M; bytes = B * M * sizeof(int);
+    } else if (what == 2 || what == 3) {
+        if (level < 0 || level > 3) return PSG_EINVAL;
+        const size_t Nf = n->npts[level];
+        if (what == 2) src = n->fp[level].nn_idx + (size_t)t * B * Nf * 3;
+        else src = n->fp[level].nn_w + (size_t)t * B * Nf * 3;
+        bytes = B * Nf * 3 * 4;
+    } else
+        return PSG_EINVAL;
+    if (dst_bytes < bytes) return PSG_EWORKSPACE;
+    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return PSG_ECUDA;
+    return PSG_OK;
+}
+
 static inline TView tv(float *p, int width, int col0 = 0) { return TView{p, width / 4, col0 / 4}; }
 
 static PsgSaFused sa_fused_desc(psg_net *n, int l, int b, int t)

@@ -88,6 +88,7 @@ class Engine:
         self._fill(d.conv1, *layers["conv1"])
         self._fill(d.conv2, *layers["conv2"])
         self.npoints = [sa["npoint"] for sa in layers["sa"]]
+        self._nsample = [list(sa["nsample"]) for sa in layers["sa"]]
         self.num_classes = layers["num_classes"]
         self.in_channels = layers["in_channels"]
         self.c4 = sum(m[-1][0].shape[0] for m in layers["sa"][3]["mlps"])
@@ -187,6 +188,23 @@ class Engine:
         with torch.cuda.stream(self._stream_obj) if self._stream_obj is not None else contextlib.nullcontext():
             self._starts_dev = starts.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         L.psg_net_geometry(self._net, self._starts_dev.data_ptr(), T, self._stream())
+
+    @_on_engine_device
+    def read_geometry(self, what: str, level: int, branch: int = 0, t: int = 0) -> torch.Tensor:
+        """The resident index buffers the network forward consumes (slot t): ``what`` in fps | ball | nn_idx | nn_w |
+        xyz; SA levels 1..4, FP levels 0 (fp1) .. 3 (fp4).  Parity tests compare them with the oracle."""
+        code = {"fps": 0, "ball": 1, "nn_idx": 2, "nn_w": 3, "xyz": 4}[what]
+        np_ = [self.N] + self.npoints
+        if code == 0:
+            out = torch.empty(self.B, np_[level], dtype=torch.int32, device=self.device)
+        elif code == 4:
+            out = torch.empty(self.B, np_[level], 3, dtype=torch.float32, device=self.device)
+        elif code == 1:
+            out = torch.empty(self.B, np_[level], self._nsample[level - 1][branch], dtype=torch.int32, device=self.device)
+        else:
+            out = torch.empty(self.B, np_[level], 3, dtype=torch.int32 if code == 2 else torch.float32, device=self.device)
+        L.psg_net_read_geometry(self._net, code, level, branch, t, out.data_ptr(), out.numel() * 4, self._stream())
+        return out
 
     @_on_engine_device
     def forward(self, t: int = 0, want_logp: bool = True, want_l4: bool = False):

@@ -184,6 +184,7 @@ def nu_attack(atk, images, labels, mask, target, neighbour, masked_variant=None)
         step = end
     L.psg_net_set_xyz_grad(eng._net, 0)
     atk.model._generation += 1
+    atk.last_cost = cost          # per-step cost of this call (device tensor; entries past an early exit stay 0)
     return adv
 
 

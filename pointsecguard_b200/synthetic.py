@@ -87,6 +87,30 @@ def zband_labels(x: torch.Tensor) -> torch.Tensor:
     return torch.clamp(torch.floor(z * (13.0 / 3.0)), 0, NUM_CLASSES - 1).to(torch.int64)
 
 
+def class_palette() -> torch.Tensor:
+    """[13, 3] fixed class colours in [0.15, 0.85] of the *painted* synthetic blocks."""
+    g = torch.Generator("cpu").manual_seed(77)
+    return 0.15 + 0.7 * torch.rand(NUM_CLASSES, 3, generator=g, dtype=torch.float32)
+
+
+def make_painted_blocks(B: int, N: int = 4096, seed: int = 0, noise: float = 0.08):
+    """Synthetic *labelled* blocks for training and for informative attack metrics: uniform blocks
+    (``make_blocks``) cut into 13 horizontal slabs whose class is painted into the colour channels, colour =
+    palette[class] + noise * N(0,1) clipped to [0,1].  The slab pattern is shifted cyclically by a random offset per
+    block (class = floor(13 * frac(z / 3 + u_b))), so the absolute height says nothing about the class: a network
+    trained on these blocks reads the class from the colours of a neighbourhood, and a colour attack can move its
+    predictions -- which a random-init network's metrics never show.
+    Returns (x [B,9,N] non-contiguous view like make_blocks, labels int64 [B,N])."""
+    x = make_blocks(B, N, seed, "uniform")
+    g = torch.Generator("cpu").manual_seed(seed + 7919)
+    shift = torch.rand(B, 1, generator=g, dtype=torch.float32)
+    frac = torch.remainder(x[:, 2, :] / 3.0 + shift, 1.0)
+    labels = torch.clamp(torch.floor(frac * NUM_CLASSES), 0, NUM_CLASSES - 1).to(torch.int64)
+    col = class_palette()[labels] + noise * torch.randn(B, N, 3, generator=g, dtype=torch.float32)
+    x[:, 3:6] = col.clamp_(0.0, 1.0).transpose(2, 1)
+    return x, labels
+
+
 def _conv_keys(prefix, cin, cout, ndim):
     shape = (cout, cin, 1, 1) if ndim == 2 else (cout, cin, 1)
     return [(prefix + ".weight", shape, cin), (prefix + ".bias", (cout,), cin)]
@@ -168,6 +192,20 @@ def make_state_dict(arch: str = "ssg", seed: int = 1234, randomize_bn: bool = Tr
         else:
             bound = 1.0 / math.sqrt(kind)
             sd[key] = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
+    return sd
+
+
+def load_checkpoint(arch: str = "ssg") -> "OrderedDict[str, torch.Tensor]":
+    """The synthetic *trained* checkpoint shipped with the tests (tests/golden/ckpt_<arch>_painted.npz: 300 Adam steps
+    on ``make_painted_blocks`` from the ``init="he"`` network, made by oracle/make_checkpoint.py; stored rounded to
+    float16, widened here exactly).  On it the colour attacks visibly move accuracy / mIoU / target hit-rate."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", f"ckpt_{arch}_painted.npz")
+    z = np.load(path)
+    sd = OrderedDict()
+    for key, _, _ in state_dict_spec(arch):
+        v = torch.from_numpy(z[key])
+        sd[key] = v.float() if v.dtype == torch.float16 else v
     return sd
 
 

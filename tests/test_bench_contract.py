@@ -18,9 +18,13 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "pgd_attack_steps_per_sec" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    from oracle import build_ref
+    assert cb["kind"] == ("reference" if build_ref.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and "B=16x4096" in d["config"]["workload"]
+    import bench
+    assert d["config"] == bench.config_dict()          # both arms print the same config
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():

@@ -107,3 +107,27 @@ def test_bn_folding_matches_conv_bn_eval():
                                                  "running_var": bn.running_var}, bn.eps)
     y = torch.einsum("oc,bcn->bon", torch.from_numpy(w), x) + torch.from_numpy(b)[None, :, None]
     torch.testing.assert_close(y, bn(conv(x)), rtol=1e-5, atol=1e-5)
+
+
+def test_bare_name_drop_in_imports():
+    """The reference's scripts put models/ and attacks/ on sys.path and import by bare name
+    (NB_nontarget_test_semseg.py:18-20, 33, 100-103); the package offers the same names under those directories."""
+    import subprocess
+    import sys
+    pkg = os.path.join(REPO, "pointsecguard_b200")
+    code = (
+        "import sys, importlib\n"
+        f"sys.path.insert(0, {REPO!r}); sys.path.append({os.path.join(pkg, 'models')!r}); sys.path.append({pkg!r})\n"
+        "MODEL = importlib.import_module('pointnet2_sem_seg'); MSG = importlib.import_module('pointnet2_sem_seg_msg')\n"
+        "import torchattacks\n"
+        "assert 'pointsecguard_b200' in MODEL.__file__ and 'pointsecguard_b200' in torchattacks.__file__\n"
+        "m = MODEL.get_model(13); MSG.get_model(13); MODEL.get_loss()\n"
+        "for n in ('NB_attack', 'NU_attack', 'tar_NB_attack', 'tar_NU_attack'):\n"
+        "    getattr(torchattacks, n)(m)\n"
+        "import pointnet_util as PU\n"
+        "for n in ('square_distance', 'index_points', 'farthest_point_sample', 'query_ball_point', 'sample_and_group',\n"
+        "          'sample_and_group_all', 'PointNetSetAbstraction', 'PointNetSetAbstractionMsg', 'PointNetFeaturePropagation'):\n"
+        "    assert hasattr(PU, n), n\n"
+        "print('ok')\n")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("ok"), p.stderr[-2000:]

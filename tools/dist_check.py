@@ -20,9 +20,16 @@ sys.path.insert(0, REPO)
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # PSG_DIST_BACKEND=gloo lets several ranks share one GPU (NCCL refuses that): the host-side sharding logic, the
+    # all-reduced counters and the per-step NU exchange are the same code, only the transport differs
+    backend = os.environ.get("PSG_DIST_BACKEND", "nccl")
+    local = local % torch.cuda.device_count()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group(backend)
     from pointsecguard_b200 import distributed as D, metrics as MT, synthetic as syn, torchattacks
     from pointsecguard_b200.models.pointnet2_sem_seg import get_model
     m = get_model(13)
@@ -36,9 +43,11 @@ def main():
     ok = True
 
     def gather(t):
+        if backend != "nccl":                       # gloo gathers host tensors
+            t = t.cpu()
         parts = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(parts, t.contiguous())
-        return torch.cat(parts)
+        return torch.cat(parts).to(dev)
 
     for name, make in (("NB", lambda mm: torchattacks.NB_attack(mm, eps=0.1, alpha=0.05, iters=4)),
                        ("NU", lambda mm: torchattacks.NU_attack(mm, c=0.1, kappa=0, steps=6, lr=0.01))):
@@ -95,7 +104,7 @@ def main():
               f"adv scene mIoU {ref['adv_scene']['miou_seen']:.4f} (clean {ref['scene']['miou_seen']:.4f})", flush=True)
         ok = ok and same and mine_ok
     dist.barrier()
-    flag = torch.tensor([1 if ok else 0], device=dev)
+    flag = torch.tensor([1 if ok else 0], device=dev if backend == "nccl" else "cpu")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
