@@ -103,6 +103,10 @@ int psg_segment_sum(const float *src_base, int src_wchunks, int src_c0, int64_t 
 typedef struct psg_mlp psg_mlp;
 psg_mlp *psg_mlp_create(const float *w_host, const float *b_host, int cin, int cout);
 void psg_mlp_destroy(psg_mlp *m);
+/* training: a layer whose W [cout][cin] / b [cout] live in DEVICE memory (nn.Parameter storage) and change every
+ * optimiser step; psg_mlp_load (re)packs them into the operand layouts with one small kernel on `stream` */
+psg_mlp *psg_mlp_create_device(int cin, int cout);
+int psg_mlp_load(psg_mlp *m, const float *w_dev, const float *b_dev, psg_stream_t stream);
 /* forward: out = act([a1 | a2] W^T + b), relu = 1/0.  Widths in 16-byte chunks. */
 int psg_mlp_forward(const psg_mlp *m, const float *a1_base, int a1_wchunks, int a1_c0, int k1chunks,
                     const float *a2_base, int a2_wchunks, int a2_c0, int k2chunks, int64_t rows,
@@ -110,6 +114,48 @@ int psg_mlp_forward(const psg_mlp *m, const float *a1_base, int a1_wchunks, int 
 /* dgrad: dx = (dy W) [. (mask > 0) if mask_base]; dy is grad w.r.t. the pre-activation */
 int psg_mlp_backward(const psg_mlp *m, const float *dy_base, int dy_wchunks, int64_t rows, float *dx_base,
                      int dx_wchunks, const float *mask_base, int mask_wchunks, int mode, psg_stream_t stream);
+
+/* ---- training step of the same network (train_semseg.py:164-179) ------------
+ * The forward / dgrad GEMMs, grouping, max-pool, interpolation and segmented sums above are reused; these entry
+ * points add what training needs.  All reductions are deterministic (fixed partitions, ordered combination). */
+/* nn.BatchNorm{1,2}d.train() + optional ReLU over the rows of z (pointnet_util.py:200-203, :317-319): batch mean /
+ * biased variance -> y = relu?((z - mean) * invstd * gamma + beta); running_mean / running_var (may be null) updated in
+ * place with `momentum` (variance unbiased); save_mean / save_invstd [C] feed the backward.  C % 4 == 0. */
+size_t psg_bn_workspace(int C);
+int psg_bn_train_forward(const float *z_base, int z_wchunks, int64_t rows, int C, const float *gamma, const float *beta,
+                         float *running_mean, float *running_var, float momentum, float eps, float *y_base,
+                         int y_wchunks, int relu, float *save_mean, float *save_invstd, void *workspace,
+                         size_t workspace_bytes, psg_stream_t stream);
+/* autograd of the same: g = dy * [y > 0] (y_base null: no ReLU); dgamma = sum g xhat, dbeta = sum g,
+ * dz = (g - dbeta/n - xhat dgamma/n) gamma invstd (dz may alias dy; rows past the end are zeroed) */
+int psg_bn_train_backward(const float *dy_base, int dy_wchunks, const float *y_base, int y_wchunks, const float *z_base,
+                          int z_wchunks, int64_t rows, int C, const float *gamma, const float *save_mean,
+                          const float *save_invstd, float *dgamma, float *dbeta, float *dz_base, int dz_wchunks,
+                          void *workspace, size_t workspace_bytes, psg_stream_t stream);
+/* weight / bias gradient of a 1x1 conv: dW[cout][k1+k2] (row-major) = dz^T [A1 | A2], db[cout] = column sums of dz
+ * (db may be null; accumulate != 0 adds to dW).  Split-K over rows, partial tiles summed in order. */
+size_t psg_wgrad_workspace(int cout, int cin, int64_t rows);
+int psg_conv_wgrad(const float *dz_base, int dz_wchunks, int cout, const float *a1_base, int a1_wchunks, int a1_c0, int k1,
+                   const float *a2_base, int a2_wchunks, int a2_c0, int k2, int64_t rows, float *dW, float *db,
+                   int accumulate, void *workspace, size_t workspace_bytes, psg_stream_t stream);
+/* F.log_softmax over the class logits (pointnet2_sem_seg.py:38) -> logp [rows][ncls] row-major, and its autograd */
+int psg_log_softmax_rows(const float *z_base, int z_wchunks, int64_t rows, int ncls, float *logp, psg_stream_t stream);
+int psg_dlogits_from_dlogp(const float *z_base, int z_wchunks, const float *dlogp, int64_t rows, int ncls, float *dz_base,
+                           int dz_wchunks, psg_stream_t stream);
+/* get_loss = F.nll_loss(pred, target, weight) (pointnet2_sem_seg.py:43-49): loss[0] = -sum w[y] logp[y] / sum w[y];
+ * wsum[0] = sum w[y] (kept for the backward); labels int64; weight [ncls] or null */
+size_t psg_nll_workspace(void);
+int psg_nll_loss(const float *logp, const int64_t *labels, const float *weight, int64_t rows, int ncls, float *loss,
+                 float *wsum, void *workspace, size_t workspace_bytes, psg_stream_t stream);
+int psg_nll_loss_backward(const int64_t *labels, const float *weight, int64_t rows, int ncls, const float *grad_out,
+                          const float *wsum, float *dlogp, psg_stream_t stream);
+/* x *= m * scale, both T-layout [rows][C] (nn.Dropout(0.5) forward and backward with a 0/1 keep mask, scale 2) */
+int psg_tl_mul(float *x_base, int x_wchunks, const float *m_base, int m_wchunks, int64_t rows, int C, float scale,
+               psg_stream_t stream);
+/* torch.optim.Adam step over one flat buffer (train_semseg.py:125-132: betas (0.9, 0.999), eps 1e-8, L2 weight_decay
+ * added to the gradient); `step` counts from 1 */
+int psg_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, psg_stream_t stream);
 
 /* ---- whole-network engine (pointnet2_sem_seg.py:22-40, pointnet2_sem_seg_msg.py:23-41) -------- */
 typedef struct { int cin, cout; const float *w_host; const float *b_host; } psg_mlp_desc;

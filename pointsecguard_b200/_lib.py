@@ -71,6 +71,20 @@ _PROTOS = {
     "psg_segment_sum": (_i, [_vp, _i, _i, _i64, _i, _vp, _vp, _vp, _i, _i, _i64, _i, _vp, _i, _i, _i, _vp]),
     "psg_mlp_create": (_vp, [_vp, _vp, _i, _i]),
     "psg_mlp_destroy": (None, [_vp]),
+    "psg_mlp_create_device": (_vp, [_i, _i]),
+    "psg_mlp_load": (_i, [_vp, _vp, _vp, _vp]),
+    "psg_bn_workspace": (_sz, [_i]),
+    "psg_bn_train_forward": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "psg_bn_train_backward": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "psg_wgrad_workspace": (_sz, [_i, _i, _i64]),
+    "psg_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i64, _vp, _vp, _i, _vp, _sz, _vp]),
+    "psg_log_softmax_rows": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "psg_dlogits_from_dlogp": (_i, [_vp, _i, _vp, _i64, _i, _vp, _i, _vp]),
+    "psg_nll_workspace": (_sz, []),
+    "psg_nll_loss": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
+    "psg_nll_loss_backward": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
+    "psg_tl_mul": (_i, [_vp, _i, _vp, _i, _i64, _i, _f, _vp]),
+    "psg_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp]),
     "psg_mlp_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp]),
     "psg_mlp_backward": (_i, [_vp, _vp, _i, _i64, _vp, _i, _vp, _i, _i, _vp]),
     "psg_net_create": (_vp, [C.POINTER(NetDesc)]),

@@ -71,6 +71,9 @@ int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, c
 int psg_copy_cols(TView src, TView dst, long long rows, int ncols, int accumulate, cudaStream_t st);
 int psg_index_points_rm(const float *pts, const long long *idx, int B, int N, int C, long long M, float *out,
                         cudaStream_t st);
+// train.cu
+int psg_repack_weights(const float *w, const float *b, int cout, int cin, int kpad, int npad, int nwf, int nwb, float *wf,
+                       float *wb, float *wf_c, float *wb_c, float *bias, float comp, cudaStream_t st);
 // gemm_simt.cu / gemm_tc.cu
 int psg_gemm_simt(const PsgGemmArgs &g, cudaStream_t st);
 int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st);

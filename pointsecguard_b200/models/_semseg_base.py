@@ -84,7 +84,8 @@ class SemSegBase(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("pointsecguard_b200 models run on CUDA devices only; there is no CPU fallback")
         if self.training:
-            raise RuntimeError("pointsecguard_b200 implements the eval-mode (attack) path only; call model.eval()")
+            raise RuntimeError("the folded-BatchNorm engine is the eval-mode (attack) path; train mode runs through "
+                               "pointsecguard_b200.train (model.train()(x) or train.Trainer)")
         key = self._param_key(device)
         if self._engine is None or key != self._engine_key:
             self._engine = Engine(self.describe(), device, self.mlp_mode)
@@ -160,6 +161,12 @@ class SemSegBase(nn.Module):
     def forward(self, xyz):
         if xyz.dim() != 3 or xyz.shape[1] != 9:
             raise ValueError(f"expected [B, 9, N] input, got {tuple(xyz.shape)}")
+        if self.training:
+            # train mode (train_semseg.py:168-169): batch-statistics BatchNorm, dropout, gradients to the parameters
+            if not xyz.is_cuda:
+                raise RuntimeError("pointsecguard_b200 models run on CUDA devices only; there is no CPU fallback")
+            from pointsecguard_b200 import train as _train
+            return _train.train_forward(self, xyz)
         eng = self.engine(xyz.device)
         eng.bind(xyz.shape[0], xyz.shape[2], 1)
         starts = eng.draw_starts(1)

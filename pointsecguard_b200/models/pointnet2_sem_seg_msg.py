@@ -27,5 +27,9 @@ class get_model(SemSegBase):
 
 
 class get_loss(nn.Module):
+    """pointnet2_sem_seg_msg.py:44-50: weighted NLL = F.nll_loss(pred, target, weight=weight), as its own deterministic kernel pair
+    (csrc/train.cu: ordered double-precision reduction forward, one elementwise kernel backward)."""
+
     def forward(self, pred, target, trans_feat, weight):
-        return F.nll_loss(pred, target, weight=weight)
+        from pointsecguard_b200.train import nll_loss
+        return nll_loss(pred, target, weight)

@@ -40,16 +40,7 @@ def _nb_loop(atk, images, labels, target, mask):
     eng = atk._engine(images)
     dev = images.device
     B, C, N = images.shape
-    adv = images.detach().clone(memory_format=torch.contiguous_format)
-    ori = images.detach()[:, 3:6].contiguous()
     src = images.detach()
-    lab = atk._labels_i32(labels, dev) if target < 0 else None
-    msk = atk._mask_u8(mask, B, N, dev) if mask is not None else None
-    if msk is not None and B > 1 and getattr(mask, "ndim", 2) == 1:
-        # target.py:26,36 with a batch: the cost reads outputs[0] only, so the gradient of every other block is zero and
-        # sign(0) = 0 leaves it where it is -- the reference attacks block 0 alone.  A [B,N] mask attacks every block.
-        msk = msk.clone()
-        msk[1:] = 0
     # nontarget.py:34: sum-CE / N;  target.py:38: mean CE over the B*N points
     scale = 1.0 / N if target < 0 else 1.0 / (B * N)
     # Blocks are independent in every op of the path: split the batch into sub-batches, one engine and
@@ -76,6 +67,7 @@ def _nb_loop(atk, images, labels, target, mask):
         e.bind(p.size, N, chunk)
         e.set_input(p.slice(src))
     sizes = [N] + eng.npoints[:3]
+    adv = ori = lab = msk = None
     try:
         done = 0
         while done < atk.iters:
@@ -83,11 +75,33 @@ def _nb_loop(atk, images, labels, target, mask):
             starts = D.draw_starts(sizes, t, whole)                       # int32 [4, t, B]
             for e, p in zip(engs, parts):
                 e.geometry(p.slice(starts.permute(2, 0, 1)).permute(1, 2, 0).contiguous())
+            if adv is None:
+                # the loop's own tensors are made AFTER the first geometry pass is enqueued: their host work (label / mask
+                # conversion and upload, clones) then runs while the GPU computes FPS / ball query / 3-NN instead of before it
+                adv = images.detach().clone(memory_format=torch.contiguous_format)
+                ori = images.detach()[:, 3:6].contiguous()
+                lab = atk._labels_i32(labels, dev) if target < 0 else None
+                msk = atk._mask_u8(mask, B, N, dev) if mask is not None else None
+                if msk is not None and B > 1 and getattr(mask, "ndim", 2) == 1:
+                    # target.py:26,36 with a batch: the cost reads outputs[0] only, so the gradient of every other block is
+                    # zero and sign(0) = 0 leaves it where it is -- the reference attacks block 0 alone.  A [B,N] mask
+                    # attacks every block.
+                    msk = msk.clone()
+                    msk[1:] = 0
+                if nsub > 1:
+                    # side streams read these tensors: order them after their creation on the current stream
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    for st_ in streams:
+                        if st_ is not None:
+                            st_.wait_event(ready)
             for i in range(t):
                 for e, p in zip(engs, parts):
                     e.nb_attack(p.slice(adv), p.slice(ori), p.slice(msk) if msk is not None else None,
                                 p.slice(lab) if lab is not None else None, target, 1, i, atk.alpha, atk.eps, scale)
             done += t
+        if adv is None:                                                    # iters == 0
+            adv = images.detach().clone(memory_format=torch.contiguous_format)
     finally:
         for e, st_ in zip(engs, streams):
             if st_ is not None:

@@ -72,9 +72,11 @@ def _replay_last_step(make_attack, xd, labels_np, g, alpha, iters, sel=None):
     """One iteration from the golden trajectory's state before its last iteration, with the FPS draws of that forward."""
     from pointsecguard_b200 import distributed as D
     B = xd.shape[0]
-    prev = torch.from_numpy(g["prev"].astype(np.float32)).cuda()
+    code = torch.from_numpy(g["prev"].astype(np.int16)).cuda()              # int8 code: -128 / 127 = clipped to 0 / 1
+    col = xd[:, 3:6] + code.float() * alpha
+    col = torch.where(code == -128, torch.zeros_like(col), torch.where(code == 127, torch.ones_like(col), col))
     x2 = xd.clone()
-    x2[:, 3:6] = torch.clamp(xd[:, 3:6] + prev * alpha, 0.0, 1.0)
+    x2[:, 3:6] = col
     torch.manual_seed(0)
     D.draw_starts(LEVELS, iters - 1, D.Shard(B, 0, B))        # the draws of the first iters-1 forwards
     adv = make_attack(1)(x2, labels_np)

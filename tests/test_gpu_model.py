@@ -82,10 +82,10 @@ def test_backward_needs_latest_forward():
         logp.sum().backward()
 
 
-def test_train_mode_and_cpu_are_refused():
+def test_cpu_tensors_are_refused_in_both_modes():
     m = _model("ssg")
     with pytest.raises(RuntimeError):
-        m.train()(syn.make_blocks(1, 1024, 0).cuda())
+        m.train()(syn.make_blocks(1, 1024, 0))
     with pytest.raises(RuntimeError):
         m.eval()(syn.make_blocks(1, 1024, 0))
 

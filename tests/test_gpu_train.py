@@ -1,0 +1,140 @@
+"""GPU parity of the TRAINING step against golden vectors made by executing the unmodified reference
+(reference get_model.train() + get_loss + torch.optim.Adam, two steps, B=2 x 1024 painted blocks; oracle/make_golden_train.py).
+
+Stated tolerances (fp32 mode): loss rtol 2e-5; log-probabilities rtol 1e-3 / atol 2e-4; gradients of the stored tensors within
+2e-3 of their largest element; per-tensor sum |grad| within 2e-3 relative (tensors whose gradient is rounding noise -- conv
+biases in front of a BatchNorm, whose true gradient is zero -- are excluded); parameters after two Adam steps: >= 99 % of the
+elements within 1e-5 (Adam's first steps are sign-like, lr * g / (|g| + eps): an element whose gradient is rounding noise moves
+by +-lr on either side), running statistics rtol 1e-4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pointsecguard_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+CLASS_WEIGHTS = [1.0, 1.2, 0.8, 1.5, 1.0, 0.7, 1.3, 1.0, 0.9, 1.1, 1.4, 0.6, 1.0]     # oracle/make_golden_train.py
+
+
+def _model(arch):
+    if arch == "ssg":
+        from pointsecguard_b200.models.pointnet2_sem_seg import get_model, get_loss
+    else:
+        from pointsecguard_b200.models.pointnet2_sem_seg_msg import get_model, get_loss
+    m = get_model(13)
+    m.load_state_dict(syn.make_state_dict(arch, init="he"))
+    return m.cuda(), get_loss()
+
+
+def _draws(B, N):
+    """The CPU-generator draws of one reference train-mode forward, in its order: four FPS starts, then the dropout mask."""
+    starts = [torch.randint(0, n, (B,), dtype=torch.long) for n in (N, 1024, 256, 64)]
+    keep = torch.empty(B, 128, N).bernoulli_(0.5)
+    return starts, keep
+
+
+def _noise_tensor(name):
+    """conv biases followed by a BatchNorm: the true gradient is zero, both sides hold rounding noise"""
+    return name.endswith(".bias") and ("mlp_convs" in name or "conv_blocks" in name or name == "conv1.bias")
+
+
+@pytest.mark.parametrize("arch", ["ssg", "msg"])
+def test_trainer_matches_reference_training_steps(golden_dir, arch):
+    from pointsecguard_b200.train import Trainer
+    g = dict(np.load(os.path.join(golden_dir, f"train_{arch}.npz")))
+    m, _ = _model(arch)
+    tr = Trainer(m, lr=1e-3, weight_decay=1e-4)
+    names = {p: n for n, p in m.named_parameters()}
+    pn = [str(k) for k in g["pnames"]]
+    byname = dict(m.named_parameters())
+    w = torch.tensor(CLASS_WEIGHTS)
+    torch.manual_seed(11)
+    for s in range(2):
+        x, y = syn.make_painted_blocks(2, 1024, 50 + s)
+        starts, keep = _draws(2, 1024)
+        loss, logp = tr.loss_and_grads(x.cuda(), y.cuda(), w.cuda(), dropout_mask=keep, starts=starts)
+        ref_loss = float(g[f"loss{s}"])
+        print(f"{arch} step {s}: loss {loss.item():.7f} (reference {ref_loss:.7f})")
+        assert abs(loss.item() - ref_loss) < 2e-5 * abs(ref_loss)
+        np.testing.assert_allclose(logp.cpu().numpy(), g[f"logp{s}"], rtol=1e-3, atol=2e-4)
+        ga = np.array([tr.grad_of(byname[k]).double().abs().sum().item() for k in pn])
+        keepm = np.array([not _noise_tensor(k) for k in pn])
+        rel = np.abs(ga - g[f"gradabs{s}"]) / np.maximum(g[f"gradabs{s}"], 1e-12)
+        print(f"    sum|grad| worst relative deviation {rel[keepm].max():.2e} ({pn[int(np.argmax(np.where(keepm, rel, 0)))]})")
+        assert rel[keepm].max() < 2e-3
+        if s == 0:
+            for k in g:
+                if k.startswith("grad0/"):
+                    ref = g[k]
+                    mine = tr.grad_of(byname[k[6:]]).cpu().numpy()
+                    assert np.abs(mine - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-9, k
+        tr.apply_adam()
+    assert np.array_equal(torch.get_rng_state().numpy()[:64], g["rng_after"])       # the draws were the reference's
+    sd = m.state_dict()
+    for k in g:
+        if not k.startswith("final/"):
+            continue
+        name, ref, mine = k[6:], g[k], sd[k[6:]].cpu().numpy()
+        if "running_" in name:
+            np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-6)
+        elif not _noise_tensor(name):
+            frac = (np.abs(mine - ref) <= 1e-5).mean()
+            print(f"    {name}: within 1e-5 after two Adam steps: {frac:.4f}")
+            assert frac >= 0.99, (name, frac)
+    assert int(sd["bn1.num_batches_tracked"]) == 2
+
+
+def test_reference_style_training_loop():
+    """train_semseg.py:164-179 verbatim on the drop-in classes: optimizer.zero_grad(); classifier.train(); forward;
+    criterion; loss.backward(); optimizer.step() -- equals the Trainer's fused step."""
+    from pointsecguard_b200.train import Trainer
+    w = torch.tensor(CLASS_WEIGHTS).cuda()
+    x, y = syn.make_painted_blocks(2, 1024, 60)
+    torch.manual_seed(3)
+    starts, keep = _draws(2, 1024)
+
+    ma, criterion = _model("ssg")
+    opt = torch.optim.Adam(ma.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-08, weight_decay=1e-4)
+    opt.zero_grad()
+    ma = ma.train()
+    ma._dropout_mask, ma._fps_starts = keep.cuda(), starts
+    seg_pred, trans_feat = ma(x.cuda())
+    loss = criterion(seg_pred.contiguous().view(-1, 13), y.cuda().view(-1), trans_feat, w)
+    loss.backward()
+    opt.step()
+
+    mb, _ = _model("ssg")
+    tr = Trainer(mb, lr=1e-3, weight_decay=1e-4)
+    loss_b, _ = tr.step(x.cuda(), y.cuda(), w, dropout_mask=keep, starts=starts)
+    assert abs(loss.item() - loss_b.item()) < 1e-6
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        if not _noise_tensor(n):
+            assert (pa - pb).abs().max().item() < 2e-6, n
+    # eval mode afterwards uses the updated weights and running statistics
+    ma.eval()
+    ma._dropout_mask = ma._fps_starts = None
+    torch.manual_seed(0)
+    lp, _ = ma(x.cuda())
+    assert torch.isfinite(lp).all()
+
+
+def test_training_learns_on_painted_blocks():
+    """A few dozen steps from the random initialisation: the loss falls and the accuracy rises (the same schedule that
+    oracle/make_checkpoint.py runs on the CPU for 300 steps)."""
+    from pointsecguard_b200.train import Trainer
+    m, _ = _model("ssg")
+    tr = Trainer(m, lr=1e-3, weight_decay=1e-4)
+    torch.manual_seed(4321)
+    first = last = None
+    for step in range(40):
+        x, y = syn.make_painted_blocks(4, 2048, 1000 + step)
+        loss, logp = tr.step(x.cuda(), y.cuda())
+        if step == 0:
+            first = loss.item()
+        last = loss.item()
+        acc = (logp.argmax(2).cpu() == y).float().mean().item()
+    print(f"loss {first:.3f} -> {last:.3f}, train accuracy at step 39: {acc:.3f}")
+    assert last < 0.5 * first and acc > 0.5
