@@ -331,6 +331,10 @@ class TrainEngine:
             sr = c["sa"][l - 1]
             S, R, D = sr["S"], sr["R"], sr["D"]
             dsrc = dlevel[l]
+            if getattr(self, "debug", None) is not None:          # tools/train_diag.py
+                tmp = TTensor(1, 16, dev)
+                tmp.buf, tmp.cpad, tmp.rows, tmp.rpad = dsrc.buf, dsrc.cpad, dsrc.rows, dsrc.rpad
+                self.debug[l] = tmp.to_channels_first(B, S, c["widths"][l], 0)
             for bi, br in enumerate(sr["branches"]):
                 K, cw = br["K"], br["cw"]
                 rows = B * S * K
@@ -339,7 +343,9 @@ class TrainEngine:
                                          br["arg"].data_ptr(), B * S, K, cw, dy.ptr, dy.wchunks, st)
                 dG = self._chain_backward(br["recs"], dy, grads, need_input_grad=(l > 1))
                 if l > 1:
-                    offs, perm = self._csr(br["idx"], B, S * K, R, pad_group=K)
+                    # every slot counts here: BatchNorm's backward makes the gradient rows of the padded slots (copies of
+                    # the first hit) non-zero, unlike in the eval-mode path where only arg-max rows carry gradient
+                    offs, perm = self._csr(br["idx"], B, S * K, R, pad_group=0)
                     tgt = dlevel[l - 1]
                     L.psg_segment_sum(dG.ptr, dG.wchunks, 0, S * K, 1, None, offs.data_ptr(), perm.data_ptr(), S * K, R, B, D,
                                       tgt.ptr, tgt.wchunks, 0, 1, st)

@@ -19,9 +19,11 @@ def main():
     sd = syn.load_checkpoint("ssg")
     g = np.load(os.path.join(REPO, "tests", "golden", "atsize_config1.npz"))
     x, labels = syn.make_painted_blocks(4, 4096, 0)
-    prev = torch.from_numpy(g["prev"].astype(np.float32))
+    code = torch.from_numpy(g["prev"].astype(np.int16))
+    col = x[:, 3:6] + code.float() * 0.05
+    col = torch.where(code == -128, torch.zeros_like(col), torch.where(code == 127, torch.ones_like(col), col))
     x2 = x.clone()
-    x2[:, 3:6] = torch.clamp(x[:, 3:6] + prev * 0.05, 0, 1)
+    x2[:, 3:6] = col
     m = get_model(13); m.load_state_dict(sd); m = m.cuda().eval()
     om = PO.OracleModel(sd, "ssg")
     for name, inp in (("clean", x), ("step9", x2)):
@@ -49,6 +51,13 @@ def main():
             print(f"{name} {mname}: max|dlogp| {dl:.2e} grad rel {rel:.2e}; ref zeros {z_o.mean():.4f} mine zeros {z_g.mean():.4f} "
                   f"zero-mismatch {(z_o != z_g).mean():.5f}; sign flips among nonzero {flips:.5f}; |g|<1e-6 max: {small.mean():.4f}; "
                   f"quantiles |g|/max {np.quantile(np.abs(go[nz]) / amax, [0.01, 0.05, 0.25, 0.5])}")
+            # the attack entry point on the same input and draws: one NB step = x + alpha * sign(g)
+            from pointsecguard_b200 import torchattacks
+            torch.manual_seed(3)
+            adv1 = torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=1)(inp.cuda(), labels.numpy().astype(np.float64))
+            sg_attack = np.rint(((adv1[:, 3:6] - inp.cuda()[:, 3:6]) / 0.05).cpu().numpy())
+            print(f"    attack step vs oracle sign: identical {(sg_attack == np.sign(go)).mean():.5f}; attack step vs autograd sign of the same mode: "
+                  f"{(sg_attack == np.sign(gg)).mean():.5f}; moved where oracle gradient is zero: {(sg_attack[z_o] != 0).mean():.5f}")
             bad = nz.copy(); bad[nz] = np.sign(gg[nz]) != np.sign(go[nz])
             if bad.any():
                 print("    flipped elements: median |g_ref|/max", np.median(np.abs(go[bad])) / amax, " median |g_mine - g_ref|/max", np.median(np.abs(gg[bad] - go[bad])) / amax)
