@@ -11,7 +11,7 @@ PY="${PYTHON:-python}"
 status=0
 for tool in memcheck racecheck synccheck; do
   log="$OUT/sanitize_$tool.log"
-  timeout 1500 compute-sanitizer --tool "$tool" --error-exitcode 9 --print-limit 20 \
+  timeout 700 compute-sanitizer --tool "$tool" --error-exitcode 9 --print-limit 20 \
       "$PY" tools/sanitize_workload.py > "$log" 2>&1
   rc=$?
   tail -n 3 "$log" | sed "s/^/[$tool] /"
