@@ -27,6 +27,8 @@ int g_psg_sm_cap = 0;
 // GEMM CTAs with a deep operand ring beat one cluster per tile (B = 16: fp3 as a tile program 1133 steps/s, per
 // layer 1153; psg_set_option "fp_min_tiles")
 static int g_fp_min_tiles = 48;
+// fused SA branches run on compacted neighbourhood rows (compact.cu); psg_set_option "sa_compact" 0 restores the padded layout
+static int g_sa_compact = 1;
 
 // ------------------------------------------------------------------------------------------------
 // per-kernel-family device timing (bench.py's live roofline measurement).  When enabled, every
@@ -276,6 +278,8 @@ struct Branch {
     bool streamed;         // ... or, for wide layers, as a tile program with streamed weights (chain_fused.cu)
     unsigned *m0, *m1;     // ReLU bits of layers 0 / 1 (fused path)
     int *csr_off, *csr_perm;   // [T*B][R+1], [T*B][S*K]
+    bool compactable;      // fused branch whose kernels can run on compacted rows (real ball-query hits only, compact.cu)
+    PsgCompact cp;
 };
 
 struct SaLevel {
@@ -327,6 +331,7 @@ struct psg_net {
     float *dxyz[5];        // [B][npts[l]][3]
     float *xyz_tmp;        // [B][N*3][3] coarse-side vectors of the interpolation backward
     bool head_fused;
+    bool compact_valid;    // the resident geometry carries compacted rows for the fused SA branches
     bool z_valid;          // logits of the last forward are materialised in Z
     struct { int kind, target; const float *dlogp; const int *labels; float scale, kappa; float *loss_rows;
              unsigned char *hit; bool set; } loss;
@@ -442,6 +447,7 @@ extern "C" int psg_set_option(const char *name, int value)
     if (!strcmp(name, "fp_min_tiles")) { g_fp_min_tiles = value; return PSG_OK; }
     if (!strcmp(name, "fp_slabs")) { psg_tile_set_fp_slabs(value != 0); return PSG_OK; }
     if (!strcmp(name, "sa_ng")) { psg_sa_force_ng(value); return PSG_OK; }
+    if (!strcmp(name, "sa_compact")) { g_sa_compact = value != 0; return PSG_OK; }
     if (!strcmp(name, "dbg")) { psg_tile_set_dbg(value); return PSG_OK; }
     if (!strcmp(name, "sm_cap")) { g_psg_sm_cap = value > 0 ? value : 0; return PSG_OK; }
     return PSG_EINVAL;
@@ -501,6 +507,13 @@ static size_t plan(psg_net *n, int B, int N, int T, char *base)
             if (Br.fused || Br.streamed) {
                 Br.m0 = bp.take<unsigned>(psg_sa_mask_words(rows, Br.mlp[0]->npad));
                 Br.m1 = bp.take<unsigned>(psg_sa_mask_words(rows, Br.mlp[1]->npad));
+            }
+            Br.compactable = Br.fused && psg_sa_compactable(Br.K, Br.gpad, Br.mlp[0]->npad, Br.mlp[1]->npad, Br.mlp[2]->npad);
+            memset(&Br.cp, 0, sizeof(Br.cp));
+            if (Br.compactable) {
+                char *cws = bp.take<char>(psg_sa_compact_bytes(P, T, S, Br.K));
+                if (cws) Br.cp = psg_sa_compact_carve(cws, P, T, S, Br.K);
+                Br.cp.cap = (long long)B * S * Br.K;
             }
             size_t s = (size_t)round_up_ll(rows, 128) * wmax;
             if (s > scratch) scratch = s;
@@ -629,8 +642,14 @@ extern "C" int psg_net_geometry(psg_net *n, const int32_t *starts, int T, psg_st
         } else
         PSG_RUN(PF_BALL, psg_ball_query_launch(cloud, stride, nclouds, P, R, n->xyz[l], S, L.nbr, L.radius, ns, L.br[0].ball,
                                       L.nbr > 1 ? L.br[1].ball : nullptr, st));
-        for (int b = 0; b < L.nbr; ++b)
+        for (int b = 0; b < L.nbr; ++b) {
             PSG_RUN(PF_CSR, psg_csr_build(L.br[b].ball, P, S * L.br[b].K, R, L.br[b].K, L.br[b].csr_off, L.br[b].csr_perm, n->csr_ws, st));
+            // compacted rows of the fused branches (skipped when the coordinates move: the geometric-gradient kernels
+            // read the padded [S][K] layout)
+            if (L.br[b].compactable && g_sa_compact && n->mode == 1 && !n->xyz_grad)
+                PSG_RUN(PF_CSR, psg_sa_compact_build(L.br[b].ball, L.br[b].csr_perm, T, B, S, L.br[b].K, L.br[b].cp, st));
+        }
+        n->compact_valid = g_sa_compact && n->mode == 1 && !n->xyz_grad;
     }
     for (int f = 0; f < 4; ++f) {
         FpLevel &F = n->fp[f];
@@ -694,6 +713,12 @@ static PsgSaFused sa_fused_desc(psg_net *n, int l, int b, int t)
     }
     f.m0 = Br.m0; f.m1 = Br.m1;
     f.out = tv(n->feats[l], n->wfeat[l], Br.col0); f.arg = Br.arg;
+    f.crow_src = f.crow_g = f.ntiles_dev = nullptr;
+    if (Br.compactable && n->compact_valid) {
+        f.crow_src = Br.cp.crow_src + (size_t)t * Br.cp.cap;
+        f.crow_g = Br.cp.crow_g + (size_t)t * Br.cp.cap;
+        f.ntiles_dev = Br.cp.ctiles + t;
+    }
     return f;
 }
 
@@ -878,6 +903,9 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
     if (!n || !n->bound || t < 0 || t >= n->T || t != n->last_t) return PSG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int B = n->B;
+    // the geometric-gradient kernels read the padded [S][K] gradient rows: the geometry must have been built with the
+    // coordinate gradient already switched on (psg_net_set_xyz_grad before psg_net_geometry)
+    if (n->xyz_grad && n->compact_valid) return PSG_EINVAL;
     if (n->xyz_grad)
         for (int l = 0; l <= 4; ++l)
             if (cudaMemsetAsync(n->dxyz[l], 0, (size_t)B * n->npts[l] * 3 * sizeof(float), st) != cudaSuccess) return PSG_ECUDA;
@@ -962,6 +990,10 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
                 PSG_RUN(PF_SA_BWD, Br.fused ? psg_sa_fused_bwd(f, dl, dg, gcols, n->Srm, rmo, st) : psg_sa_stream_bwd(f, dl, dg, gcols, n->Srm, rmo, st));
                 const size_t go = (size_t)t * B;
                 const int M = S * Br.K;
+                if (f.crow_src)      // compacted gradient rows: the permutation addresses them relative to the forward
+                    PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[0], Br.gpad), 0, 1, nullptr, Br.csr_off + go * (R + 1), Br.cp.cperm + go * M, M, R,
+                                       B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, n->Srm, Br.gpad, st));
+                else
                 PSG_RUN(PF_SEGSUM, psg_segsum(tv(n->S[0], Br.gpad), M, 1, nullptr, Br.csr_off + go * (R + 1), Br.csr_perm + go * M, M, R,
                                    B, D, tv(n->dfeat[l - 1], n->wfeat[l - 1]), (l > 1 || b > 0) ? 1 : 0, nullptr, n->Srm, Br.gpad, st));
                 if (n->xyz_grad)

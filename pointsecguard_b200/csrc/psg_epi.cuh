@@ -73,6 +73,58 @@ __device__ __forceinline__ void psg_pool_transposed(const float *y, float *scrat
     __syncwarp();
 }
 
+// Segmented variant for COMPACTED rows (compact.cu): the warp's 32 rows are four octets; `vm` bit o says octet o holds rows,
+// `sm` bit o that it starts a new neighbourhood whose centroid is gq[o]; a neighbourhood spans 1..4 consecutive octets of
+// the slice.  Same transposition, the scan emits (centroid, max, rank of the first max) at every segment end.  All control
+// flow depends on the warp-uniform masks only.
+template <int NC, class Emit>
+__device__ __forceinline__ void psg_pool_segmented(const float *y, float *scratch, int lane, const int (&gq)[4], unsigned sm,
+                                                   unsigned vm, Emit emit)
+{
+#pragma unroll
+    for (int c = 0; c < NC; ++c) scratch[c * 32 + (lane ^ ((c & 7) << 2))] = y[c];
+    __syncwarp();
+    if (lane < NC) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(scratch) + lane * 8;
+        float b = -1.f;
+        int bi = 0, g = -1, first = 0;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (!((vm >> o) & 1u)) continue;
+            if ((sm >> o) & 1u) {
+                if (g >= 0) emit(g, b, bi);
+                g = gq[o]; b = -1.f; bi = 0; first = 8 * o;
+            }
+#pragma unroll
+            for (int j = 2 * o; j < 2 * o + 2; ++j) {
+                const float4 q = s4[j ^ (lane & 7)];
+                const int r0 = 4 * j - first;
+                if (q.x > b) { b = q.x; bi = r0; }
+                if (q.y > b) { b = q.y; bi = r0 + 1; }
+                if (q.z > b) { b = q.z; bi = r0 + 2; }
+                if (q.w > b) { b = q.w; bi = r0 + 3; }
+            }
+        }
+        if (g >= 0) emit(g, b, bi);
+    }
+    __syncwarp();
+}
+
+// centroids of the four octets of a warp slice + the segment masks described above, from each lane's centroid (-1: empty row)
+__device__ __forceinline__ void psg_slice_segments(int g_lane, int (&gq)[4], unsigned &sm, unsigned &vm)
+{
+#pragma unroll
+    for (int o = 0; o < 4; ++o) gq[o] = __shfl_sync(0xffffffffu, g_lane, 8 * o);
+    sm = vm = 0;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        if (gq[o] >= 0) {
+            vm |= 1u << o;
+            if (o == 0 || gq[o] != gq[o - 1]) sm |= 1u << o;
+        }
+    }
+}
+
 // ---- arg-max scatter (backward of the neighbourhood max-pool) as a warp-cooperative refill ------------------
 // dY[(g, k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0 for `planes` 4-column chunks starting at chunk c0.
 // The K rows of a neighbourhood need the SAME three rows (dOut, out, arg) and differ only in the comparison with
@@ -80,6 +132,40 @@ __device__ __forceinline__ void psg_pool_transposed(const float *y, float *scrat
 // per-warp staging area and every lane then reads the staged chunks back as shared-memory broadcasts -- instead of
 // 3 global requests per chunk per lane (the scatter was ~40 % of a backward tile's latency chain).
 // stage_d / stage_a: 32 float4 + 32 uchar4 per warp.  put(chunk, value) writes the A operand.
+// `rank` = the row's position inside its neighbourhood (lane % K in the padded layout; with compacted rows K = 8 is the
+// cooperating octet and the rank runs over the 1..4 octets of the neighbourhood).
+template <int K, class Put>
+__device__ __forceinline__ void psg_scatter_warp_rank(const TView &dout, const TView &outv, const unsigned char *arg, int argC,
+                                                      long long g, bool valid, int lane, int rank, int c0, int planes,
+                                                      float4 *stage_d, uchar4 *stage_a, Put put)
+{
+    const int kk = lane % K, gl = lane / K;
+    for (int cb = 0; cb < planes; cb += K) {
+        const int c = cb + kk;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        uchar4 am = make_uchar4(255, 255, 255, 255);
+        if (valid && c < planes) {
+            d = tv_ld(dout, g, c0 + c);
+            const float4 o = tv_ld(outv, g, c0 + c);
+            am = *reinterpret_cast<const uchar4 *>(arg + g * argC + 4 * (c0 + c));
+            d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f; d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+        }
+        stage_d[lane] = d; stage_a[lane] = am;
+        __syncwarp();
+        const int n = planes - cb < K ? planes - cb : K;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const float4 dd = stage_d[gl * K + j];
+            const uchar4 aa = stage_a[gl * K + j];
+            float4 q;
+            q.x = aa.x == rank ? dd.x : 0.f; q.y = aa.y == rank ? dd.y : 0.f;
+            q.z = aa.z == rank ? dd.z : 0.f; q.w = aa.w == rank ? dd.w : 0.f;
+            put(cb + j, q);
+        }
+        __syncwarp();
+    }
+}
+
 template <int K, class Put>
 __device__ __forceinline__ void psg_scatter_warp(const TView &dout, const TView &outv, const unsigned char *arg, int argC,
                                                  long long g, bool valid, int lane, int c0, int planes, float4 *stage_d,

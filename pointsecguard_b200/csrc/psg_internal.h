@@ -78,6 +78,23 @@ int psg_repack_weights(const float *w, const float *b, int cout, int cin, int kp
 int psg_gemm_simt(const PsgGemmArgs &g, cudaStream_t st);
 int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st);
 // sa_fused.cu: one set-abstraction branch (gather -> 3 layers -> neighbourhood max) per kernel
+// compact.cu: compacted neighbourhood rows (real ball-query hits only) of one fused SA branch
+struct PsgCompact {
+    int *cnt;        // [P*S] real hits of each neighbourhood
+    int *slot;       // [P*S] octet position of the neighbourhood inside its problem's compact rows
+    int *nsl;        // [P]   32-row slices used by the problem
+    int *base;       // [P]   first compact row of the problem inside its forward's row space
+    int *ctiles;     // [T]   128-row tiles of each forward
+    int *crow_src;   // [T][B*S*K] source point of each compact row (-1: empty)
+    int *crow_g;     // [T][B*S*K] centroid (b*S + s) of each compact row (-1: empty)
+    int *cperm;      // [P][S*K] gather-backward CSR permutation rewritten to compact rows (relative to the forward)
+    long long cap;
+};
+size_t psg_sa_compact_bytes(long long P, int T, int S, int K);
+PsgCompact psg_sa_compact_carve(void *ws, long long P, int T, int S, int K);
+int psg_sa_compact_build(const int *ball, const int *csr_perm, int T, int B, int S, int K, PsgCompact c, cudaStream_t st);
+bool psg_sa_compactable(int K, int gpad, int n0, int n1, int n2);
+
 struct PsgSaFused {
     int K;
     TView feats; int D; const float *xyz; long long cloud_stride; int nclouds; int Nsrc;
@@ -87,6 +104,9 @@ struct PsgSaFused {
     const float *wb[3]; int nwb[3];
     unsigned *m0, *m1;             // ReLU bits of layers 0 / 1, psg_sa_mask_words(rows, n) words each
     TView out; unsigned char *arg; // pooled rows [groups][n2 slice of the level's features], arg-max [groups][n2]
+    // compacted rows (compact.cu), all null for the padded [S][K] layout: per compact row its source point / centroid, and
+    // the forward's tile count in device memory (only the device knows how many real hits there are)
+    const int *crow_src, *crow_g, *ntiles_dev;
 };
 bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2);
 void psg_sa_force_ng(int ng);      // A/B switch: tiles in flight per CTA of the fused SA kernels (0 = automatic)

@@ -73,6 +73,7 @@ struct SaFwdArgs {
     TView out; unsigned char *arg;
     int ntiles;
     long long *trace;
+    const int *crow_src, *crow_g, *ntiles_dev;      // compacted rows (compact.cu); CP kernels only
 };
 
 // accumulator -> bias + ReLU -> next A operand in shared memory (+ one ReLU bit per element)
@@ -100,7 +101,9 @@ __device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n,
     }
 }
 
-template <int K, int NG>
+// CP: the rows are the compacted real hits (compact.cu) -- source point and centroid come from crow_src / crow_g, the tile
+// count from device memory, and the pool scans variable-length segments of the warp's four octets.
+template <int K, int NG, bool CP>
 __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_fwd_kernel(SaFwdArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     if (gtr) gtr[2] = gtimer();
     const uint32_t tmem = tmem_slot;
     const int tstride = gridDim.x * NG;
+    const int ntiles = CP ? __ldg(a.ntiles_dev) : a.ntiles;
 
     if (warp >= NG * 4) {
         if (lane == 0) {
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             const uint32_t b_in = tc::smem_u32(&bar_in[g]), b_acc = tc::smem_u32(&bar_acc[g]);
             const uint32_t sA = sG + g * szG, tm = tmem + g * gcols;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x * NG + g; tile < a.ntiles; tile += tstride) {
+            for (int tile = blockIdx.x * NG + g; tile < ntiles; tile += tstride) {
 #pragma unroll 1
                 for (int layer = 0; layer < 3; ++layer) {
                     tc::mbar_spin(b_in, ph); ph ^= 1u;
@@ -189,16 +193,18 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
 #define SA_STAMP() do { if (tr && tn < 510) tr[tn++] = clock64(); } while (0)
         SA_STAMP();
         int tile = blockIdx.x * NG + grp;
-        int src_next = (tile < a.ntiles && (long long)tile * 128 + r < a.rows) ? a.idx[(long long)tile * 128 + r] : 0;
-        for (; tile < a.ntiles; tile += tstride) {
+        int src_next = CP ? (tile < ntiles ? a.crow_src[(long long)tile * 128 + r] : -1)
+                          : ((tile < ntiles && (long long)tile * 128 + r < a.rows) ? a.idx[(long long)tile * 128 + r] : 0);
+        for (; tile < ntiles; tile += tstride) {
             const long long row = (long long)tile * 128 + r;
-            const bool valid = row < a.rows;
+            const bool valid = CP ? src_next >= 0 : row < a.rows;
+            const int cg = CP ? (valid ? a.crow_g[row] : -1) : 0;         // centroid of a compacted row
             // ---- gather: [ feats[src] (D) | xyz[src] - centre (3) | 0 ] -> A operand ----
             {
                 const long long rr = valid ? row : 0;
-                const long long ps = rr / K;
+                const long long ps = CP ? (valid ? cg : 0) : rr / K;
                 const int p = (int)(ps / a.S);
-                const int src = src_next;
+                const int src = valid ? src_next : 0;
                 const int cloud = p % a.nclouds;
                 const long long srow = (long long)cloud * a.Nsrc + src;
                 const int D = a.D;
@@ -225,7 +231,8 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
                 }
                 // prefetch the next tile's neighbour index: takes one L2 round trip off its gather
                 const long long nrow = row + (long long)tstride * 128;
-                src_next = (nrow < a.rows) ? a.idx[nrow] : 0;
+                if (CP) src_next = (tile + tstride < ntiles) ? a.crow_src[nrow] : -1;
+                else src_next = (nrow < a.rows) ? a.idx[nrow] : 0;
             }
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
@@ -250,7 +257,36 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
             SA_STAMP();
             const long long g = row / K;
-            if (szG >= 16384) {
+            if (CP) {
+                // compacted rows: the warp's four octets form 1..4 neighbourhoods of 8..32 rows (compact.cu)
+                float *scratch = reinterpret_cast<float *>(pA + (size_t)wq * 4096);
+                int gq[4];
+                unsigned sm, vm;
+                psg_slice_segments(cg, gq, sm, vm);
+                int c = 0;
+                for (; c + 32 <= a.n2; c += 32) {
+                    float v[32];
+                    tc::tmem_ld32(tl + (uint32_t)c, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + sbias[2][c + i], 0.f);
+                    const int col = c + lane;
+                    psg_pool_segmented<32>(v, scratch, lane, gq, sm, vm, [&](int gg, float best, int arg) {
+                        a.out.base[tv_off(a.out, gg, col >> 2) + (col & 3)] = best;
+                        a.arg[(long long)gg * a.n2 + col] = (unsigned char)arg;
+                    });
+                }
+                if (c < a.n2) {
+                    float v[16];
+                    tc::tmem_ld16(tl + (uint32_t)c, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + sbias[2][c + i], 0.f);
+                    const int col = c + lane;
+                    psg_pool_segmented<16>(v, scratch, lane, gq, sm, vm, [&](int gg, float best, int arg) {
+                        a.out.base[tv_off(a.out, gg, col >> 2) + (col & 3)] = best;
+                        a.arg[(long long)gg * a.n2 + col] = (unsigned char)arg;
+                    });
+                }
+            } else if (szG >= 16384) {
                 // transposed pool: the tile's operand buffer is dead once MMA 2 has completed (every warp of
                 // the tile waited on the same barrier), so warp wq borrows 4 KB of it as scratch
                 float *scratch = reinterpret_cast<float *>(pA + (size_t)wq * 4096);
@@ -314,7 +350,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             // tile's gather writes this warp's rows of EVERY plane: a warp that ran ahead would scribble over the scratch
             // of a sibling still pooling (seen as a rare run-to-run difference of a 50-step attack).  The four warps of
             // a tile meet here first (named barrier per tile in flight; they meet again at the next MMA hand-off anyway).
-            if (szG >= 16384) asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+            if (CP || szG >= 16384) asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
         }
     }
     tc::fence_before_sync();
@@ -335,6 +371,7 @@ struct SaBwdArgs {
     int gpad, n0, n1, n2;
     int ntiles;
     long long *trace;
+    const int *crow_g, *ntiles_dev;                 // compacted rows (compact.cu); CP kernels only
 };
 
 // accumulator -> ReLU-bit mask -> next A operand in shared memory
@@ -362,7 +399,7 @@ __device__ __forceinline__ void epilogue_mask_to_smem(uint32_t tmem_lane, int n,
     }
 }
 
-template <int K, int NG>
+template <int K, int NG, bool CP>
 __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_bwd_kernel(SaBwdArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -407,6 +444,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     tc::pdl_wait();                   // ... and ours overlapped our predecessor's: wait for its results now
     const uint32_t tmem = tmem_slot;
     const int tstride = gridDim.x * NG;
+    const int ntiles = CP ? __ldg(a.ntiles_dev) : a.ntiles;
 
     if (warp >= NG * 4) {
         if (lane == 0) {
@@ -415,7 +453,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             const uint32_t b_in = tc::smem_u32(&bar_in[g]), b_acc = tc::smem_u32(&bar_acc[g]);
             const uint32_t sD = sG + g * szG, tm = tmem + g * gcols;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x * NG + g; tile < a.ntiles; tile += tstride) {
+            for (int tile = blockIdx.x * NG + g; tile < ntiles; tile += tstride) {
 #pragma unroll 1
                 for (int L = 0; L < nslab + 2; ++L) {
                     tc::mbar_spin(b_in, ph); ph ^= 1u;
@@ -439,13 +477,30 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
         long long *tr = (a.trace && blockIdx.x == 0 && r == 0 && grp < 2) ? a.trace + grp * 512 : nullptr;
         int tn = 0;
         SA_STAMP();
-        for (int tile = blockIdx.x * NG + grp; tile < a.ntiles; tile += tstride) {
+        for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += tstride) {
             const long long row = (long long)tile * 128 + r;
-            const bool valid = row < a.rows;
-            const long long g = (valid ? row : 0) / K;
+            const int cg = CP ? a.crow_g[row] : 0;
+            const bool valid = CP ? cg >= 0 : row < a.rows;
+            const long long g = CP ? (valid ? cg : 0) : (valid ? row : 0) / K;
+            int rank = lane % K;
+            if (CP) {
+                // rank inside the neighbourhood: rows since the first octet that carries the same centroid
+                int gq[4];
+                unsigned sm, vm;
+                psg_slice_segments(cg, gq, sm, vm);
+                int f = lane >> 3;
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+                    if (f > 0 && !((sm >> f) & 1u)) --f;
+                rank = lane - 8 * f;
+            }
             // ---- dY2[(g,k)][c] = (k == arg[g][c] && out[g][c] > 0) ? dOut[g][c] : 0, one slab of columns at a
             // time: the operand buffer stays small (more tiles in flight), the MMA accumulates over slabs ----
             for (int sl = 0; sl < nslab; ++sl) {
+                if (CP)
+                    psg_scatter_warp_rank<8>(a.dout, a.outv, a.arg, a.n2, g, valid, lane, rank, sl * (a.slab / 4), a.slab / 4,
+                                             stg_d[warp], stg_a[warp], [&](int c, float4 q) { *plane_ptr(pD2, c, r) = q; });
+                else
                 psg_scatter_warp<K>(a.dout, a.outv, a.arg, a.n2, g, valid, lane, sl * (a.slab / 4), a.slab / 4,
                                     stg_d[warp], stg_a[warp], [&](int c, float4 q) { *plane_ptr(pD2, c, r) = q; });
                 tc::fence_before_sync();
@@ -562,11 +617,20 @@ int num_sms()
 
 template <int K> void (*fwd_kern(int ng))(SaFwdArgs)
 {
-    return ng == 1 ? sa_fwd_kernel<K, 1> : ng == 2 ? sa_fwd_kernel<K, 2> : ng == 3 ? sa_fwd_kernel<K, 3> : sa_fwd_kernel<K, 4>;
+    return ng == 1 ? sa_fwd_kernel<K, 1, false> : ng == 2 ? sa_fwd_kernel<K, 2, false> : ng == 3 ? sa_fwd_kernel<K, 3, false> : sa_fwd_kernel<K, 4, false>;
 }
 template <int K> void (*bwd_kern(int ng))(SaBwdArgs)
 {
-    return ng == 1 ? sa_bwd_kernel<K, 1> : ng == 2 ? sa_bwd_kernel<K, 2> : ng == 3 ? sa_bwd_kernel<K, 3> : sa_bwd_kernel<K, 4>;
+    return ng == 1 ? sa_bwd_kernel<K, 1, false> : ng == 2 ? sa_bwd_kernel<K, 2, false> : ng == 3 ? sa_bwd_kernel<K, 3, false> : sa_bwd_kernel<K, 4, false>;
+}
+// compacted-row variants (the template's K is unused by them: the octet structure replaces it)
+void (*fwd_kern_cp(int ng))(SaFwdArgs)
+{
+    return ng == 1 ? sa_fwd_kernel<32, 1, true> : ng == 2 ? sa_fwd_kernel<32, 2, true> : ng == 3 ? sa_fwd_kernel<32, 3, true> : sa_fwd_kernel<32, 4, true>;
+}
+void (*bwd_kern_cp(int ng))(SaBwdArgs)
+{
+    return ng == 1 ? sa_bwd_kernel<32, 1, true> : ng == 2 ? sa_bwd_kernel<32, 2, true> : ng == 3 ? sa_bwd_kernel<32, 3, true> : sa_bwd_kernel<32, 4, true>;
 }
 
 // tiles in flight per SM = NG (per CTA, sharing the resident weights) x CTAs per SM: take the combination
@@ -624,6 +688,13 @@ bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2)
     return fwd_smem(gpad, n0, n1, n2, 1) <= kSmemPerCtaMax && bwd_smem(gpad, n0, n1, n2, 1) <= kSmemPerCtaMax;
 }
 
+// the segmented pool of the compacted-row kernels borrows 4 KB of the tile's operand buffer per warp
+bool psg_sa_compactable(int K, int gpad, int n0, int n1, int n2)
+{
+    if (!psg_sa_fusable(K, gpad, n0, n1, n2)) return false;
+    return max3(gpad, n0, n1) * 512 >= 16384;
+}
+
 size_t psg_sa_mask_words(long long rows, int n)
 {
     return (size_t)((rows + 127) / 128) * ((n + 31) / 32) * 128;
@@ -640,15 +711,22 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     a.m0 = f.m0; a.m1 = f.m1; a.out = f.out; a.arg = f.arg;
     a.ntiles = (int)((f.rows + 127) / 128);
     a.trace = psg_tile_trace_slot();
+    a.crow_src = f.crow_src; a.crow_g = f.crow_g; a.ntiles_dev = f.ntiles_dev;
+    const bool cp = f.crow_src && f.crow_g && f.ntiles_dev;
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.n2 ? a.n0 : a.n2) : (a.n1 > a.n2 ? a.n1 : a.n2));
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
+    if (cp && !psg_sa_compactable(f.K, a.gpad, a.n0, a.n1, a.n2)) return PSG_EUNSUPPORTED;
     auto smem_of = [&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g); };
-    const Pick pk = f.K == 32 ? cached_pick(0, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern<32>, smem_of, gc)
+    const Pick pk = cp ? cached_pick(2, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern_cp, smem_of, gc)
+                  : f.K == 32 ? cached_pick(0, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern<32>, smem_of, gc)
                               : cached_pick(0, 16, a.gpad, a.n0, a.n1, a.n2, fwd_kern<16>, smem_of, gc);
     if (pk.ng < 1 || pk.occ < 1 || num_sms() < 1) return PSG_EUNSUPPORTED;
-    const int want = (a.ntiles + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
+    // compacted rows: only the device knows the tile count; one third of the padded count covers S3DIS densities, and
+    // the persistent CTAs stride over whatever there is
+    const int tiles_for_grid = cp ? (a.ntiles + 2) / 3 : a.ntiles;
+    const int want = (tiles_for_grid + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
     const int grid = want < cap ? want : cap;
-    auto kern = f.K == 32 ? fwd_kern<32>(pk.ng) : fwd_kern<16>(pk.ng);
+    auto kern = cp ? fwd_kern_cp(pk.ng) : f.K == 32 ? fwd_kern<32>(pk.ng) : fwd_kern<16>(pk.ng);
     { cudaError_t e__ = psg_launch_pdl(kern, dim3(grid), dim3(pk.ng * 160), smem_of(pk.ng), st, 1, a);
       if (e__ != cudaSuccess) { fprintf(stderr, "sa launch: %s (ng %d occ %d grid %d smem %zu)\n", cudaGetErrorString(e__), pk.ng, pk.occ, grid, smem_of(pk.ng)); return PSG_ECUDA; } }
     PSG_LAUNCH_CHECK();
@@ -666,15 +744,19 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
     a.trace = psg_tile_trace_slot();
+    a.crow_g = f.crow_g; a.ntiles_dev = f.ntiles_dev;
+    const bool cp = f.crow_src && f.crow_g && f.ntiles_dev;
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.gpad ? a.n0 : a.gpad) : (a.n1 > a.gpad ? a.n1 : a.gpad));
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
     auto smem_of = [&](int g) { return bwd_smem(a.gpad, a.n0, a.n1, a.n2, g); };
-    const Pick pk = f.K == 32 ? cached_pick(1, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern<32>, smem_of, gc)
+    const Pick pk = cp ? cached_pick(3, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern_cp, smem_of, gc)
+                  : f.K == 32 ? cached_pick(1, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern<32>, smem_of, gc)
                               : cached_pick(1, 16, a.gpad, a.n0, a.n1, a.n2, bwd_kern<16>, smem_of, gc);
     if (pk.ng < 1 || pk.occ < 1 || num_sms() < 1) return PSG_EUNSUPPORTED;
-    const int want = (a.ntiles + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
+    const int tiles_for_grid = cp ? (a.ntiles + 2) / 3 : a.ntiles;
+    const int want = (tiles_for_grid + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
     const int grid = want < cap ? want : cap;
-    auto kern = f.K == 32 ? bwd_kern<32>(pk.ng) : bwd_kern<16>(pk.ng);
+    auto kern = cp ? bwd_kern_cp(pk.ng) : f.K == 32 ? bwd_kern<32>(pk.ng) : bwd_kern<16>(pk.ng);
     { cudaError_t e__ = psg_launch_pdl(kern, dim3(grid), dim3(pk.ng * 160), smem_of(pk.ng), st, 1, a);
       if (e__ != cudaSuccess) { fprintf(stderr, "sa launch: %s (ng %d occ %d grid %d smem %zu)\n", cudaGetErrorString(e__), pk.ng, pk.occ, grid, smem_of(pk.ng)); return PSG_ECUDA; } }
     PSG_LAUNCH_CHECK();

@@ -25,6 +25,9 @@ class _NetFn(torch.autograd.Function):
         eng = model.engine(x.device)
         eng.bind(x.shape[0], x.shape[2], 1)
         eng.set_input(x)
+        # decided before the geometry pass: with the coordinate gradient wanted, the set-abstraction rows stay in the padded
+        # layout its kernels read (csrc/compact.cu)
+        eng.set_xyz_grad(bool(getattr(model, "xyz_grad", False)))
         eng.geometry(starts)
         logp, l4 = eng.forward(0, True, True)
         model._generation += 1
@@ -39,7 +42,6 @@ class _NetFn(torch.autograd.Function):
             raise RuntimeError("pointsecguard_b200: the activations of this forward were overwritten by a later "
                                "forward of the same model; back-propagate before running the model again")
         ctx.eng.loss_grad_generic(dlogp)
-        ctx.eng.set_xyz_grad(bool(getattr(ctx.model, "xyz_grad", False)))
         g = ctx.eng.backward(0, True)
         ctx.eng.set_xyz_grad(False)
         return g, None, None

@@ -65,6 +65,7 @@ def _nb_loop(atk, images, labels, target, mask):
         if st_ is not None:
             st_.wait_event(fork)
         e.bind(p.size, N, chunk)
+        e.set_xyz_grad(False)                       # colour attack: no geometric gradient (decided before the geometry pass)
         e.set_input(p.slice(src))
     sizes = [N] + eng.npoints[:3]
     adv = ori = lab = msk = None
