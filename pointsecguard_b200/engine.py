@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import os
 from typing import Dict, List, Sequence
 
 import numpy as np
@@ -132,10 +133,26 @@ class Engine:
         if need == 0:
             raise L.PsgError("psg_net_workspace: invalid problem size")
         self._ws = None
-        self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
-        base = (self._ws.data_ptr() + 1023) & ~1023
+        # PSG_GUARD=<MiB>: guard bands of a known byte pattern around the workspace (tests/test_gpu_guard.py checks them
+        # after whole attacks -- the pool's compute-sanitizer is closed, so out-of-bounds writes are hunted this way)
+        guard = int(os.environ.get("PSG_GUARD", "0")) << 20
+        self._guard = guard
+        self._ws = torch.empty(need + 1024 + 2 * guard, dtype=torch.uint8, device=self.device)
+        if guard:
+            self._ws.fill_(0xA5)
+        base = (self._ws.data_ptr() + guard + 1023) & ~1023
+        self._ws_span = (base - self._ws.data_ptr(), need)
         L.psg_net_bind(self._net, B, N, T, base, need)
         self.B, self.N, self.T = B, N, T
+
+    def guard_intact(self) -> bool:
+        """True when the guard bands around the workspace (PSG_GUARD) still hold their pattern."""
+        if not getattr(self, "_guard", 0) or self._ws is None:
+            return True
+        off, need = self._ws_span
+        head = self._ws[:off]
+        tail = self._ws[off + need:]
+        return bool((head == 0xA5).all().item()) and bool((tail == 0xA5).all().item())
 
     def _stream(self):
         """Stream the C library enqueues on: the one set with ``use_stream`` (sub-batch pipelining,
