@@ -28,7 +28,7 @@ def test_workspace_guard_bands_survive_whole_attacks(monkeypatch, arch, mode):
     m = m.cuda().eval()
     m.set_mlp_mode(MLP_TF32 if mode == "tf32" else MLP_FP32)
     try:
-        for B, N, kind in ((3, 4096, "uniform"), (2, 1000, "clustered"), (1, 5000, "duplicates")):
+        for B, N, kind in ((3, 4096, "uniform"), (2, 2000, "clustered"), (1, 5000, "duplicates")):
             x = syn.make_blocks(B, N, 4, kind).cuda()
             labels = syn.zband_labels(x.cpu())
             lab = labels.numpy().astype(np.float64)
