@@ -459,6 +459,20 @@ __global__ void index_points_kernel(const float *__restrict__ pts, const long lo
     out[t] = pts[(b * N + src) * C + ch];
 }
 
+// C % 4 == 0: one 128-bit load + store per thread, a gathered row is read and written as whole 16-byte pieces by
+// consecutive threads (full sectors both ways); the index is read once per 16 bytes, not once per float
+__global__ void index_points_v4_kernel(const float4 *__restrict__ pts, const long long *__restrict__ idx, int N, int C4, long long M,
+                                       long long total, float4 *__restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total * C4) return;
+    const long long e = t / C4;
+    const int ch = (int)(t - e * C4);
+    const long long b = e / M;
+    const long long src = __ldg(idx + e);
+    out[t] = __ldg(pts + (b * N + src) * C4 + ch);
+}
+
 inline unsigned nblocks(long long threads, int bs) { return (unsigned)((threads + bs - 1) / bs); }
 
 }  // namespace
@@ -593,6 +607,12 @@ int psg_index_points_rm(const float *pts, const long long *idx, int B, int N, in
                         cudaStream_t st)
 {
     const long long total = (long long)B * M;
+    if (C % 4 == 0 && ((uintptr_t)pts & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+        index_points_v4_kernel<<<nblocks(total * (C / 4), 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(pts), idx, N, C / 4, M,
+                                                                             total, reinterpret_cast<float4 *>(out));
+        PSG_LAUNCH_CHECK();
+        return PSG_OK;
+    }
     index_points_kernel<<<nblocks(total * C, 256), 256, 0, st>>>(pts, idx, N, C, M, total, out);
     PSG_LAUNCH_CHECK();
     return PSG_OK;
