@@ -157,6 +157,13 @@ int psg_tl_mul(float *x_base, int x_wchunks, const float *m_base, int m_wchunks,
 int psg_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, psg_stream_t stream);
 
+/* ---- dense kNN graph in feature space (ResGCN/gcn_lib/dense/torch_edge.py:32-59) ----
+ * x [B,N,C] row-major, C <= 64, k <= 32: nn_idx [B,N,k] (int64, nearest first, the point itself included) = the indices
+ * torch.topk(-pairwise_distance(x), k) returns; nn_d2 (optional) the squared distances.  No [B,N,N] matrix is formed. */
+int psg_dense_knn(const float *x, int B, int N, int C, int k, int64_t *nn_idx, float *nn_d2, psg_stream_t stream);
+/* pairwise_distance(x) of torch_edge.py:32-43 as the full [B,N,N] matrix (API completeness, small clouds) */
+int psg_pairwise_distance(const float *x, int B, int N, int C, float *out, psg_stream_t stream);
+
 /* ---- whole-network engine (pointnet2_sem_seg.py:22-40, pointnet2_sem_seg_msg.py:23-41) -------- */
 typedef struct { int cin, cout; const float *w_host; const float *b_host; } psg_mlp_desc;
 typedef struct {

@@ -87,6 +87,8 @@ _PROTOS = {
     "psg_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp]),
     "psg_mlp_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp]),
     "psg_mlp_backward": (_i, [_vp, _vp, _i, _i64, _vp, _i, _vp, _i, _i, _vp]),
+    "psg_dense_knn": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "psg_pairwise_distance": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "psg_net_create": (_vp, [C.POINTER(NetDesc)]),
     "psg_net_destroy": (None, [_vp]),
     "psg_net_set_mlp_mode": (_i, [_vp, _i]),

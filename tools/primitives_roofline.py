@@ -100,6 +100,15 @@ def main():
         gout = torch.empty(P, S * K, 64, device=dev)
         f = lambda: L.psg_index_points(pts.data_ptr(), idx64.data_ptr(), P, N, 64, S * K, gout.data_ptr(), st)
         res["index_points_C64"] = (timed(f, flush), 8 * S * K + 4 * 64 * N + 4 * 64 * S * K)
+        # dense kNN graph (ResGCN's graph op, csrc/knn.cu): k = 16 over the cloud itself, xyz and 64-wide features
+        if N <= 16384:
+            knn_out = torch.empty(P, N, 16, dtype=torch.int64, device=dev)
+            f = lambda: L.psg_dense_knn(xyz.data_ptr(), P, N, 3, 16, knn_out.data_ptr(), None, st)
+            res["dense_knn_C3_k16"] = (timed(f, flush, reps=5), 12 * N + 8 * 16 * N)
+            if P * N <= 16 * 16384:
+                f64 = pts[:, :, :64].contiguous()
+                f = lambda: L.psg_dense_knn(f64.data_ptr(), P, N, 64, 16, knn_out.data_ptr(), None, st)
+                res["dense_knn_C64_k16"] = (timed(f, flush, reps=3), 256 * N + 8 * 16 * N)
         case = {}
         for k, ((med, best), nbytes) in res.items():
             gb = nbytes * P / (med / 1e3) / 1e9
