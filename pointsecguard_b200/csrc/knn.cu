@@ -5,9 +5,9 @@
 // first.  The reference materialises the [B, N, N] matrix (268 MB per 16 clouds of 4096 points) and sorts it; here a CTA keeps
 // 128 queries in registers (features + a sorted top-k list each), streams the cloud through shared memory in tiles, and
 // never writes a distance to HBM.  Arithmetic: |x|^2 as separately rounded products added left to right, the dot product as
-// an fma chain over the channels, the sum as ((|x_i|^2 + (-2 dot)) + |x_j|^2) -- for C = 3 exactly the reference's CPU
-// result (the expansion of pointnet_util.square_distance); for wider features the reference's sgemm
-// accumulates in another order, so neighbours can swap where two distances agree to ~1e-6 relative.  Ties go to the
+// an fma chain over the channels, the sum as ((|x_i|^2 + (-2 dot)) + |x_j|^2).  The reference's sgemm on x x^T accumulates in
+// its own order, so distances agree to rounding (measured: 4 of 65 536 neighbour slots differ at C = 3, each between two
+// candidates whose distances agree to 1e-6 relative).  Ties go to the
 // smaller index (torch.topk leaves them unspecified).
 #include "../../include/psg_b200.h"
 #include "psg_common.cuh"
