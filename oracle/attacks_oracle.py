@@ -35,7 +35,7 @@ def nb_attack(model, images, labels, eps=0.3, alpha=2 / 255, iters=40, field=sli
     col = images[:, field].clone().detach()
     ori = col.clone()
     adv = images.clone().detach()
-    y = _labels(labels)
+    y = _labels(labels).to(images.device)
     for _ in range(iters):
         if snapshots is not None:
             snapshots.append(col.detach().clone())

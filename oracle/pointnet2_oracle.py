@@ -38,7 +38,7 @@ def square_distance(src, dst):
 def index_points(points, idx):
     """pointnet_util.py:43-60: points[b, idx[b, ...], :]."""
     B = points.shape[0]
-    bsel = torch.arange(B).view(B, *([1] * (idx.dim() - 1))).expand_as(idx)
+    bsel = torch.arange(B, device=points.device).view(B, *([1] * (idx.dim() - 1))).expand_as(idx)
     return points[bsel, idx]
 
 
@@ -47,13 +47,14 @@ def farthest_point_sample(xyz, npoint, start=None):
     generator exactly like line 75."""
     B, N, _ = xyz.shape
     if start is None:
-        start = torch.randint(0, N, (B,), dtype=torch.long)
+        start = torch.randint(0, N, (B,), dtype=torch.long)         # CPU generator, then moved (pointnet_util.py:75)
     if GEOMETRY == "c":
         return cgeom.fps(xyz, npoint, start)
-    out = torch.zeros(B, npoint, dtype=torch.long)
-    mind = torch.full((B, N), 1e10)
-    far = start.clone()
-    rows = torch.arange(B)
+    dev = xyz.device                                                # (device-agnostic: tools/stock_torch_baseline.py runs it on a GPU)
+    out = torch.zeros(B, npoint, dtype=torch.long, device=dev)
+    mind = torch.full((B, N), 1e10, device=dev)
+    far = start.clone().to(dev)
+    rows = torch.arange(B, device=dev)
     for i in range(npoint):
         out[:, i] = far
         c = xyz[rows, far].unsqueeze(1)
@@ -70,7 +71,7 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     d = square_distance(new_xyz, xyz)
-    idx = torch.arange(N).expand(B, S, N).clone()
+    idx = torch.arange(N, device=xyz.device).expand(B, S, N).clone()
     idx[d > radius ** 2] = N
     idx = idx.sort(-1)[0][:, :, :nsample]
     first = idx[:, :, :1].expand(-1, -1, nsample)
