@@ -35,9 +35,13 @@ def _check_neighbours(mine_idx, ref_idx, dist_of, rtol):
 def test_oracle_matches_reference_golden(golden_dir, case):
     name, x, k, dil = _inputs()[case]
     g = np.load(os.path.join(golden_dir, "knn.npz"))
-    torch.set_num_threads(1)
     xt = x.transpose(2, 1).squeeze(-1)
-    d = KO.pairwise_distance(xt)
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)                      # the golden rows were produced single-threaded; restored below so that
+    try:                                          # later tests see the process default again
+        d = KO.pairwise_distance(xt)
+    finally:
+        torch.set_num_threads(nthreads)
     np.testing.assert_array_equal(d[:, :2].numpy(), g[name + "_drow"])               # same ops, same order: bit-identical
     e = KO.dense_knn_matrix(x, k)
     assert np.array_equal(e[0].numpy(), g[name + "_knn"].astype(np.int64))
