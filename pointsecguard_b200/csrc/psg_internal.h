@@ -77,6 +77,20 @@ int psg_repack_weights(const float *w, const float *b, int cout, int cin, int kp
 // gemm_simt.cu / gemm_tc.cu
 int psg_gemm_simt(const PsgGemmArgs &g, cudaStream_t st);
 int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st);
+// deep.cu: the per-layer FP levels as one persistent kernel -- a recorder collects the phases, flush launches them
+#define PSG_DEEP_MAX_PHASES 10
+void psg_deep_begin();
+void psg_deep_tune(int bn_min, int items_min);
+bool psg_deep_recording();
+int psg_deep_phases();
+void psg_deep_cancel();
+bool psg_deep_can_gemm(const PsgGemmArgs &g);
+int psg_deep_add_gemm(const PsgGemmArgs &g);
+int psg_deep_add_interp(TView feats, int S, const int *idx, const float *w, long long P, int N, int nch, TView out);
+bool psg_deep_can_segsum(int ncols);
+int psg_deep_add_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, const int *offs, const int *perm, int M, int R,
+                        long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, const float *src_rm, int rm_stride);
+int psg_deep_flush(unsigned *ctr, unsigned *epoch, cudaStream_t st);
 // sa_fused.cu: one set-abstraction branch (gather -> 3 layers -> neighbourhood max) per kernel
 // compact.cu: compacted neighbourhood rows (real ball-query hits only) of one fused SA branch
 struct PsgCompact {
@@ -109,6 +123,7 @@ struct PsgSaFused {
     const int *crow_src, *crow_g, *ntiles_dev;
 };
 bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2);
+void psg_sa_grid_div(int d);       // A/B switch: grid of the compacted-row kernels = padded tiles / d (default 1)
 void psg_sa_force_ng(int ng);      // A/B switch: tiles in flight per CTA of the fused SA kernels (0 = automatic)
 size_t psg_sa_mask_words(long long rows, int n);
 int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st);

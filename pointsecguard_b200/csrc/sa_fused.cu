@@ -657,10 +657,15 @@ struct PickEnt { PickKey k; Pick p; };
 PickEnt g_picks[128];
 int g_npicks = 0;
 int g_ng_forced = 0;
+// compacted rows: only the device knows the tile count.  The grid is sized for padded tiles / g_grid_div; 1 = as if nothing
+// compacted (CTAs without a tile leave after the prologue), 3 = the S3DIS-density guess of the first version, which left
+// SA2 (rows / 2, not / 3.6) on 86 of 148 SMs for two rounds of tiles
+int g_grid_div = 1;
 
 }  // namespace
 
 void psg_sa_force_ng(int ng) { g_ng_forced = ng; g_npicks = 0; }
+void psg_sa_grid_div(int d) { g_grid_div = d < 1 ? 1 : d; }
 
 namespace {
 template <class KernOf, class SmemOf>
@@ -721,9 +726,8 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
                   : f.K == 32 ? cached_pick(0, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern<32>, smem_of, gc)
                               : cached_pick(0, 16, a.gpad, a.n0, a.n1, a.n2, fwd_kern<16>, smem_of, gc);
     if (pk.ng < 1 || pk.occ < 1 || num_sms() < 1) return PSG_EUNSUPPORTED;
-    // compacted rows: only the device knows the tile count; one third of the padded count covers S3DIS densities, and
-    // the persistent CTAs stride over whatever there is
-    const int tiles_for_grid = cp ? (a.ntiles + 2) / 3 : a.ntiles;
+    // compacted rows: only the device knows the tile count; the persistent CTAs stride over whatever there is
+    const int tiles_for_grid = cp ? (a.ntiles + g_grid_div - 1) / g_grid_div : a.ntiles;
     const int want = (tiles_for_grid + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
     const int grid = want < cap ? want : cap;
     auto kern = cp ? fwd_kern_cp(pk.ng) : f.K == 32 ? fwd_kern<32>(pk.ng) : fwd_kern<16>(pk.ng);
@@ -753,7 +757,7 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float
                   : f.K == 32 ? cached_pick(1, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern<32>, smem_of, gc)
                               : cached_pick(1, 16, a.gpad, a.n0, a.n1, a.n2, bwd_kern<16>, smem_of, gc);
     if (pk.ng < 1 || pk.occ < 1 || num_sms() < 1) return PSG_EUNSUPPORTED;
-    const int tiles_for_grid = cp ? (a.ntiles + 2) / 3 : a.ntiles;
+    const int tiles_for_grid = cp ? (a.ntiles + g_grid_div - 1) / g_grid_div : a.ntiles;
     const int want = (tiles_for_grid + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
     const int grid = want < cap ? want : cap;
     auto kern = cp ? bwd_kern_cp(pk.ng) : f.K == 32 ? bwd_kern<32>(pk.ng) : bwd_kern<16>(pk.ng);
