@@ -191,6 +191,10 @@ size_t psg_net_workspace(const psg_net *net, int B, int N, int T);
 int psg_net_bind(psg_net *net, int B, int N, int T, void *workspace, size_t workspace_bytes);
 /* x [B,C,N] with element strides (sb, sc, sn): packs features and xyz */
 int psg_net_set_input(psg_net *net, const float *x, int64_t sb, int64_t sc, int64_t sn, psg_stream_t stream);
+/* The packed model input of `src` (as its last psg_net_set_input / psg_net_pgd_update left it) becomes the input of
+ * `net`; both bound to the same B and N.  The attack loops hand a running attack from one engine to another with it
+ * (nontarget.py:31-39: `color` is the PROJECTED value that enters the next forward, adv_images the un-projected one). */
+int psg_net_copy_input(psg_net *net, const psg_net *src, psg_stream_t stream);
 /* starts int32 [4][T][B]: FPS start index per level / forward / block (pointnet_util.py:75 draws) */
 int psg_net_geometry(psg_net *net, const int32_t *starts, int T, psg_stream_t stream);
 /* Copy one resident geometry buffer of forward slot t into dst (device memory, dst_bytes large enough; enqueued on

@@ -633,6 +633,15 @@ extern "C" int psg_net_set_input(psg_net *n, const float *x, int64_t sb, int64_t
     return PSG_OK;
 }
 
+extern "C" int psg_net_copy_input(psg_net *n, const psg_net *src, psg_stream_t stream)
+{
+    if (!n || !src || !n->bound || !src->bound || n->B != src->B || n->N != src->N || n->wfeat[0] != src->wfeat[0]) return PSG_EINVAL;
+    if (n == src) return PSG_OK;
+    if (cudaMemcpyAsync(n->feats[0], src->feats[0], tl_bytes((long long)n->B * n->N, n->wfeat[0]), cudaMemcpyDeviceToDevice,
+                        (cudaStream_t)stream) != cudaSuccess) return PSG_ECUDA;
+    return PSG_OK;
+}
+
 // coordinates of level l for forward t
 static inline const float *lvl_xyz(const psg_net *n, int l, int t)
 {

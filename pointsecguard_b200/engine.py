@@ -195,6 +195,13 @@ class Engine:
         L.psg_net_set_input(self._net, x.data_ptr(), sb, sc, sn, self._stream())
 
     @_on_engine_device
+    def copy_input_from(self, other: "Engine"):
+        """Take over the packed model input of ``other`` (same B, N): the colours as its last update projected them."""
+        rc = L.psg_net_copy_input(self._net, other._net, self._stream())
+        if rc != 0:
+            raise L.PsgError(f"psg_net_copy_input failed ({rc})")
+
+    @_on_engine_device
     def geometry(self, starts: torch.Tensor):
         """starts: int32 [4, T, B] (CPU or device)."""
         T = starts.shape[1]

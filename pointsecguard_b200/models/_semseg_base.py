@@ -114,12 +114,26 @@ class SemSegBase(nn.Module):
             e.set_mlp_mode(self.mlp_mode)
         return engs, self._sub_streams[:count]
 
+    def tail_engine(self, device, primary=None):
+        """A second engine (same folded weights, own workspace) and a side stream: the norm-bounded attacks compute the
+        geometry of all but the first forwards on it while the loop already runs (torchattacks/attacks/nontarget.py)."""
+        if primary is None:
+            primary = self.engine(device)
+        if getattr(self, "_tail", None) is None or self._tail_of is not primary:
+            self._tail = Engine(self.describe(), primary.device, self.mlp_mode)
+            self._tail_of = primary
+            self._tail_stream = torch.cuda.Stream(primary.device)
+        self._tail.set_mlp_mode(self.mlp_mode)
+        return self._tail, self._tail_stream
+
     def set_mlp_mode(self, mode: int):
         self.mlp_mode = mode
         if self._engine is not None:
             self._engine.set_mlp_mode(mode)
             for e in self._sub_engines:
                 e.set_mlp_mode(mode)
+            if getattr(self, "_tail", None) is not None:
+                self._tail.set_mlp_mode(mode)
             self._engine_key = self._param_key(self._engine.device)
 
     def _sa_desc(self, sa):
