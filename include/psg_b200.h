@@ -179,7 +179,7 @@ typedef struct {
     psg_sa_desc sa[4];
     psg_fp_desc fp[4];          /* fp[f]: fine level f, coarse level f+1 (reference fp1 = fp[0]) */
     psg_mlp_desc conv1, conv2;
-    int mlp_mode;               /* 0 = fp32 CUDA-core GEMM (exact), 1 = tcgen05 TF32 */
+    int mlp_mode;               /* 0 = fp32 CUDA-core GEMM (exact), 1 = tcgen05 TF32 (fused kernels), 2 = tcgen05 3xTF32 (per layer, fp32-grade) */
 } psg_net_desc;
 
 typedef struct psg_net psg_net;

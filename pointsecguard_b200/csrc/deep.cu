@@ -26,6 +26,7 @@
 #include "psg_common.cuh"
 #include "psg_internal.h"
 #include "psg_tc.cuh"
+#include "psg_segsum.cuh"
 
 namespace {
 
@@ -46,8 +47,7 @@ struct DeepPhase {
     // DP_INTERP
     TView i_src; int i_S; const int *i_idx; const float *i_w; long long i_rows; int i_N, i_nch; TView i_out;
     // DP_SEGSUM
-    TView s_src; long long s_rows_per_p; int s_div; const float *s_wgt; const int *s_offs, *s_perm; int s_M, s_R; long long s_P;
-    int s_nch, s_tail; TView s_dst; int s_acc; TView s_rmask; const float *s_rm; int s_rm_stride;
+    PsgSegsumArgs s;
 };
 
 struct DeepArgs {
@@ -65,7 +65,6 @@ __device__ __forceinline__ long long gtimer()
     return t;
 }
 
-__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
 {
@@ -206,9 +205,9 @@ __device__ __forceinline__ void phase_interp(const DeepPhase &p)
             const int *ii = p.i_idx + row[u] * 3;
             const float *ww = p.i_w + row[u] * 3;
             const int c = in ? ch[u] : 0;
-            a[u] = ldcg4(p.i_src.base + tv_off(p.i_src, base + __ldg(ii), c));
-            b[u] = ldcg4(p.i_src.base + tv_off(p.i_src, base + __ldg(ii + 1), c));
-            d[u] = ldcg4(p.i_src.base + tv_off(p.i_src, base + __ldg(ii + 2), c));
+            a[u] = psg_ldcg4(p.i_src.base + tv_off(p.i_src, base + __ldg(ii), c));
+            b[u] = psg_ldcg4(p.i_src.base + tv_off(p.i_src, base + __ldg(ii + 1), c));
+            d[u] = psg_ldcg4(p.i_src.base + tv_off(p.i_src, base + __ldg(ii + 2), c));
             w0[u] = __ldg(ww); w1[u] = __ldg(ww + 1); w2[u] = __ldg(ww + 2);
         }
 #pragma unroll
@@ -220,88 +219,6 @@ __device__ __forceinline__ void phase_interp(const DeepPhase &p)
             r.z = __fadd_rn(__fadd_rn(__fmul_rn(a[u].z, w0[u]), __fmul_rn(b[u].z, w1[u])), __fmul_rn(d[u].z, w2[u]));
             r.w = __fadd_rn(__fadd_rn(__fmul_rn(a[u].w, w0[u]), __fmul_rn(b[u].w, w1[u])), __fmul_rn(d[u].w, w2[u]));
             tv_st(p.i_out, row[u], ch[u], r);
-        }
-    }
-}
-
-// ---- ordered segmented sum (gather.cu::segsum_kernel), a warp per destination row: lane l fetches entry lo + l of the
-// bucket (slot and weight) once, the warp then walks the entries in bucket order with four rows in flight per lane and
-// chunk.  Chunks lane, lane + 32, ... (NC of them) belong to the lane. ----
-template <int NC>
-__device__ __forceinline__ void phase_segsum(const DeepPhase &p, int warp, int lane)
-{
-    const long long nrows = p.s_P * p.s_R;
-    const int wpc = blockDim.x >> 5;
-    const long long wstride = (long long)gridDim.x * wpc;
-    for (long long wid = (long long)blockIdx.x * wpc + warp; wid < nrows; wid += wstride) {
-        const long long pp = wid / p.s_R;
-        const int r = (int)(wid % p.s_R);
-        const int lo = __ldg(p.s_offs + pp * (p.s_R + 1) + r), hi = __ldg(p.s_offs + pp * (p.s_R + 1) + r + 1);
-        const int *pm = p.s_perm + pp * p.s_M;
-        const float *ww = p.s_wgt ? p.s_wgt + pp * p.s_M : nullptr;
-        const long long sbase = pp * p.s_rows_per_p;
-        float4 acc[NC];
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            const int c = lane + 32 * k;
-            acc[k] = (p.s_acc && c < p.s_nch) ? ldcg4(p.s_dst.base + tv_off(p.s_dst, wid, c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int w0 = lo; w0 < hi; w0 += 32) {
-            const int e = w0 + lane;
-            const int my_slot = e < hi ? __ldg(pm + e) : -1;
-            const float my_w = (ww && my_slot >= 0) ? __ldg(ww + my_slot) : 1.f;
-            const int cnt = min(32, hi - w0);
-            for (int j0 = 0; j0 < cnt; j0 += 4) {
-                int slot[4]; float sc[4]; float4 v[4][NC];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    slot[u] = __shfl_sync(0xffffffffu, my_slot, (j0 + u) & 31);
-                    sc[u] = __shfl_sync(0xffffffffu, my_w, (j0 + u) & 31);
-                    if (j0 + u >= cnt) slot[u] = -1;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        const int c = lane + 32 * k;
-                        v[u][k] = (slot[u] < 0 || c >= p.s_nch) ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                : p.s_rm ? ldcg4(p.s_rm + (sbase + slot[u] / p.s_div) * p.s_rm_stride + 4 * c)
-                                         : ldcg4(p.s_src.base + tv_off(p.s_src, sbase + slot[u] / p.s_div, c));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (slot[u] < 0) continue;
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        const int c = lane + 32 * k;
-                        float4 q = v[u][k];
-                        if (c == p.s_nch - 1 && p.s_tail) {       // keep only the first tail columns of the last chunk
-                            if (p.s_tail < 2) q.y = 0.f;
-                            if (p.s_tail < 3) q.z = 0.f;
-                            q.w = 0.f;
-                        }
-                        if (ww) {
-                            acc[k].x = fmaf(q.x, sc[u], acc[k].x); acc[k].y = fmaf(q.y, sc[u], acc[k].y);
-                            acc[k].z = fmaf(q.z, sc[u], acc[k].z); acc[k].w = fmaf(q.w, sc[u], acc[k].w);
-                        } else {
-                            acc[k].x += q.x; acc[k].y += q.y; acc[k].z += q.z; acc[k].w += q.w;
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            const int c = lane + 32 * k;
-            if (c >= p.s_nch) continue;
-            float4 o = acc[k];
-            if (p.s_rmask.base) {                          // gradient w.r.t. the pre-activation of a ReLU layer
-                const float4 y = tv_ld(p.s_rmask, wid, c);
-                o.x = y.x > 0.f ? o.x : 0.f; o.y = y.y > 0.f ? o.y : 0.f;
-                o.z = y.z > 0.f ? o.z : 0.f; o.w = y.w > 0.f ? o.w : 0.f;
-            }
-            tv_st(p.s_dst, wid, c, o);
         }
     }
 }
@@ -347,10 +264,11 @@ __global__ void __launch_bounds__(kThreads, 1) deep_kernel(const __grid_constant
         } else if (p.kind == DP_INTERP) {
             phase_interp(p);
         } else {
-            const int nc = (p.s_nch + 31) / 32;
-            if (nc <= 1) phase_segsum<1>(p, warp, lane);
-            else if (nc == 2) phase_segsum<2>(p, warp, lane);
-            else phase_segsum<4>(p, warp, lane);
+            const int nc = (p.s.nch + 31) / 32;
+            const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + warp, ws = (long long)gridDim.x * (blockDim.x >> 5);
+            if (nc <= 1) psg_segsum_warp<1, true>(p.s, w0, ws, lane);
+            else if (nc == 2) psg_segsum_warp<2, true>(p.s, w0, ws, lane);
+            else psg_segsum_warp<4, true>(p.s, w0, ws, lane);
         }
         if (tr) { tr[2 + 2 * pi] = gtimer(); tr[102 + pi] = p.kind; }
         if (pi + 1 < a.nph) {
@@ -416,9 +334,9 @@ int psg_deep_add_segsum(TView src, long long src_rows_per_p, int div, const floa
     if (!psg_deep_can_segsum(ncols)) return PSG_EUNSUPPORTED;
     DeepPhase &p = g_rec.ph[g_rec.nph++];
     p.kind = DP_SEGSUM;
-    p.s_src = src; p.s_rows_per_p = src_rows_per_p; p.s_div = div; p.s_wgt = wgt; p.s_offs = offs; p.s_perm = perm; p.s_M = M; p.s_R = R;
-    p.s_P = P; p.s_nch = (ncols + 3) / 4; p.s_tail = ncols & 3; p.s_dst = dst; p.s_acc = accumulate;
-    p.s_rmask = relu_mask ? *relu_mask : TView{nullptr, 0, 0}; p.s_rm = src_rm; p.s_rm_stride = rm_stride;
+    p.s.src = src; p.s.rows_per_p = src_rows_per_p; p.s.div = div; p.s.wgt = wgt; p.s.offs = offs; p.s.perm = perm; p.s.M = M; p.s.R = R;
+    p.s.P = P; p.s.nch = (ncols + 3) / 4; p.s.tail = ncols & 3; p.s.dst = dst; p.s.acc = accumulate;
+    p.s.rmask = relu_mask ? *relu_mask : TView{nullptr, 0, 0}; p.s.rm = src_rm; p.s.rm_stride = rm_stride;
     return PSG_OK;
 }
 

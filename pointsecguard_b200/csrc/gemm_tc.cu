@@ -32,20 +32,27 @@ __device__ __forceinline__ long long gtimer()
     return t;
 }
 
-template <int EPI>
+// X3: error-compensated TF32 ("3xTF32"), fp32-grade products on the tensor cores.  tcgen05.mma.kind::tf32 reads the top
+// 19 bits of each fp32 operand, so A as it lies in shared memory IS A_hi; the four epilogue warps, idle during the K
+// loop, write A_lo = A - A_hi (exact in fp32) next to every stage as it lands; the weights arrive pre-split from the host
+// (W_hi = nearest TF32 of W, W_lo = nearest TF32 of W - W_hi).  Three MMAs per K step accumulate A_lo W_hi + A_hi W_lo +
+// A_hi W_hi into the same TMEM accumulator; the dropped A_lo W_lo term is 2^-22 relative.
+template <int EPI, bool X3>
 __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn_tile, int kStages, long long *trace,
                                                            const __grid_constant__ CUtensorMap wmap, int use_map)
 {
     long long *tr = (trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) ? trace : nullptr;   // first epilogue thread
     if (tr) tr[0] = gtimer();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc;
+    __shared__ __align__(8) unsigned long long bar_full[kMaxStages], bar_empty[kMaxStages], bar_split[kMaxStages], bar_acc;
     __shared__ uint32_t tmem_slot;
 
-    // 1024-byte aligned operand staging area
+    // 1024-byte aligned operand staging area: [A stages][A_lo stages (X3)][B stages (X3: hi | lo per stage)]
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int kBBytes = kBlk * bn_tile * 16;
-    const uint32_t sA = sbase, sB = sbase + kStages * kABytes;
+    const int kBHalf = kBlk * bn_tile * 16;
+    const int kBBytes = X3 ? 2 * kBHalf : kBHalf;
+    const uint32_t sA = sbase, sAlo = sbase + kStages * kABytes, sB = sbase + (X3 ? 2 : 1) * kStages * kABytes;
+    unsigned char *pA = smem_raw + (sbase - tc::smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row0 = (long long)blockIdx.x * 128;
@@ -54,7 +61,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
     const uint32_t ncols = tc::next_pow2_cols(BN);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < kStages; ++s) {
+            tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1);
+            tc::mbar_init(tc::smem_u32(&bar_split[s]), 128);
+        }
         tc::mbar_init(tc::smem_u32(&bar_acc), 1);
         tc::fence_mbar_init();
     }
@@ -81,7 +91,15 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
             n = min(kBlk, (srcI == 0 ? g.k1chunks : g.k2chunks) - c);
         };
         auto issue_w = [&](int s, int c, int kglob, int n, uint32_t full) {
-            if (use_map && BN == bn_tile) {
+            if (X3) {
+                // lanes 1..n: the hi plane, lanes 9..8+n: the lo plane of the same K chunk
+                const int j = (lane - 1) & 7;
+                if (lane >= 1 && lane <= 16 && j < n) {
+                    const float *w = lane <= 8 ? g.W : g.Wlo;
+                    tc::bulk_g2s(sB + s * kBBytes + (lane <= 8 ? 0 : kBHalf) + j * BN * 16, w + ((size_t)(kglob + c + j) * g.Nw + n0) * 4,
+                                 (uint32_t)(BN * 16), full);
+                }
+            } else if (use_map && BN == bn_tile) {
                 if (lane == 1) psg_tmap_load(sB + s * kBBytes, &wmap, n0, kglob + c, full);
             } else if (lane >= 1 && lane <= n) {
                 const int j = lane - 1;
@@ -93,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
             int srcI, c, kglob, n;
             stage_of(it, srcI, c, kglob, n);
             const uint32_t full = tc::smem_u32(&bar_full[it]);
-            if (lane == 0) tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + n * BN * 16));
+            if (lane == 0) tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + (X3 ? 2 : 1) * n * BN * 16));
             __syncwarp();
             issue_w(it, c, kglob, n, full);
         }
@@ -115,7 +133,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
             const uint32_t full = tc::smem_u32(&bar_full[s]);
             if (lane == 0) {
                 tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
-                tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + n * BN * 16));
+                tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + (X3 ? 2 : 1) * n * BN * 16));
             }
             __syncwarp();
             if (lane == 0) tc::bulk_g2s(sA + s * kABytes, src.base + tv_off(src, row0, c), (uint32_t)(n * 2048), full);
@@ -133,11 +151,18 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
                     const int n = min(kBlk, kch - c);
                     const int s = it % kStages;
                     const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-                    tc::mbar_wait(tc::smem_u32(&bar_full[s]), ph);
+                    tc::mbar_wait(tc::smem_u32(X3 ? &bar_split[s] : &bar_full[s]), ph);
                     tc::fence_after_sync();
                     for (int j = 0; j < n; j += 2) {
                         const uint64_t ad = tc::smem_desc(sA + s * kABytes + j * 2048, 2048, 128);
                         const uint64_t bd = tc::smem_desc(sB + s * kBBytes + j * BN * 16, (uint32_t)(BN * 16), 128);
+                        if (X3) {
+                            const uint64_t al = tc::smem_desc(sAlo + s * kABytes + j * 2048, 2048, 128);
+                            const uint64_t bl = tc::smem_desc(sB + s * kBBytes + kBHalf + j * BN * 16, (uint32_t)(BN * 16), 128);
+                            tc::mma_tf32(tmem, al, bd, idesc, acc);       // small terms first
+                            tc::mma_tf32(tmem, ad, bl, idesc, 1u);
+                            tc::mma_tf32(tmem, ad, bd, idesc, 1u);
+                        } else
                         tc::mma_tf32(tmem, ad, bd, idesc, acc);
                         acc = 1;
                     }
@@ -150,6 +175,35 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
         // ---- epilogue: warp q owns TMEM lanes [32q, 32q + 32) ----
         const int q = warp & 3;
         const long long row = row0 + q * 32 + lane;
+        if (X3) {
+            // A_lo of every stage as it lands (the K loop's stage order; these warps have nothing else to do until the
+            // accumulator is complete)
+            const int tid = threadIdx.x - 64;
+            int it = 0;
+            for (int srcI = 0; srcI < 2; ++srcI) {
+                const int kch = srcI == 0 ? g.k1chunks : g.k2chunks;
+                for (int c = 0; c < kch; c += kBlk, ++it) {
+                    const int n = min(kBlk, kch - c);
+                    const int s = it % kStages;
+                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                    tc::mbar_wait(tc::smem_u32(&bar_full[s]), ph);
+                    const float4 *src = reinterpret_cast<const float4 *>(pA + (size_t)s * kABytes);
+                    float4 *dst = reinterpret_cast<float4 *>(pA + (size_t)(kStages + s) * kABytes);
+#pragma unroll 4
+                    for (int i = tid; i < n * 128; i += 128) {
+                        const float4 a = src[i];
+                        float4 l;
+                        l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+                        l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+                        l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+                        l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+                        dst[i] = l;
+                    }
+                    tc::fence_async_smem();
+                    tc::mbar_arrive(tc::smem_u32(&bar_split[s]));
+                }
+            }
+        }
         tc::mbar_wait(tc::smem_u32(&bar_acc), 0);
         tc::fence_after_sync();
         if (tr) tr[3] = gtimer();
@@ -191,12 +245,12 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
     if (warp == 1) tc::tmem_dealloc(tmem, ncols);
 }
 
-template <int EPI>
+template <int EPI, bool X3>
 int launch(const PsgGemmArgs &g, cudaStream_t st)
 {
     static PsgDeviceOnce attr_once;
     if (attr_once.need()) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tc_kernel<EPI, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
             return PSG_ECUDA;
         attr_once.mark();
     }
@@ -204,16 +258,22 @@ int launch(const PsgGemmArgs &g, cudaStream_t st)
     // B stages let more of the K loop be in flight at once
     int bn = kBNMax;
     while (bn > 32 && g.mtiles * ((g.nout_pad + bn - 1) / bn) < 96) bn >>= 1;
-    int nst = kRingBytes / (kABytes + kBlk * bn * 16);
+    const int stage_bytes = (X3 ? 2 : 1) * (kABytes + kBlk * bn * 16);
+    int nst = kRingBytes / stage_bytes;
     if (nst > kMaxStages) nst = kMaxStages;
+    // a short K loop needs no deeper ring than it has stages: the narrow layers (K = 16 .. 128, thousands of row tiles)
+    // then fit several CTAs per SM instead of one behind a 200 KB ring, and their prologues overlap
+    const int kstages = (g.k1chunks + kBlk - 1) / kBlk + (g.k2chunks + kBlk - 1) / kBlk;
+    if (nst > kstages) nst = kstages;
+    const size_t smem = (size_t)nst * stage_bytes + 1024;
     dim3 grid((unsigned)g.mtiles, (unsigned)((g.nout_pad + bn - 1) / bn));
     // weights [K/4][Nw][4] as a tiled TMA source: boxes of kBlk planes x bn columns (K is a multiple of 16, i.e. of
     // 4 planes; a last short stage reads past the layer's planes only if K % 32 != 0, where the map clips)
     CUtensorMap wmap;
     memset(&wmap, 0, sizeof(wmap));
     const long long planes = g.k1chunks + g.k2chunks;
-    const int use_map = (planes % kBlk == 0 && psg_weight_tmap(&wmap, g.W, planes, g.Nw, kBlk, bn)) ? 1 : 0;
-    if (psg_launch_pdl(gemm_tc_kernel<EPI>, grid, dim3(kThreads), (size_t)kSmemBytes, st, 1, g, bn, nst, psg_tile_trace_slot(), wmap, use_map) != cudaSuccess) return PSG_ECUDA;
+    const int use_map = (!X3 && planes % kBlk == 0 && psg_weight_tmap(&wmap, g.W, planes, g.Nw, kBlk, bn)) ? 1 : 0;
+    if (psg_launch_pdl(gemm_tc_kernel<EPI, X3>, grid, dim3(kThreads), smem, st, 1, g, bn, nst, psg_tile_trace_slot(), wmap, use_map) != cudaSuccess) return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
@@ -224,11 +284,20 @@ int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st)
 {
     if (g.k1chunks % 4 || g.k2chunks % 4 || g.k1chunks <= 0 || g.mtiles <= 0 || g.nout_pad % 16) return PSG_EINVAL;
     if (g.Nw < g.nout_pad) return PSG_EINVAL;
+    if (g.Wlo) {
+        switch (g.epi) {
+        case PSG_EPI_BIAS_RELU: return launch<PSG_EPI_BIAS_RELU, true>(g, st);
+        case PSG_EPI_BIAS: return launch<PSG_EPI_BIAS, true>(g, st);
+        case PSG_EPI_MASK: return launch<PSG_EPI_MASK, true>(g, st);
+        case PSG_EPI_NONE: return launch<PSG_EPI_NONE, true>(g, st);
+        }
+        return PSG_EINVAL;
+    }
     switch (g.epi) {
-    case PSG_EPI_BIAS_RELU: return launch<PSG_EPI_BIAS_RELU>(g, st);
-    case PSG_EPI_BIAS: return launch<PSG_EPI_BIAS>(g, st);
-    case PSG_EPI_MASK: return launch<PSG_EPI_MASK>(g, st);
-    case PSG_EPI_NONE: return launch<PSG_EPI_NONE>(g, st);
+    case PSG_EPI_BIAS_RELU: return launch<PSG_EPI_BIAS_RELU, false>(g, st);
+    case PSG_EPI_BIAS: return launch<PSG_EPI_BIAS, false>(g, st);
+    case PSG_EPI_MASK: return launch<PSG_EPI_MASK, false>(g, st);
+    case PSG_EPI_NONE: return launch<PSG_EPI_NONE, false>(g, st);
     }
     return PSG_EINVAL;
 }

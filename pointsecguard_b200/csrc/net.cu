@@ -106,6 +106,7 @@ struct psg_mlp {
     float *wb;       // [npad/4][nwb][4]   wb[(n/4, k, n%4)] = W[n][k]
     float *bias;     // [nwf]
     float *wf_tf32, *wb_tf32;   // the same two packings for the tcgen05 path: TF32 values, truncation-compensated (below)
+    float *wf_hi, *wf_lo, *wb_hi, *wb_lo;   // mode 2 (3xTF32): W_hi = nearest TF32 of W, W_lo = nearest TF32 of W - W_hi
 };
 
 // tcgen05.mma kind::tf32 reads the upper 19 bits of its fp32 operands: it TRUNCATES.  Truncation loses half a TF32 ulp on
@@ -126,8 +127,8 @@ static inline float tf32_rna(double x)
     memcpy(&f, &u, 4);
     return f;
 }
-static inline const float *w_fwd(const psg_mlp *m, int mode) { return mode == 1 ? m->wf_tf32 : m->wf; }
-static inline const float *w_bwd(const psg_mlp *m, int mode) { return mode == 1 ? m->wb_tf32 : m->wb; }
+static inline const float *w_fwd(const psg_mlp *m, int mode) { return mode == 1 ? m->wf_tf32 : mode == 2 ? m->wf_hi : m->wf; }
+static inline const float *w_bwd(const psg_mlp *m, int mode) { return mode == 1 ? m->wb_tf32 : mode == 2 ? m->wb_hi : m->wb; }
 
 extern "C" psg_mlp *psg_mlp_create(const float *w, const float *b, int cin, int cout)
 {
@@ -149,12 +150,23 @@ extern "C" psg_mlp *psg_mlp_create(const float *w, const float *b, int cin, int 
         hbias[n] = b ? b[n] : 0.f;
     }
     m->wf = m->wb = m->bias = m->wf_tf32 = m->wb_tf32 = nullptr;
+    m->wf_hi = m->wf_lo = m->wb_hi = m->wb_lo = nullptr;
     std::vector<float> cf(hf.size()), cb(hb.size());
     for (size_t i = 0; i < hf.size(); ++i) cf[i] = tf32_rna((double)hf[i] * (1.0 + kTf32Comp));
     for (size_t i = 0; i < hb.size(); ++i) cb[i] = tf32_rna((double)hb[i] * (1.0 + kTf32Comp));
+    // 3xTF32 split of the exact weights (both parts TF32-representable: the hardware's truncation leaves them alone)
+    std::vector<float> fh(hf.size()), fl(hf.size()), bh(hb.size()), bl(hb.size());
+    for (size_t i = 0; i < hf.size(); ++i) { fh[i] = tf32_rna((double)hf[i]); fl[i] = tf32_rna((double)hf[i] - (double)fh[i]); }
+    for (size_t i = 0; i < hb.size(); ++i) { bh[i] = tf32_rna((double)hb[i]); bl[i] = tf32_rna((double)hb[i] - (double)bh[i]); }
     bool ok = cudaMalloc(&m->wf, hf.size() * 4) == cudaSuccess && cudaMalloc(&m->wb, hb.size() * 4) == cudaSuccess &&
               cudaMalloc(&m->wf_tf32, hf.size() * 4) == cudaSuccess && cudaMalloc(&m->wb_tf32, hb.size() * 4) == cudaSuccess &&
-              cudaMalloc(&m->bias, hbias.size() * 4) == cudaSuccess;
+              cudaMalloc(&m->bias, hbias.size() * 4) == cudaSuccess &&
+              cudaMalloc(&m->wf_hi, hf.size() * 4) == cudaSuccess && cudaMalloc(&m->wf_lo, hf.size() * 4) == cudaSuccess &&
+              cudaMalloc(&m->wb_hi, hb.size() * 4) == cudaSuccess && cudaMalloc(&m->wb_lo, hb.size() * 4) == cudaSuccess;
+    ok = ok && cudaMemcpy(m->wf_hi, fh.data(), fh.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(m->wf_lo, fl.data(), fl.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(m->wb_hi, bh.data(), bh.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(m->wb_lo, bl.data(), bl.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(m->wf, hf.data(), hf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(m->wb, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(m->wf_tf32, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -176,6 +188,7 @@ extern "C" psg_mlp *psg_mlp_create_device(int cin, int cout)
     m->nwf = round_up(m->npad, 64);
     m->nwb = round_up(m->kpad, 64);
     m->wf = m->wb = m->bias = m->wf_tf32 = m->wb_tf32 = nullptr;
+    m->wf_hi = m->wf_lo = m->wb_hi = m->wb_lo = nullptr;       // training layers: modes 0 / 1 only
     const size_t nf = (size_t)m->kpad * m->nwf * 4, nb = (size_t)m->npad * m->nwb * 4;
     bool ok = cudaMalloc(&m->wf, nf) == cudaSuccess && cudaMalloc(&m->wb, nb) == cudaSuccess &&
               cudaMalloc(&m->wf_tf32, nf) == cudaSuccess && cudaMalloc(&m->wb_tf32, nb) == cudaSuccess &&
@@ -196,13 +209,14 @@ extern "C" void psg_mlp_destroy(psg_mlp *m)
 {
     if (!m) return;
     cudaFree(m->wf); cudaFree(m->wb); cudaFree(m->bias); cudaFree(m->wf_tf32); cudaFree(m->wb_tf32);
+    cudaFree(m->wf_hi); cudaFree(m->wf_lo); cudaFree(m->wb_hi); cudaFree(m->wb_lo);
     delete m;
 }
 
 static int run_gemm(const PsgGemmArgs &g, int mode, cudaStream_t st)
 {
     if (mode == 1 && psg_deep_recording()) return psg_deep_add_gemm(g);      // a phase of the deep kernel (deep.cu)
-    return mode == 1 ? psg_gemm_tc(g, st) : psg_gemm_simt(g, st);
+    return mode >= 1 ? psg_gemm_tc(g, st) : psg_gemm_simt(g, st);
 }
 
 // forward of one layer: Out = act([A1 | A2] W^T + b)
@@ -212,7 +226,8 @@ static int mlp_fwd(const psg_mlp *m, TView a1, int k1chunks, TView a2, int k2chu
     if ((k1chunks + k2chunks) * 4 != m->kpad) return PSG_EINVAL;
     PsgGemmArgs g;
     g.A1 = a1; g.k1chunks = k1chunks; g.A2 = a2; g.k2chunks = k2chunks;
-    g.W = w_fwd(m, mode); g.Nw = m->nwf; g.bias = m->bias; g.Out = out; g.nout_pad = m->npad;
+    if (mode == 2 && !m->wf_hi) return PSG_EUNSUPPORTED;
+    g.W = w_fwd(m, mode); g.Wlo = mode == 2 ? m->wf_lo : nullptr; g.Nw = m->nwf; g.bias = m->bias; g.Out = out; g.nout_pad = m->npad;
     g.Mask = TView{nullptr, 0, 0};
     g.Out2 = TView{nullptr, 0, 0}; g.out2_cols = 0;
     g.mtiles = (int)(round_up_ll(rows, 128) / 128);
@@ -227,7 +242,8 @@ static int mlp_bwd(const psg_mlp *m, TView dy, long long rows, TView dx, const T
     PsgGemmArgs g;
     g.Out2 = out2 ? *out2 : TView{nullptr, 0, 0}; g.out2_cols = out2 ? out2_cols : 0;
     g.A1 = dy; g.k1chunks = m->npad / 4; g.A2 = TView{nullptr, 0, 0}; g.k2chunks = 0;
-    g.W = w_bwd(m, mode); g.Nw = m->nwb; g.bias = nullptr; g.Out = dx; g.nout_pad = m->kpad;
+    if (mode == 2 && !m->wb_hi) return PSG_EUNSUPPORTED;
+    g.W = w_bwd(m, mode); g.Wlo = mode == 2 ? m->wb_lo : nullptr; g.Nw = m->nwb; g.bias = nullptr; g.Out = dx; g.nout_pad = m->kpad;
     g.Mask = mask ? *mask : TView{nullptr, 0, 0};
     g.mtiles = (int)(round_up_ll(rows, 128) / 128);
     g.epi = mask ? PSG_EPI_MASK : PSG_EPI_NONE;
@@ -437,7 +453,7 @@ extern "C" void psg_net_destroy(psg_net *n)
 
 extern "C" int psg_net_set_mlp_mode(psg_net *n, int mode)
 {
-    if (!n || mode < 0 || mode > 1) return PSG_EINVAL;
+    if (!n || mode < 0 || mode > 2) return PSG_EINVAL;
     n->mode = mode;
     return PSG_OK;
 }
@@ -458,6 +474,7 @@ extern "C" int psg_set_option(const char *name, int value)
     if (!strcmp(name, "deep")) { g_deep = value; return PSG_OK; }
     if (!strcmp(name, "deep_bn_min")) { psg_deep_tune(value, 0); return PSG_OK; }
     if (!strcmp(name, "deep_items")) { psg_deep_tune(0, value); return PSG_OK; }
+    if (!strcmp(name, "segsum_warp")) { g_psg_segsum_warp = value; return PSG_OK; }
     if (!strcmp(name, "sa_grid_div")) { psg_sa_grid_div(value); return PSG_OK; }
     if (!strcmp(name, "dbg")) { psg_tile_set_dbg(value); return PSG_OK; }
     if (!strcmp(name, "sm_cap")) { g_psg_sm_cap = value > 0 ? value : 0; return PSG_OK; }
@@ -998,7 +1015,7 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             PSG_RUN(PF_FP_BWD, psg_fp_stream_bwd(q, top, tv(n->S[cat_buf], F.C1 + F.C2), n->Srm, tv(n->dfeat[f], n->wfeat[f]), st));
             rm_src = n->Srm + F.C1; rm_stride = F.C1 + F.C2;
             skip_done = true;
-        } else if (f > 0 && n->mode == 1 && F.C1) {
+        } else if (f > 0 && n->mode >= 1 && F.C1) {
             TView dsk = tv(n->dfeat[f], n->wfeat[f]);
             PSG_TRY(chain_bwd(n, mlps, Ys, nl, rows, top, top_buf, &cat_buf, st, &dsk, F.C1));
             skip_done = true;

@@ -12,6 +12,7 @@ struct PsgGemmArgs {
     TView A1; int k1chunks;     // first K1 = 4*k1chunks columns of the A operand
     TView A2; int k2chunks;     // optional second source (FP concat); k2chunks = 0 if unused
     const float *W; int Nw;     // packed weights [K/4][Nw][4], Nw = output channels padded to 64
+    const float *Wlo;           // tcgen05 path: W is W_hi and this the TF32 residual W_lo (error-compensated 3xTF32), or null
     const float *bias;          // [nout_pad] (zero padded) or null
     TView Out; int nout_pad;    // columns written (multiple of 16)
     TView Mask;                 // PSG_EPI_MASK: forward activation of the layer below
@@ -68,6 +69,7 @@ int psg_csr_build(const int *keys, long long P, int M, int R, int grp, int *offs
 int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, const int *offs, const int *perm,
                int M, int R, long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, const float *src_rm,
                int rm_stride, cudaStream_t st);
+extern int g_psg_segsum_warp;
 int psg_copy_cols(TView src, TView dst, long long rows, int ncols, int accumulate, cudaStream_t st);
 int psg_index_points_rm(const float *pts, const long long *idx, int B, int N, int C, long long M, float *out,
                         cudaStream_t st);

@@ -33,7 +33,8 @@ def _on_engine_device(fn):
 
 
 MLP_FP32 = 0     # CUDA-core fp32 GEMMs (parity mode)
-MLP_TF32 = 1     # tcgen05 TF32 tensor-core GEMMs
+MLP_TF32 = 1     # tcgen05 TF32 tensor-core GEMMs (fused kernels)
+MLP_TF32X3 = 2   # tcgen05, error-compensated 3xTF32 per-layer GEMMs: fp32-grade results on the tensor cores
 
 
 def fold_conv_bn(w: torch.Tensor, b: torch.Tensor, bn: Dict[str, torch.Tensor] | None, eps: float = 1e-5):

@@ -15,14 +15,16 @@ from pointsecguard_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 
-def _model(arch):
+def _model(arch, mode=0):
     if arch == "ssg":
         from pointsecguard_b200.models.pointnet2_sem_seg import get_model
     else:
         from pointsecguard_b200.models.pointnet2_sem_seg_msg import get_model
     m = get_model(13)
     m.load_state_dict(syn.make_state_dict(arch))
-    return m.cuda().eval()
+    m = m.cuda().eval()
+    m.set_mlp_mode(mode)          # 0: fp32 CUDA cores; 2: error-compensated 3xTF32 on tcgen05 -- both held to the fp32 gates
+    return m
 
 
 def _grad_report(mine, ref):
@@ -33,10 +35,11 @@ def _grad_report(mine, ref):
     return rel, sign, close
 
 
+@pytest.mark.parametrize("mode", [0, 2], ids=["fp32", "x3"])
 @pytest.mark.parametrize("arch", ["ssg", "msg"])
-def test_forward_and_input_gradient_vs_reference_golden(golden_dir, arch):
+def test_forward_and_input_gradient_vs_reference_golden(golden_dir, arch, mode):
     g = dict(np.load(os.path.join(golden_dir, f"model_{arch}.npz")))
-    m = _model(arch)
+    m = _model(arch, mode)
     x = syn.make_blocks(2, 2048, 0, "uniform").cuda().requires_grad_(True)
     torch.manual_seed(0)
     logp, l4 = m(x)
@@ -90,10 +93,11 @@ def test_cpu_tensors_are_refused_in_both_modes():
         m.eval()(syn.make_blocks(1, 1024, 0))
 
 
-def test_nb_attack_vs_reference_golden(golden_dir):
+@pytest.mark.parametrize("mode", [0, 2], ids=["fp32", "x3"])
+def test_nb_attack_vs_reference_golden(golden_dir, mode):
     from pointsecguard_b200 import torchattacks
     g = dict(np.load(os.path.join(golden_dir, "attack.npz")))
-    m = _model("ssg")
+    m = _model("ssg", mode)
     x = syn.make_blocks(2, 4096, 0, "uniform").cuda()
     torch.manual_seed(0)
     adv = torchattacks.NB_attack(m, eps=0.1, alpha=0.05, iters=3)(x, g["nb_labels"].astype(np.float64))
