@@ -11,6 +11,7 @@
 #include "psg_internal.h"
 #include "psg_segsum.cuh"
 
+int g_psg_segsum_fast = 1;      // psg_set_option "segsum_fast": 0 restores the generic kernel
 int g_psg_segsum_warp = 0;      // psg_set_option "segsum_warp" n: rows of 32..32n chunks go through the warp-per-row kernel (measured: no gain)
 
 namespace {
@@ -437,6 +438,87 @@ segsum_kernel(TView src, long long src_rows_per_p, int div, const float *__restr
     }
 }
 
+// The same kernel specialised for the two callers that matter (ncu, warm caches: the generic kernel above is
+// instruction-issue bound -- 66 % issue utilisation at 38 % occupancy, 87 warp instructions per bucket entry of which 4 are
+// the FFMAs: a run-time integer division per entry, 64-bit address products, per-entry tail / weight / mirror branches):
+//   INTERP: backward of the 3-NN interpolation (slot / 3, weighted, fmaf);  !INTERP: backward of the grouping gather
+//   (slot, unweighted, add);  RM: sources are the row-major mirror.  No tail columns (ncols % 4 == 0).  Offsets inside a
+// problem are 32-bit.  Same order of additions, same bits.
+template <int LPR, bool INTERP, bool RM>
+__global__ void __launch_bounds__(256)
+segsum_fast_kernel(TView src, unsigned src_rows_per_p, const float *__restrict__ wgt, const int *__restrict__ offs,
+                   const int *__restrict__ perm, int M, int R, long long P, int nch, TView dst, int accumulate, TView rmask,
+                   const float *__restrict__ src_rm, unsigned rm_stride)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // launched with programmatic stream serialization
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long wid = gid / LPR;                 // destination row
+    const int lane = (int)(gid % LPR);
+    if (wid >= P * R) return;
+    const long long p = wid / R;
+    const int r = (int)(wid - p * R);
+    const int lo = offs[p * (R + 1) + r], hi = offs[p * (R + 1) + r + 1];
+    const int *pm = perm + p * M;
+    const float *ww = INTERP ? wgt + p * M : nullptr;
+    // base of this problem's source rows: row-major mirror, or T-layout (whole problems start on 128-row tile boundaries
+    // whenever rows_per_p % 128 == 0; otherwise the row offset is folded into the per-entry row)
+    const float *rmb = RM ? src_rm + (size_t)p * src_rows_per_p * rm_stride : nullptr;
+    const unsigned row0 = RM ? 0u : (unsigned)((p * src_rows_per_p) & 127);
+    const float *tlb = RM ? nullptr : src.base + ((size_t)((p * src_rows_per_p) >> 7) * src.wchunks + src.c0) * 512;
+    const unsigned wch = (unsigned)src.wchunks;
+    for (int c = lane; c < nch; c += LPR) {
+        float4 acc = accumulate ? tv_ld(dst, wid, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int U = 4;          // entries in flight (8: measured slower; 8 CTAs per SM at 32 registers: within noise)
+        for (int e = lo; e < hi; e += U) {
+            unsigned srow[U]; float4 v[U]; float sc[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int sl = e + u < hi ? pm[e + u] : -1;
+                if (INTERP) sc[u] = sl >= 0 ? ww[sl] : 0.f;
+                srow[u] = sl < 0 ? 0xffffffffu : (INTERP ? (unsigned)sl / 3u : (unsigned)sl);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (srow[u] == 0xffffffffu) { v[u] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+                if (RM) v[u] = *reinterpret_cast<const float4 *>(rmb + srow[u] * rm_stride + 4u * (unsigned)c);
+                else {
+                    const unsigned rr = srow[u] + row0;
+                    v[u] = *reinterpret_cast<const float4 *>(tlb + ((size_t)((rr >> 7) * wch + (unsigned)c) * 512u + (rr & 127u) * 4u));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (srow[u] == 0xffffffffu) continue;
+                if (INTERP) {
+                    acc.x = fmaf(v[u].x, sc[u], acc.x); acc.y = fmaf(v[u].y, sc[u], acc.y);
+                    acc.z = fmaf(v[u].z, sc[u], acc.z); acc.w = fmaf(v[u].w, sc[u], acc.w);
+                } else {
+                    acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+                }
+            }
+        }
+        if (rmask.base) {                          // gradient w.r.t. the pre-activation of a ReLU layer
+            float4 y = tv_ld(rmask, wid, c);
+            acc.x = y.x > 0.f ? acc.x : 0.f; acc.y = y.y > 0.f ? acc.y : 0.f;
+            acc.z = y.z > 0.f ? acc.z : 0.f; acc.w = y.w > 0.f ? acc.w : 0.f;
+        }
+        tv_st(dst, wid, c, acc);
+    }
+}
+
+template <int LPR>
+cudaError_t launch_segsum_fast(bool interp, bool rm, unsigned grid, cudaStream_t st, TView src, long long src_rows_per_p, const float *wgt,
+                               const int *offs, const int *perm, int M, int R, long long P, int nch, TView dst, int accumulate, TView rmk,
+                               const float *src_rm, int rm_stride)
+{
+    const unsigned rpp = (unsigned)src_rows_per_p, rs = (unsigned)rm_stride;
+    if (interp && rm) return psg_launch_pdl(segsum_fast_kernel<LPR, true, true>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs);
+    if (interp) return psg_launch_pdl(segsum_fast_kernel<LPR, true, false>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs);
+    if (rm) return psg_launch_pdl(segsum_fast_kernel<LPR, false, true>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs);
+    return psg_launch_pdl(segsum_fast_kernel<LPR, false, false>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs);
+}
+
 // the same sums with a warp per destination row (psg_segsum.cuh): rows of >= 32 chunks
 template <int NC>
 __global__ void __launch_bounds__(256) segsum_warp_kernel(const PsgSegsumArgs a)
@@ -594,6 +676,15 @@ int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, c
         if (nch <= 32) err = psg_launch_pdl(segsum_warp_kernel<1>, dim3(grid), dim3(256), 0, st, 1, a);
         else if (nch <= 64) err = psg_launch_pdl(segsum_warp_kernel<2>, dim3(grid), dim3(256), 0, st, 1, a);
         else err = psg_launch_pdl(segsum_warp_kernel<4>, dim3(grid), dim3(256), 0, st, 1, a);
+    } else if (g_psg_segsum_fast && (ncols & 3) == 0 && ((div == 3 && wgt) || (div == 1 && !wgt)) &&
+               src_rows_per_p < (1ll << 24) && (long long)M < (1ll << 30)) {
+        // the two real callers (interpolation backward, gather backward): specialised kernel, same sums
+        const bool interp = div == 3, rmm = src_rm != nullptr;
+        const int lpr = nch <= 4 ? 4 : nch <= 8 ? 8 : nch <= 16 ? 16 : nch <= 32 ? 32 : nch <= 64 ? 64 : 128;
+        const unsigned grid = nblocks(P * R * lpr, 256);
+#define PSG_SF(L) launch_segsum_fast<L>(interp, rmm, grid, st, src, src_rows_per_p, wgt, offs, perm, M, R, P, nch, dst, accumulate, rm, src_rm, rm_stride)
+        err = lpr == 4 ? PSG_SF(4) : lpr == 8 ? PSG_SF(8) : lpr == 16 ? PSG_SF(16) : lpr == 32 ? PSG_SF(32) : lpr == 64 ? PSG_SF(64) : PSG_SF(128);
+#undef PSG_SF
     } else
     if (nch <= 4)
         err = psg_launch_pdl(segsum_kernel<4>, dim3(nblocks(P * R * 4, 256)), dim3(256), 0, st, 1, src, src_rows_per_p, div, wgt,

@@ -474,6 +474,7 @@ extern "C" int psg_set_option(const char *name, int value)
     if (!strcmp(name, "deep")) { g_deep = value; return PSG_OK; }
     if (!strcmp(name, "deep_bn_min")) { psg_deep_tune(value, 0); return PSG_OK; }
     if (!strcmp(name, "deep_items")) { psg_deep_tune(0, value); return PSG_OK; }
+    if (!strcmp(name, "segsum_fast")) { g_psg_segsum_fast = value; return PSG_OK; }
     if (!strcmp(name, "segsum_warp")) { g_psg_segsum_warp = value; return PSG_OK; }
     if (!strcmp(name, "sa_grid_div")) { psg_sa_grid_div(value); return PSG_OK; }
     if (!strcmp(name, "dbg")) { psg_tile_set_dbg(value); return PSG_OK; }

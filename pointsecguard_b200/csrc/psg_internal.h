@@ -69,7 +69,7 @@ int psg_csr_build(const int *keys, long long P, int M, int R, int grp, int *offs
 int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, const int *offs, const int *perm,
                int M, int R, long long P, int ncols, TView dst, int accumulate, const TView *relu_mask, const float *src_rm,
                int rm_stride, cudaStream_t st);
-extern int g_psg_segsum_warp;
+extern int g_psg_segsum_warp, g_psg_segsum_fast;
 int psg_copy_cols(TView src, TView dst, long long rows, int ncols, int accumulate, cudaStream_t st);
 int psg_index_points_rm(const float *pts, const long long *idx, int B, int N, int C, long long M, float *out,
                         cudaStream_t st);

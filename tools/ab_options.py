@@ -11,7 +11,7 @@ from pointsecguard_b200.engine import MLP_TF32
 from pointsecguard_b200.models.pointnet2_sem_seg import get_model
 
 K = int(os.environ.get("AB_STEPS", "50"))
-DEFAULTS = {"deep": 0, "sa_grid_div": 1, "segsum_warp": 0}
+DEFAULTS = {"deep": 0, "sa_grid_div": 1, "segsum_warp": 0, "segsum_fast": 1}
 m = get_model(13); m.load_state_dict(syn.make_state_dict("ssg", init="he")); m = m.cuda().eval(); m.set_mlp_mode(int(os.environ.get("AB_MODE", MLP_TF32)))
 x, labels, mask = bench.make_inputs(16, 0)
 lab = labels.numpy().astype(np.float64)
