@@ -84,6 +84,8 @@ __global__ void pgd_update_kernel(float *__restrict__ adv, const float *__restri
                                   const unsigned char *__restrict__ mask, int B, int C, int N, int c0, int nc,
                                   float alpha_signed, float eps, float lo, float hi)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // launched with programmatic stream serialization
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (long long)B * N) return;
     const int b = (int)(row / N), n = (int)(row % N);
@@ -186,8 +188,8 @@ int psg_dz_cw(TView z, const int *labels, int target, long long rows, int ncls, 
 int psg_pgd_update(float *adv, const float *ori, TView grad, TView feats0, const unsigned char *mask, int B, int C,
                    int N, int c0, int nc, float alpha_signed, float eps, float lo, float hi, cudaStream_t st)
 {
-    pgd_update_kernel<<<nb((long long)B * N, 256), 256, 0, st>>>(adv, ori, grad, feats0, mask, B, C, N, c0, nc,
-                                                                alpha_signed, eps, lo, hi);
+    if (psg_launch_pdl(pgd_update_kernel, dim3(nb((long long)B * N, 256)), dim3(256), 0, st, 1, adv, ori, grad, feats0, mask, B, C, N, c0,
+                       nc, alpha_signed, eps, lo, hi) != cudaSuccess) return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }

@@ -192,6 +192,8 @@ maxpool_bwd_kernel(TView dout, TView outv, const unsigned char *__restrict__ arg
 __global__ void interp_kernel(TView feats, int S, const int *__restrict__ idx, const float *__restrict__ w,
                               long long rows, int N, int nch, TView out)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // launched with programmatic stream serialization
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long row = t % rows;
     const int c = (int)(t / rows);
@@ -627,7 +629,8 @@ int psg_interp(TView feats, int S, const int *idx, const float *w, long long P, 
                cudaStream_t st)
 {
     const long long rows = P * N;
-    interp_kernel<<<nblocks(rows * nch, 256), 256, 0, st>>>(feats, S, idx, w, rows, N, nch, out);
+    if (psg_launch_pdl(interp_kernel, dim3(nblocks(rows * nch, 256)), dim3(256), 0, st, 1, feats, S, idx, w, rows, N, nch, out) != cudaSuccess)
+        return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
