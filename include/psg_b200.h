@@ -315,6 +315,10 @@ int psg_scene_gather(const double *points, int ld, int label_col, const int32_t 
  * "sm_cap" (default 0 = all) = spread persistent launches over at most that many SMs, so that sub-batches
  * enqueued on different streams share the GPU instead of queueing behind each other */
 int psg_set_option(const char *name, int value);
+/* Measurement only (tools/l2_stream_bench.py): `ctas` CTAs each stream `passes` x region_bytes of L2-resident memory into
+ * shared memory with bulk async copies.  mode 0: CTA (or cluster) i reads region i of buf; mode 1: all read region 0.
+ * cluster in {1, 2, 4, 8}: the CTAs of a cluster want the same bytes and fetch them once, by multicast. */
+int psg_debug_l2_stream(const void *buf, int64_t region_bytes, int mode, int cluster, int passes, int ctas, psg_stream_t stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t psg_launch_count(void);
 /* per-kernel-family device timing of the engine (CUDA event pairs on the launching stream);

@@ -96,6 +96,7 @@ _PROTOS = {
     "psg_net_bind": (_i, [_vp, _i, _i, _i, _vp, _sz]),
     "psg_net_set_input": (_i, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "psg_net_copy_input": (_i, [_vp, _vp, _vp]),
+    "psg_debug_l2_stream": (_i, [_vp, _i64, _i, _i, _i, _i, _vp]),
     "psg_net_geometry": (_i, [_vp, _vp, _i, _vp]),
     "psg_net_read_geometry": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "psg_net_forward": (_i, [_vp, _i, _vp, _vp, _vp]),

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                     const uint32_t full = tc::smem_u32(&bar_full[slot]);
                     const uint32_t dst = sW + slot * a.stage_bytes;
                     if (lane == 0) {
-                        tc::mbar_wait(tc::smem_u32(&bar_empty[slot]), ph ^ 1u);
+                        tc::mbar_spin(tc::smem_u32(&bar_empty[slot]), ph ^ 1u);
                         tc::mbar_expect_tx(full, (uint32_t)np * nl * 16);
                     }
                     __syncwarp();

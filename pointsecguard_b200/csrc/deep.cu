@@ -32,8 +32,8 @@ namespace {
 
 constexpr int kMaxPhases = PSG_DEEP_MAX_PHASES;
 constexpr int kMaxStages = 12;
-constexpr int kBlk = 8;                       // chunk planes (4 floats of K each) per stage
-constexpr int kABytes = kBlk * 2048;          // 16 KB
+constexpr int kBlk = 16;                      // chunk planes (4 floats of K each) per stage (gemm_tc.cu: the producer's per-stage cost bounds the K loop)
+constexpr int kABytes = kBlk * 2048;          // 32 KB
 constexpr int kThreads = 192;
 constexpr int kRingBytes = 200 * 1024;
 constexpr int kSmemBytes = kRingBytes + 1024;

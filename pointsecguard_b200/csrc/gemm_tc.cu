@@ -18,9 +18,11 @@
 namespace {
 
 constexpr int kMaxStages = 12;
-constexpr int kBlk = 8;                       // chunk planes (4 floats of K each) per stage
+// chunk planes (4 floats of K each) per stage: 16 (32 KB of activations) -- the producer's per-stage bookkeeping (wait,
+// expect_tx, issue: ~350 ns, tools/l2_stream_bench.py) bounds the K loop, not the L2 (>= 100 GB/s per SM), so stages are
+// as large as the ring allows; the 3xTF32 kernel keeps 8 (its stages hold A, A_lo, W_hi and W_lo)
+template <bool X3> struct StageK { static constexpr int value = X3 ? 8 : 16; };
 constexpr int kBNMax = 128;
-constexpr int kABytes = kBlk * 2048;          // 16 KB
 constexpr int kThreads = 192;
 constexpr int kRingBytes = 200 * 1024;        // operand ring: as many stages as fit (the K loop is a latency chain)
 constexpr int kSmemBytes = kRingBytes + 1024;
@@ -41,6 +43,8 @@ template <int EPI, bool X3>
 __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn_tile, int kStages, long long *trace,
                                                            const __grid_constant__ CUtensorMap wmap, int use_map)
 {
+    constexpr int kBlk = StageK<X3>::value;
+    constexpr int kABytes = kBlk * 2048;
     long long *tr = (trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) ? trace : nullptr;   // first epilogue thread
     if (tr) tr[0] = gtimer();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             const uint32_t full = tc::smem_u32(&bar_full[s]);
             if (lane == 0) {
-                tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
+                tc::mbar_spin(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
                 tc::mbar_expect_tx(full, (uint32_t)(n * 2048 + (X3 ? 2 : 1) * n * BN * 16));
             }
             __syncwarp();
@@ -248,6 +252,8 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
 template <int EPI, bool X3>
 int launch(const PsgGemmArgs &g, cudaStream_t st)
 {
+    constexpr int kBlk = StageK<X3>::value;
+    constexpr int kABytes = kBlk * 2048;
     static PsgDeviceOnce attr_once;
     if (attr_once.need()) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<EPI, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)

@@ -474,6 +474,9 @@ extern "C" int psg_set_option(const char *name, int value)
     if (!strcmp(name, "deep")) { g_deep = value; return PSG_OK; }
     if (!strcmp(name, "deep_bn_min")) { psg_deep_tune(value, 0); return PSG_OK; }
     if (!strcmp(name, "deep_items")) { psg_deep_tune(0, value); return PSG_OK; }
+    if (!strcmp(name, "stream_stages")) { psg_stream_tune(value, 0, 0); return PSG_OK; }
+    if (!strcmp(name, "stream_stage_bytes")) { psg_stream_tune(0, value, 0); return PSG_OK; }
+    if (!strcmp(name, "stream_rings")) { psg_stream_tune(0, 0, value); return PSG_OK; }
     if (!strcmp(name, "segsum_fast")) { g_psg_segsum_fast = value; return PSG_OK; }
     if (!strcmp(name, "segsum_warp")) { g_psg_segsum_warp = value; return PSG_OK; }
     if (!strcmp(name, "sa_grid_div")) { psg_sa_grid_div(value); return PSG_OK; }

@@ -76,6 +76,8 @@ int psg_index_points_rm(const float *pts, const long long *idx, int B, int N, in
 // train.cu
 int psg_repack_weights(const float *w, const float *b, int cout, int cin, int kpad, int npad, int nwf, int nwb, float *wf,
                        float *wb, float *wf_c, float *wb_c, float *bias, float comp, cudaStream_t st);
+// streambench.cu (measurement only)
+void psg_stream_tune(int stages, int stage_bytes, int rings);
 // gemm_simt.cu / gemm_tc.cu
 int psg_gemm_simt(const PsgGemmArgs &g, cudaStream_t st);
 int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st);
