@@ -99,11 +99,13 @@ def _nb_loop(atk, images, labels, target, mask):
                 fork2.record(cur)
                 side.wait_event(fork2)
                 tail.use_stream(side)
-                tail.set_input(src)
-                tail.geometry(starts[:, head:].contiguous())
-                tail_ready = torch.cuda.Event()
-                tail_ready.record(side)
-                tail.use_stream(None)
+                try:
+                    tail.set_input(src)
+                    tail.geometry(starts[:, head:].contiguous())
+                    tail_ready = torch.cuda.Event()
+                    tail_ready.record(side)
+                finally:
+                    tail.use_stream(None)
                 eng.geometry(starts[:, :head].contiguous())
             else:
                 for e, p in zip(engs, parts):

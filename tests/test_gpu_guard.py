@@ -14,10 +14,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("arch", ["ssg", "msg"])
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "x3"])
 def test_workspace_guard_bands_survive_whole_attacks(monkeypatch, arch, mode):
     from pointsecguard_b200 import torchattacks
-    from pointsecguard_b200.engine import MLP_FP32, MLP_TF32
+    from pointsecguard_b200.engine import MLP_FP32, MLP_TF32, MLP_TF32X3
     monkeypatch.setenv("PSG_GUARD", "8")
     if arch == "ssg":
         from pointsecguard_b200.models.pointnet2_sem_seg import get_model
@@ -26,7 +26,7 @@ def test_workspace_guard_bands_survive_whole_attacks(monkeypatch, arch, mode):
     m = get_model(13)
     m.load_state_dict(syn.load_checkpoint(arch))
     m = m.cuda().eval()
-    m.set_mlp_mode(MLP_TF32 if mode == "tf32" else MLP_FP32)
+    m.set_mlp_mode({"fp32": MLP_FP32, "tf32": MLP_TF32, "x3": MLP_TF32X3}[mode])
     try:
         for B, N, kind in ((3, 4096, "uniform"), (2, 2000, "clustered"), (1, 5000, "duplicates")):
             x = syn.make_blocks(B, N, 4, kind).cuda()
@@ -39,6 +39,9 @@ def test_workspace_guard_bands_survive_whole_attacks(monkeypatch, arch, mode):
                 assert m.engine(x.device).guard_intact(), (B, N, kind, compact, "NB")
                 torchattacks.tar_NB_attack(m, eps=0.5, alpha=0.1, iters=2, target=7, mask=labels == 11)(x, lab)
                 assert m.engine(x.device).guard_intact(), (B, N, kind, compact, "tar-NB")
+                # long enough for the geometry head start: the second engine's workspace is guarded too
+                torchattacks.NB_attack(m, eps=0.1, alpha=0.02, iters=16)(x, lab)
+                assert m.engine(x.device).guard_intact() and m._tail is not None and m._tail.guard_intact(), (B, N, kind, compact, "head start")
                 if arch == "ssg":
                     torchattacks.NU_attack(m, c=0.1, kappa=0, steps=2, lr=0.01)(x, lab)
                     assert m.engine(x.device).guard_intact(), (B, N, kind, compact, "NU")
