@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     const int szW0 = a.gpad * a.n0 * 4, szW1 = a.n0 * a.n1 * 4, szW2 = (a.n1 * a.n2 * 4 + 1023) & ~1023;
     // per tile ONE operand buffer: a layer's MMA has completed before its epilogue runs, so the
     // epilogue overwrites the layer's own input in place (gather -> Y0 -> Y1)
-    const int szG = max(a.gpad, max(a.n0, a.n1)) * 512;
+    // (compacted rows: the segmented pool borrows 4 KB of the buffer per warp, so narrow branches get at least 16 KB)
+    const int szG = CP ? max(max(a.gpad, max(a.n0, a.n1)) * 512, 16384) : max(a.gpad, max(a.n0, a.n1)) * 512;
     unsigned char *pW0 = base, *pW1 = pW0 + szW0, *pW2 = pW1 + szW1, *pG = pW2 + szW2;
     const uint32_t sW0 = sbase, sW1 = sW0 + szW0, sW2 = sW1 + szW1, sG = sW2 + szW2;
 
@@ -554,10 +555,11 @@ constexpr size_t kSmemPerCtaMax = 224 * 1024;
 
 inline size_t r1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
 inline int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
-inline size_t fwd_smem(int gpad, int n0, int n1, int n2, int ng)
+inline size_t fwd_smem(int gpad, int n0, int n1, int n2, int ng, bool cp = false)
 {
-    return (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4) +
-           (size_t)ng * (size_t)max3(gpad, n0, n1) * 512 + 1024;
+    size_t g = (size_t)max3(gpad, n0, n1) * 512;
+    if (cp && g < 16384) g = 16384;              // the segmented pool's per-warp scratch lives in the operand buffer
+    return (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4) + (size_t)ng * g + 1024;
 }
 // columns of dY2 scattered per pass: the largest 16-multiple divisor of n2 not wider than the hidden layers
 // (the operand buffer has to hold those anyway)
@@ -696,8 +698,7 @@ bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2)
 // the segmented pool of the compacted-row kernels borrows 4 KB of the tile's operand buffer per warp
 bool psg_sa_compactable(int K, int gpad, int n0, int n1, int n2)
 {
-    if (!psg_sa_fusable(K, gpad, n0, n1, n2)) return false;
-    return max3(gpad, n0, n1) * 512 >= 16384;
+    return psg_sa_fusable(K, gpad, n0, n1, n2) && fwd_smem(gpad, n0, n1, n2, 1, true) <= kSmemPerCtaMax;
 }
 
 size_t psg_sa_mask_words(long long rows, int n)
@@ -721,7 +722,7 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.n2 ? a.n0 : a.n2) : (a.n1 > a.n2 ? a.n1 : a.n2));
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
     if (cp && !psg_sa_compactable(f.K, a.gpad, a.n0, a.n1, a.n2)) return PSG_EUNSUPPORTED;
-    auto smem_of = [&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g); };
+    auto smem_of = [&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g, cp); };
     const Pick pk = cp ? cached_pick(2, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern_cp, smem_of, gc)
                   : f.K == 32 ? cached_pick(0, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern<32>, smem_of, gc)
                               : cached_pick(0, 16, a.gpad, a.n0, a.n1, a.n2, fwd_kern<16>, smem_of, gc);
