@@ -444,13 +444,13 @@ segsum_kernel(TView src, long long src_rows_per_p, int div, const float *__restr
 // instruction-issue bound -- 66 % issue utilisation at 38 % occupancy, 87 warp instructions per bucket entry of which 4 are
 // the FFMAs: a run-time integer division per entry, 64-bit address products, per-entry tail / weight / mirror branches):
 //   INTERP: backward of the 3-NN interpolation (slot / 3, weighted, fmaf);  !INTERP: backward of the grouping gather
-//   (slot, unweighted, add);  RM: sources are the row-major mirror.  No tail columns (ncols % 4 == 0).  Offsets inside a
+//   (slot, unweighted, add);  RM: sources are the row-major mirror.  Offsets inside a
 // problem are 32-bit.  Same order of additions, same bits.
 template <int LPR, bool INTERP, bool RM>
 __global__ void __launch_bounds__(256)
 segsum_fast_kernel(TView src, unsigned src_rows_per_p, const float *__restrict__ wgt, const int *__restrict__ offs,
                    const int *__restrict__ perm, int M, int R, long long P, int nch, TView dst, int accumulate, TView rmask,
-                   const float *__restrict__ src_rm, unsigned rm_stride)
+                   const float *__restrict__ src_rm, unsigned rm_stride, int tail_cols)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");          // launched with programmatic stream serialization
@@ -470,7 +470,8 @@ segsum_fast_kernel(TView src, unsigned src_rows_per_p, const float *__restrict__
     const float *tlb = RM ? nullptr : src.base + ((size_t)((p * src_rows_per_p) >> 7) * src.wchunks + src.c0) * 512;
     const unsigned wch = (unsigned)src.wchunks;
     for (int c = lane; c < nch; c += LPR) {
-        float4 acc = accumulate ? tv_ld(dst, wid, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 acc0 = accumulate ? tv_ld(dst, wid, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = acc0;
         constexpr int U = 4;          // entries in flight (8: measured slower; 8 CTAs per SM at 32 registers: within noise)
         for (int e = lo; e < hi; e += U) {
             unsigned srow[U]; float4 v[U]; float sc[U];
@@ -500,6 +501,11 @@ segsum_fast_kernel(TView src, unsigned src_rows_per_p, const float *__restrict__
                 }
             }
         }
+        if (tail_cols && c == nch - 1) {           // columns past the tensor's width in the last chunk contribute nothing:
+            if (tail_cols < 2) acc.y = acc0.y;     // what the generic kernel gets by zeroing them in every entry
+            if (tail_cols < 3) acc.z = acc0.z;
+            acc.w = acc0.w;
+        }
         if (rmask.base) {                          // gradient w.r.t. the pre-activation of a ReLU layer
             float4 y = tv_ld(rmask, wid, c);
             acc.x = y.x > 0.f ? acc.x : 0.f; acc.y = y.y > 0.f ? acc.y : 0.f;
@@ -512,13 +518,13 @@ segsum_fast_kernel(TView src, unsigned src_rows_per_p, const float *__restrict__
 template <int LPR>
 cudaError_t launch_segsum_fast(bool interp, bool rm, unsigned grid, cudaStream_t st, TView src, long long src_rows_per_p, const float *wgt,
                                const int *offs, const int *perm, int M, int R, long long P, int nch, TView dst, int accumulate, TView rmk,
-                               const float *src_rm, int rm_stride)
+                               const float *src_rm, int rm_stride, int tail)
 {
     const unsigned rpp = (unsigned)src_rows_per_p, rs = (unsigned)rm_stride;
-    if (interp && rm) return psg_launch_pdl(segsum_fast_kernel<LPR, true, true>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs);
-    if (interp) return psg_launch_pdl(segsum_fast_kernel<LPR, true, false>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs);
-    if (rm) return psg_launch_pdl(segsum_fast_kernel<LPR, false, true>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs);
-    return psg_launch_pdl(segsum_fast_kernel<LPR, false, false>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs);
+    if (interp && rm) return psg_launch_pdl(segsum_fast_kernel<LPR, true, true>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs, tail);
+    if (interp) return psg_launch_pdl(segsum_fast_kernel<LPR, true, false>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs, tail);
+    if (rm) return psg_launch_pdl(segsum_fast_kernel<LPR, false, true>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs, tail);
+    return psg_launch_pdl(segsum_fast_kernel<LPR, false, false>, dim3(grid), dim3(256), 0, st, 1, src, rpp, wgt, offs, perm, M, R, P, nch, dst, accumulate, rmk, src_rm, rs, tail);
 }
 
 // the same sums with a warp per destination row (psg_segsum.cuh): rows of >= 32 chunks
@@ -679,13 +685,13 @@ int psg_segsum(TView src, long long src_rows_per_p, int div, const float *wgt, c
         if (nch <= 32) err = psg_launch_pdl(segsum_warp_kernel<1>, dim3(grid), dim3(256), 0, st, 1, a);
         else if (nch <= 64) err = psg_launch_pdl(segsum_warp_kernel<2>, dim3(grid), dim3(256), 0, st, 1, a);
         else err = psg_launch_pdl(segsum_warp_kernel<4>, dim3(grid), dim3(256), 0, st, 1, a);
-    } else if (g_psg_segsum_fast && (ncols & 3) == 0 && ((div == 3 && wgt) || (div == 1 && !wgt)) &&
+    } else if (g_psg_segsum_fast && ((div == 3 && wgt) || (div == 1 && !wgt)) &&
                src_rows_per_p < (1ll << 24) && (long long)M < (1ll << 30)) {
         // the two real callers (interpolation backward, gather backward): specialised kernel, same sums
         const bool interp = div == 3, rmm = src_rm != nullptr;
         const int lpr = nch <= 4 ? 4 : nch <= 8 ? 8 : nch <= 16 ? 16 : nch <= 32 ? 32 : nch <= 64 ? 64 : 128;
         const unsigned grid = nblocks(P * R * lpr, 256);
-#define PSG_SF(L) launch_segsum_fast<L>(interp, rmm, grid, st, src, src_rows_per_p, wgt, offs, perm, M, R, P, nch, dst, accumulate, rm, src_rm, rm_stride)
+#define PSG_SF(L) launch_segsum_fast<L>(interp, rmm, grid, st, src, src_rows_per_p, wgt, offs, perm, M, R, P, nch, dst, accumulate, rm, src_rm, rm_stride, ncols & 3)
         err = lpr == 4 ? PSG_SF(4) : lpr == 8 ? PSG_SF(8) : lpr == 16 ? PSG_SF(16) : lpr == 32 ? PSG_SF(32) : lpr == 64 ? PSG_SF(64) : PSG_SF(128);
 #undef PSG_SF
     } else
