@@ -21,7 +21,6 @@ constexpr int kMaxStages = 12;
 // chunk planes (4 floats of K each) per stage: 16 (32 KB of activations) -- the producer's per-stage bookkeeping (wait,
 // expect_tx, issue: ~350 ns, tools/l2_stream_bench.py) bounds the K loop, not the L2 (>= 100 GB/s per SM), so stages are
 // as large as the ring allows; the 3xTF32 kernel keeps 8 (its stages hold A, A_lo, W_hi and W_lo)
-template <bool X3> struct StageK { static constexpr int value = X3 ? 8 : 16; };
 constexpr int kBNMax = 128;
 constexpr int kThreads = 192;
 constexpr int kRingBytes = 200 * 1024;        // operand ring: as many stages as fit (the K loop is a latency chain)
@@ -39,11 +38,11 @@ __device__ __forceinline__ long long gtimer()
 // loop, write A_lo = A - A_hi (exact in fp32) next to every stage as it lands; the weights arrive pre-split from the host
 // (W_hi = nearest TF32 of W, W_lo = nearest TF32 of W - W_hi).  Three MMAs per K step accumulate A_lo W_hi + A_hi W_lo +
 // A_hi W_hi into the same TMEM accumulator; the dropped A_lo W_lo term is 2^-22 relative.
-template <int EPI, bool X3>
+template <int EPI, bool X3, int KB>
 __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn_tile, int kStages, long long *trace,
                                                            const __grid_constant__ CUtensorMap wmap, int use_map)
 {
-    constexpr int kBlk = StageK<X3>::value;
+    constexpr int kBlk = KB;
     constexpr int kABytes = kBlk * 2048;
     long long *tr = (trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) ? trace : nullptr;   // first epilogue thread
     if (tr) tr[0] = gtimer();
@@ -249,21 +248,20 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
     if (warp == 1) tc::tmem_dealloc(tmem, ncols);
 }
 
-template <int EPI, bool X3>
-int launch(const PsgGemmArgs &g, cudaStream_t st)
+int g_big_kb8 = 1;      // psg_set_option "gemm_two_ctas": 0 keeps one CTA per SM behind the full ring for large layers
+int g_nst_plain = 2, g_nst_x3 = 1, g_big_ctas = 148;      // ring depth of the many-tile layers, and what "many" means (measured: MSG B = 64 275 -> 295 steps/s, 3xTF32 mode 409 -> 536)
+
+template <int EPI, bool X3, int KB>
+int launch_kb(const PsgGemmArgs &g, int bn, cudaStream_t st)
 {
-    constexpr int kBlk = StageK<X3>::value;
+    constexpr int kBlk = KB;
     constexpr int kABytes = kBlk * 2048;
     static PsgDeviceOnce attr_once;
     if (attr_once.need()) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<EPI, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tc_kernel<EPI, X3, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
             return PSG_ECUDA;
         attr_once.mark();
     }
-    // few row tiles (the deep levels): narrower column tiles spread the layer over more SMs, and the smaller
-    // B stages let more of the K loop be in flight at once
-    int bn = kBNMax;
-    while (bn > 32 && g.mtiles * ((g.nout_pad + bn - 1) / bn) < 96) bn >>= 1;
     const int stage_bytes = (X3 ? 2 : 1) * (kABytes + kBlk * bn * 16);
     int nst = kRingBytes / stage_bytes;
     if (nst > kMaxStages) nst = kMaxStages;
@@ -271,6 +269,10 @@ int launch(const PsgGemmArgs &g, cudaStream_t st)
     // then fit several CTAs per SM instead of one behind a 200 KB ring, and their prologues overlap
     const int kstages = (g.k1chunks + kBlk - 1) / kBlk + (g.k2chunks + kBlk - 1) / kBlk;
     if (nst > kstages) nst = kstages;
+    // many tiles and a long K loop: three stages per CTA so that TWO CTAs share an SM -- one's epilogue and prologue run
+    // under the other's K loop (a single CTA behind the whole ring serialises them: MSG sa4, 256 row tiles x K = 512)
+    if (!X3 && KB == 8 && nst > g_nst_plain) nst = g_nst_plain;
+    if (X3 && g_big_kb8 && bn <= 64 && nst > g_nst_x3 && (long long)g.mtiles * ((g.nout_pad + bn - 1) / bn) > g_big_ctas) nst = g_nst_x3;
     const size_t smem = (size_t)nst * stage_bytes + 1024;
     dim3 grid((unsigned)g.mtiles, (unsigned)((g.nout_pad + bn - 1) / bn));
     // weights [K/4][Nw][4] as a tiled TMA source: boxes of kBlk planes x bn columns (K is a multiple of 16, i.e. of
@@ -279,12 +281,42 @@ int launch(const PsgGemmArgs &g, cudaStream_t st)
     memset(&wmap, 0, sizeof(wmap));
     const long long planes = g.k1chunks + g.k2chunks;
     const int use_map = (!X3 && planes % kBlk == 0 && psg_weight_tmap(&wmap, g.W, planes, g.Nw, kBlk, bn)) ? 1 : 0;
-    if (psg_launch_pdl(gemm_tc_kernel<EPI, X3>, grid, dim3(kThreads), smem, st, 1, g, bn, nst, psg_tile_trace_slot(), wmap, use_map) != cudaSuccess) return PSG_ECUDA;
+    if (psg_launch_pdl(gemm_tc_kernel<EPI, X3, KB>, grid, dim3(kThreads), smem, st, 1, g, bn, nst, psg_tile_trace_slot(), wmap, use_map) != cudaSuccess) return PSG_ECUDA;
     PSG_LAUNCH_CHECK();
     return PSG_OK;
 }
 
+template <int EPI, bool X3>
+int launch(const PsgGemmArgs &g, cudaStream_t st)
+{
+    // few row tiles (the deep levels): narrower column tiles spread the layer over more SMs, and the smaller
+    // B stages let more of the K loop be in flight at once
+    int bn = kBNMax;
+    while (bn > 32 && g.mtiles * ((g.nout_pad + bn - 1) / bn) < 96) bn >>= 1;
+    if (X3) {
+        // 3xTF32 stages hold A, A_lo, W_hi and W_lo: with 128-column tiles one CTA fills an SM.  Layers with far more
+        // tiles than SMs take 64-column tiles and a two-stage ring instead, so that two CTAs overlap on every SM.
+        if (g_big_kb8 && bn > 64 && (long long)g.mtiles * ((g.nout_pad + bn - 1) / bn) > g_big_ctas) bn = 64;
+        return launch_kb<EPI, X3, 8>(g, bn, st);
+    }
+    // 32 KB activation stages by default (the producer's per-stage cost bounds the K loop); 16 KB stages x 3 when the
+    // layer has far more tiles than SMs and its ring would otherwise leave one CTA per SM
+    const long long ctas = (long long)g.mtiles * ((g.nout_pad + bn - 1) / bn);
+    const int kstages16 = (g.k1chunks + 15) / 16 + (g.k2chunks + 15) / 16;
+    const long long ring16 = (long long)(kstages16 < kRingBytes / (32768 + 16 * bn * 16) ? kstages16 : kRingBytes / (32768 + 16 * bn * 16)) * (32768 + 16 * bn * 16);
+    if (g_big_kb8 && ctas > g_big_ctas && ring16 > 112 * 1024) return launch_kb<EPI, false, 8>(g, bn, st);
+    return launch_kb<EPI, false, 16>(g, bn, st);
+}
+
 }  // namespace
+
+void psg_gemm_tc_two_ctas(int on) { g_big_kb8 = on; }
+void psg_gemm_tc_tune(int nst_plain, int nst_x3, int big_ctas)
+{
+    if (nst_plain > 0) g_nst_plain = nst_plain;
+    if (nst_x3 > 0) g_nst_x3 = nst_x3;
+    if (big_ctas > 0) g_big_ctas = big_ctas;
+}
 
 int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st)
 {

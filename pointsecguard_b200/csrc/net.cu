@@ -477,6 +477,10 @@ extern "C" int psg_set_option(const char *name, int value)
     if (!strcmp(name, "stream_stages")) { psg_stream_tune(value, 0, 0); return PSG_OK; }
     if (!strcmp(name, "stream_stage_bytes")) { psg_stream_tune(0, value, 0); return PSG_OK; }
     if (!strcmp(name, "stream_rings")) { psg_stream_tune(0, 0, value); return PSG_OK; }
+    if (!strcmp(name, "gemm_nst_plain")) { psg_gemm_tc_tune(value, 0, 0); return PSG_OK; }
+    if (!strcmp(name, "gemm_nst_x3")) { psg_gemm_tc_tune(0, value, 0); return PSG_OK; }
+    if (!strcmp(name, "gemm_big_ctas")) { psg_gemm_tc_tune(0, 0, value); return PSG_OK; }
+    if (!strcmp(name, "gemm_two_ctas")) { psg_gemm_tc_two_ctas(value); return PSG_OK; }
     if (!strcmp(name, "segsum_fast")) { g_psg_segsum_fast = value; return PSG_OK; }
     if (!strcmp(name, "segsum_warp")) { g_psg_segsum_warp = value; return PSG_OK; }
     if (!strcmp(name, "sa_grid_div")) { psg_sa_grid_div(value); return PSG_OK; }

@@ -81,6 +81,8 @@ void psg_stream_tune(int stages, int stage_bytes, int rings);
 // gemm_simt.cu / gemm_tc.cu
 int psg_gemm_simt(const PsgGemmArgs &g, cudaStream_t st);
 int psg_gemm_tc(const PsgGemmArgs &g, cudaStream_t st);
+void psg_gemm_tc_two_ctas(int on);
+void psg_gemm_tc_tune(int nst_plain, int nst_x3, int big_ctas);
 // deep.cu: the per-layer FP levels as one persistent kernel -- a recorder collects the phases, flush launches them
 #define PSG_DEEP_MAX_PHASES 10
 void psg_deep_begin();
