@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(PsgGemmArgs g, int bn
         auto issue_w = [&](int s, int c, int kglob, int n, uint32_t full) {
             if (X3) {
                 // lanes 1..n: the hi plane, lanes 9..8+n: the lo plane of the same K chunk
-                const int j = (lane - 1) & 7;
-                if (lane >= 1 && lane <= 16 && j < n) {
-                    const float *w = lane <= 8 ? g.W : g.Wlo;
-                    tc::bulk_g2s(sB + s * kBBytes + (lane <= 8 ? 0 : kBHalf) + j * BN * 16, w + ((size_t)(kglob + c + j) * g.Nw + n0) * 4,
+                const int j = (lane - 1) % kBlk;
+                if (lane >= 1 && lane <= 2 * kBlk && j < n) {
+                    const float *w = lane <= kBlk ? g.W : g.Wlo;
+                    tc::bulk_g2s(sB + s * kBBytes + (lane <= kBlk ? 0 : kBHalf) + j * BN * 16, w + ((size_t)(kglob + c + j) * g.Nw + n0) * 4,
                                  (uint32_t)(BN * 16), full);
                 }
             } else if (use_map && BN == bn_tile) {
