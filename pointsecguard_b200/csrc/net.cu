@@ -31,6 +31,9 @@ static int g_fp_min_tiles = 48;
 static int g_sa_compact = 1;
 // the per-layer FP levels (fp4 / fp3 at B = 16) and the segmented sums around them run as ONE persistent kernel per
 // direction (deep.cu: phase list + grid barrier) instead of a launch per layer; psg_set_option "deep" 0 restores the launches
+// mode 2 (3xTF32): the narrow SA branches run as fused kernels too when their hi + lo weights and operand buffers fit
+// (psg_set_option "x3_fused" 0: every layer of mode 2 goes through the per-layer GEMM)
+static int g_x3_fused = 1;
 static int g_deep = 0;      // bit 0: on; bit 1: the backward kernel starts with the segmented sum that feeds its first level (OFF by default: measured slower)
 
 // ------------------------------------------------------------------------------------------------
@@ -472,6 +475,7 @@ extern "C" int psg_set_option(const char *name, int value)
     if (!strcmp(name, "sa_ng")) { psg_sa_force_ng(value); return PSG_OK; }
     if (!strcmp(name, "sa_compact")) { g_sa_compact = value != 0; return PSG_OK; }
     if (!strcmp(name, "deep")) { g_deep = value; return PSG_OK; }
+    if (!strcmp(name, "x3_fused")) { g_x3_fused = value; return PSG_OK; }
     if (!strcmp(name, "deep_bn_min")) { psg_deep_tune(value, 0); return PSG_OK; }
     if (!strcmp(name, "deep_items")) { psg_deep_tune(0, value); return PSG_OK; }
     if (!strcmp(name, "stream_stages")) { psg_stream_tune(value, 0, 0); return PSG_OK; }
@@ -706,10 +710,10 @@ extern "C" int psg_net_geometry(psg_net *n, const int32_t *starts, int T, psg_st
             PSG_RUN(PF_CSR, psg_csr_build(L.br[b].ball, P, S * L.br[b].K, R, L.br[b].K, L.br[b].csr_off, L.br[b].csr_perm, n->csr_ws, st));
             // compacted rows of the fused branches (skipped when the coordinates move: the geometric-gradient kernels
             // read the padded [S][K] layout)
-            if (L.br[b].compactable && g_sa_compact && n->mode == 1 && !n->xyz_grad)
+            if (L.br[b].compactable && g_sa_compact && n->mode >= 1 && !n->xyz_grad)
                 PSG_RUN(PF_CSR, psg_sa_compact_build(L.br[b].ball, L.br[b].csr_perm, T, B, S, L.br[b].K, L.br[b].cp, st));
         }
-        n->compact_valid = g_sa_compact && n->mode == 1 && !n->xyz_grad;
+        n->compact_valid = g_sa_compact && n->mode >= 1 && !n->xyz_grad;
     }
     for (int f = 0; f < 4; ++f) {
         FpLevel &F = n->fp[f];
@@ -754,6 +758,16 @@ extern "C" int psg_net_read_geometry(const psg_net *n, int what, int level, int 
 
 static inline TView tv(float *p, int width, int col0 = 0) { return TView{p, width / 4, col0 / 4}; }
 
+// does the branch run as one kernel per direction in the network's current mode?
+static inline bool branch_fused_now(const psg_net *n, const Branch &Br)
+{
+    if (n->mode == 1) return Br.fused || Br.streamed;
+    if (n->mode == 2)
+        return g_x3_fused && Br.fused && Br.compactable && n->compact_valid && !n->xyz_grad &&
+               psg_sa_fusable_x3(Br.K, Br.gpad, Br.mlp[0]->npad, Br.mlp[1]->npad, Br.mlp[2]->npad);
+    return false;
+}
+
 static PsgSaFused sa_fused_desc(psg_net *n, int l, int b, int t)
 {
     SaLevel &L = n->sa[l - 1];
@@ -766,10 +780,13 @@ static PsgSaFused sa_fused_desc(psg_net *n, int l, int b, int t)
     f.new_xyz = lvl_xyz(n, l, t); f.idx = Br.ball + (size_t)t * B * S * Br.K;
     f.rows = (long long)B * S * Br.K; f.S = S;
     f.gpad = Br.gpad;
+    const bool x3 = n->mode == 2;
     for (int j = 0; j < 3; ++j) {
         f.n[j] = Br.mlp[j]->npad;
-        f.wf[j] = w_fwd(Br.mlp[j], 1); f.nwf[j] = Br.mlp[j]->nwf; f.bias[j] = Br.mlp[j]->bias;      // (fused = tcgen05 only)
-        f.wb[j] = w_bwd(Br.mlp[j], 1); f.nwb[j] = Br.mlp[j]->nwb;
+        f.wf[j] = w_fwd(Br.mlp[j], x3 ? 2 : 1); f.nwf[j] = Br.mlp[j]->nwf; f.bias[j] = Br.mlp[j]->bias;      // (fused = tcgen05 only)
+        f.wb[j] = w_bwd(Br.mlp[j], x3 ? 2 : 1); f.nwb[j] = Br.mlp[j]->nwb;
+        f.wf_lo[j] = x3 ? Br.mlp[j]->wf_lo : nullptr;     // mode 2: 3xTF32 inside the fused kernels (sa_fused.cu)
+        f.wb_lo[j] = x3 ? Br.mlp[j]->wb_lo : nullptr;
     }
     f.m0 = Br.m0; f.m1 = Br.m1;
     f.out = tv(n->feats[l], n->wfeat[l], Br.col0); f.arg = Br.arg;
@@ -838,7 +855,7 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
         for (int b = 0; b < L.nbr; ++b) {
             Branch &Br = L.br[b];
             const long long rows = (long long)B * S * Br.K;
-            if (mode == 1 && (Br.fused || Br.streamed)) {
+            if (branch_fused_now(n, Br)) {
                 PsgSaFused f = sa_fused_desc(n, l, b, t);
                 PSG_RUN(PF_SA_FWD, Br.fused ? psg_sa_fused_fwd(f, st) : psg_sa_stream_fwd(f, st));
                 continue;
@@ -1077,7 +1094,7 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
             Branch &Br = L.br[b];
             const long long rows = (long long)B * S * Br.K;
             const int cw = Br.mlp[Br.nl - 1]->npad;
-            if (n->mode == 1 && (Br.fused || Br.streamed)) {
+            if (branch_fused_now(n, Br)) {
                 PsgSaFused f = sa_fused_desc(n, l, b, t);
                 // feature columns only, unless the coordinate gradient is wanted too
                 const int gcols = n->xyz_grad ? Br.gpad : round_up(D, 16);

@@ -127,8 +127,11 @@ struct PsgSaFused {
     // compacted rows (compact.cu), all null for the padded [S][K] layout: per compact row its source point / centroid, and
     // the forward's tile count in device memory (only the device knows how many real hits there are)
     const int *crow_src, *crow_g, *ntiles_dev;
+    // 3xTF32 (mode 2): TF32 residuals of wf / wb in the same packings (wf / wb are then the "hi" parts); all null otherwise
+    const float *wf_lo[3], *wb_lo[3];
 };
 bool psg_sa_fusable(int K, int gpad, int n0, int n1, int n2);
+bool psg_sa_fusable_x3(int K, int gpad, int n0, int n1, int n2);
 void psg_sa_grid_div(int d);       // A/B switch: grid of the compacted-row kernels = padded tiles / d (default 1)
 void psg_sa_force_ng(int ng);      // A/B switch: tiles in flight per CTA of the fused SA kernels (0 = automatic)
 size_t psg_sa_mask_words(long long rows, int n);

@@ -56,6 +56,32 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t sA, uint32_t
     }
 }
 
+// 3xTF32 (X3 kernels): kind::tf32 reads the top 19 bits of an operand, so a value as it lies in shared memory is its own
+// "hi" part; lo4 is what the hardware drops (exact in fp32), written to a second operand buffer.  Three MMAs per K step
+// -- A_lo W_hi + A_hi W_lo + A_hi W_hi -- give fp32-grade products (gemm_tc.cu has the per-layer twin).
+__device__ __forceinline__ float4 lo4(float4 a)
+{
+    float4 l;
+    l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+    l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+    l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+    l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+    return l;
+}
+__device__ __forceinline__ void issue_layer_x3(uint32_t tmem, uint32_t sA, uint32_t sAl, uint32_t sBh, uint32_t sBl, int planes, int n,
+                                               uint32_t acc = 0)
+{
+    const uint32_t idesc = tc::idesc_tf32(128, n);
+    for (int j = 0; j < planes; j += 2) {
+        const uint64_t ad = tc::smem_desc(sA + j * 2048, 2048, 128), al = tc::smem_desc(sAl + j * 2048, 2048, 128);
+        const uint64_t bh = tc::smem_desc(sBh + j * n * 16, (uint32_t)(n * 16), 128), bl = tc::smem_desc(sBl + j * n * 16, (uint32_t)(n * 16), 128);
+        tc::mma_tf32(tmem, al, bh, idesc, acc);      // small terms first
+        tc::mma_tf32(tmem, ad, bl, idesc, 1u);
+        tc::mma_tf32(tmem, ad, bh, idesc, 1u);
+        acc = 1;
+    }
+}
+
 __device__ __forceinline__ long long gtimer()
 {
     long long t;
@@ -74,11 +100,13 @@ struct SaFwdArgs {
     int ntiles;
     long long *trace;
     const int *crow_src, *crow_g, *ntiles_dev;      // compacted rows (compact.cu); CP kernels only
+    const float *w0l, *w1l, *w2l;                   // X3 kernels: the TF32 residuals of w0..w2 (same packing)
 };
 
 // accumulator -> bias + ReLU -> next A operand in shared memory (+ one ReLU bit per element)
+template <bool X3 = false>
 __device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n, const float *bias,
-                                                      unsigned char *dst, unsigned *mask_tile, int row)
+                                                      unsigned char *dst, unsigned *mask_tile, int row, unsigned char *dst_lo = nullptr)
 {
     int c = 0;
     for (; c + 32 <= n; c += 32) {
@@ -86,8 +114,11 @@ __device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n,
         tc::tmem_ld32(tmem_lane + (uint32_t)c, v);
         const unsigned w = psg_relu_bias_bits<32>(v, bias + c);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            *plane_ptr(dst, (c >> 2) + q, row) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) {
+            const float4 y = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            *plane_ptr(dst, (c >> 2) + q, row) = y;
+            if (X3) *plane_ptr(dst_lo, (c >> 2) + q, row) = lo4(y);
+        }
         mask_tile[(size_t)(c >> 5) * 128 + row] = w;
     }
     if (c < n) {
@@ -95,17 +126,21 @@ __device__ __forceinline__ void epilogue_relu_to_smem(uint32_t tmem_lane, int n,
         tc::tmem_ld16(tmem_lane + (uint32_t)c, v);
         const unsigned w = psg_relu_bias_bits<16>(v, bias + c);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            *plane_ptr(dst, (c >> 2) + q, row) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) {
+            const float4 y = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            *plane_ptr(dst, (c >> 2) + q, row) = y;
+            if (X3) *plane_ptr(dst_lo, (c >> 2) + q, row) = lo4(y);
+        }
         mask_tile[(size_t)(c >> 5) * 128 + row] = w;
     }
 }
 
 // CP: the rows are the compacted real hits (compact.cu) -- source point and centroid come from crow_src / crow_g, the tile
 // count from device memory, and the pool scans variable-length segments of the warp's four octets.
-template <int K, int NG, bool CP>
+template <int K, int NG, bool CP, bool X3 = false>
 __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_fwd_kernel(SaFwdArgs a)
 {
+    static_assert(!X3 || CP, "the 3xTF32 kernels run on compacted rows only");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG];
     __shared__ uint32_t tmem_slot;
@@ -119,8 +154,11 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     // epilogue overwrites the layer's own input in place (gather -> Y0 -> Y1)
     // (compacted rows: the segmented pool borrows 4 KB of the buffer per warp, so narrow branches get at least 16 KB)
     const int szG = CP ? max(max(a.gpad, max(a.n0, a.n1)) * 512, 16384) : max(a.gpad, max(a.n0, a.n1)) * 512;
-    unsigned char *pW0 = base, *pW1 = pW0 + szW0, *pW2 = pW1 + szW1, *pG = pW2 + szW2;
-    const uint32_t sW0 = sbase, sW1 = sW0 + szW0, sW2 = sW1 + szW1, sG = sW2 + szW2;
+    // X3: [W hi x3][W lo x3][per tile: A | A_lo]
+    const int szWall = szW0 + szW1 + szW2;
+    unsigned char *pW0 = base, *pW1 = pW0 + szW0, *pW2 = pW1 + szW1, *pG = pW2 + szW2 + (X3 ? szWall : 0);
+    const uint32_t sW0 = sbase, sW1 = sW0 + szW0, sW2 = sW1 + szW1, sG = sW2 + szW2 + (X3 ? szWall : 0);
+    const int tileG = X3 ? 2 * szG : szG;            // operand bytes per tile in flight
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long *gtr = (a.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
@@ -133,6 +171,11 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     load_weights(pW0, a.w0, a.gpad / 4, a.n0, a.nw0);
     load_weights(pW1, a.w1, a.n0 / 4, a.n1, a.nw1);
     load_weights(pW2, a.w2, a.n1 / 4, a.n2, a.nw2);
+    if (X3) {
+        load_weights(pW0 + szWall, a.w0l, a.gpad / 4, a.n0, a.nw0);
+        load_weights(pW1 + szWall, a.w1l, a.n0 / 4, a.n1, a.nw1);
+        load_weights(pW2 + szWall, a.w2l, a.n1 / 4, a.n2, a.nw2);
+    }
     for (int i = threadIdx.x; i < 128; i += blockDim.x) {
         sbias[0][i] = i < a.n0 ? __ldg(a.b0 + i) : 0.f;
         sbias[1][i] = i < a.n1 ? __ldg(a.b1 + i) : 0.f;
@@ -165,13 +208,18 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             // the other groups' issue work (a single polling thread cost ~1000 cycles per layer at NG = 4) ----
             const int g = warp - NG * 4;
             const uint32_t b_in = tc::smem_u32(&bar_in[g]), b_acc = tc::smem_u32(&bar_acc[g]);
-            const uint32_t sA = sG + g * szG, tm = tmem + g * gcols;
+            const uint32_t sA = sG + g * tileG, tm = tmem + g * gcols;
             uint32_t ph = 0;
             for (int tile = blockIdx.x * NG + g; tile < ntiles; tile += tstride) {
 #pragma unroll 1
                 for (int layer = 0; layer < 3; ++layer) {
                     tc::mbar_spin(b_in, ph); ph ^= 1u;
                     tc::fence_after_sync();
+                    if (X3) {
+                        if (layer == 0) issue_layer_x3(tm, sA, sA + szG, sW0, sW0 + szWall, a.gpad / 4, a.n0);
+                        else if (layer == 1) issue_layer_x3(tm, sA, sA + szG, sW1, sW1 + szWall, a.n0 / 4, a.n1);
+                        else issue_layer_x3(tm, sA, sA + szG, sW2, sW2 + szWall, a.n1 / 4, a.n2);
+                    } else
                     if (layer == 0) issue_layer(tm, sA, sW0, a.gpad / 4, a.n0);
                     else if (layer == 1) issue_layer(tm, sA, sW1, a.n0 / 4, a.n1);
                     else issue_layer(tm, sA, sW2, a.n1 / 4, a.n2);
@@ -182,7 +230,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     } else {
         const int grp = warp >> 2, wq = warp & 3;
         const int r = threadIdx.x & 127;                 // tile row = TMEM lane
-        unsigned char *pA = pG + (size_t)grp * szG, *pY0 = pA;
+        unsigned char *pA = pG + (size_t)grp * tileG, *pY0 = pA, *pAl = pA + szG;
         const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
         const uint32_t tl = tmem + grp * gcols + ((uint32_t)(wq * 32) << 16);
         const int k = r % K;
@@ -214,6 +262,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
                 for (int c = 0; c < nfull; ++c) {
                     float4 v = valid ? tv_ld(a.feats, srow, c) : make_float4(0.f, 0.f, 0.f, 0.f);
                     *plane_ptr(pA, c, r) = v;
+                    if (X3) *plane_ptr(pAl, c, r) = lo4(v);
                 }
                 const float *sp = a.xyz + (long long)cloud * a.cloud_stride + (long long)src * 3;
                 const float *cp = a.new_xyz + ps * 3;
@@ -229,6 +278,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
                         if (!valid) o[j] = 0.f;
                     }
                     *plane_ptr(pA, c, r) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (X3) *plane_ptr(pAl, c, r) = lo4(make_float4(o[0], o[1], o[2], o[3]));
                 }
                 // prefetch the next tile's neighbour index: takes one L2 round trip off its gather
                 const long long nrow = row + (long long)tstride * 128;
@@ -241,7 +291,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             // ---- layer 0 epilogue -> Y0 ----
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
             SA_STAMP();
-            epilogue_relu_to_smem(tl, a.n0, sbias[0], pY0, a.m0 + (size_t)tile * w0words * 128, r);
+            epilogue_relu_to_smem<X3>(tl, a.n0, sbias[0], pY0, a.m0 + (size_t)tile * w0words * 128, r, pAl);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
@@ -249,7 +299,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             // ---- layer 1 epilogue -> Y1 (reuses the gather buffer) ----
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
             SA_STAMP();
-            epilogue_relu_to_smem(tl, a.n1, sbias[1], pA, a.m1 + (size_t)tile * w1words * 128, r);
+            epilogue_relu_to_smem<X3>(tl, a.n1, sbias[1], pA, a.m1 + (size_t)tile * w1words * 128, r, pAl);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
@@ -373,11 +423,13 @@ struct SaBwdArgs {
     int ntiles;
     long long *trace;
     const int *crow_g, *ntiles_dev;                 // compacted rows (compact.cu); CP kernels only
+    const float *wb0l, *wb1l, *wb2l;                // X3 kernels: the TF32 residuals of the dgrad weights
 };
 
 // accumulator -> ReLU-bit mask -> next A operand in shared memory
+template <bool X3 = false>
 __device__ __forceinline__ void epilogue_mask_to_smem(uint32_t tmem_lane, int n, const unsigned *mask_tile,
-                                                      unsigned char *dst, int row)
+                                                      unsigned char *dst, int row, unsigned char *dst_lo = nullptr)
 {
     int c = 0;
     for (; c + 32 <= n; c += 32) {
@@ -386,8 +438,11 @@ __device__ __forceinline__ void epilogue_mask_to_smem(uint32_t tmem_lane, int n,
         tc::tmem_ld32(tmem_lane + (uint32_t)c, v);
         psg_apply_bits<32>(v, w);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            *plane_ptr(dst, (c >> 2) + q, row) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) {
+            const float4 y = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            *plane_ptr(dst, (c >> 2) + q, row) = y;
+            if (X3) *plane_ptr(dst_lo, (c >> 2) + q, row) = lo4(y);
+        }
     }
     if (c < n) {
         const unsigned w = mask_tile[(size_t)(c >> 5) * 128 + row];
@@ -395,14 +450,18 @@ __device__ __forceinline__ void epilogue_mask_to_smem(uint32_t tmem_lane, int n,
         tc::tmem_ld16(tmem_lane + (uint32_t)c, v);
         psg_apply_bits<16>(v, w);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            *plane_ptr(dst, (c >> 2) + q, row) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) {
+            const float4 y = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            *plane_ptr(dst, (c >> 2) + q, row) = y;
+            if (X3) *plane_ptr(dst_lo, (c >> 2) + q, row) = lo4(y);
+        }
     }
 }
 
-template <int K, int NG, bool CP>
+template <int K, int NG, bool CP, bool X3 = false>
 __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_bwd_kernel(SaBwdArgs a)
 {
+    static_assert(!X3 || CP, "the 3xTF32 kernels run on compacted rows only");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_in[NG], bar_acc[NG];
     __shared__ uint32_t tmem_slot;
@@ -417,8 +476,11 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     // per tile ONE operand buffer, overwritten in place: dY2 (one slab at a time) -> dY1 -> dY0
     const int szG = max(a.slab, max(a.n1, a.n0)) * 512;
     const int nslab = a.n2 / a.slab;
-    unsigned char *pW2 = base, *pW1 = pW2 + szW2, *pW0 = pW1 + szW1, *pG = pW0 + szW0;
-    const uint32_t sW2 = sbase, sW1 = sW2 + szW2, sW0 = sW1 + szW1, sG = sW0 + szW0;
+    // X3: [W hi x3][W lo x3][per tile: D | D_lo]
+    const int szWall = szW2 + szW1 + szW0;
+    unsigned char *pW2 = base, *pW1 = pW2 + szW2, *pW0 = pW1 + szW1, *pG = pW0 + szW0 + (X3 ? szWall : 0);
+    const uint32_t sW2 = sbase, sW1 = sW2 + szW2, sW0 = sW1 + szW1, sG = sW0 + szW0 + (X3 ? szWall : 0);
+    const int tileG = X3 ? 2 * szG : szG;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nmax = max(a.n0, max(a.n1, a.gpad));
@@ -428,6 +490,11 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     load_weights(pW2, a.wb2, a.n2 / 4, a.n1, a.nwb2);
     load_weights(pW1, a.wb1, a.n1 / 4, a.n0, a.nwb1);
     load_weights(pW0, a.wb0, a.n0 / 4, a.gpad, a.nwb0);
+    if (X3) {
+        load_weights(pW2 + szWall, a.wb2l, a.n2 / 4, a.n1, a.nwb2);
+        load_weights(pW1 + szWall, a.wb1l, a.n1 / 4, a.n0, a.nwb1);
+        load_weights(pW0 + szWall, a.wb0l, a.n0 / 4, a.gpad, a.nwb0);
+    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -452,13 +519,19 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             // ---- MMA issuers: one warp per tile in flight (see sa_fwd_kernel) ----
             const int g = warp - NG * 4;
             const uint32_t b_in = tc::smem_u32(&bar_in[g]), b_acc = tc::smem_u32(&bar_acc[g]);
-            const uint32_t sD = sG + g * szG, tm = tmem + g * gcols;
+            const uint32_t sD = sG + g * tileG, tm = tmem + g * gcols;
             uint32_t ph = 0;
             for (int tile = blockIdx.x * NG + g; tile < ntiles; tile += tstride) {
 #pragma unroll 1
                 for (int L = 0; L < nslab + 2; ++L) {
                     tc::mbar_spin(b_in, ph); ph ^= 1u;
                     tc::fence_after_sync();
+                    if (X3) {
+                        const uint32_t w2off = (uint32_t)L * (a.slab / 4) * a.n1 * 16;
+                        if (L < nslab) issue_layer_x3(tm, sD, sD + szG, sW2 + w2off, sW2 + szWall + w2off, a.slab / 4, a.n1, L > 0 ? 1u : 0u);
+                        else if (L == nslab) issue_layer_x3(tm, sD, sD + szG, sW1, sW1 + szWall, a.n1 / 4, a.n0);
+                        else issue_layer_x3(tm, sD, sD + szG, sW0, sW0 + szWall, a.n0 / 4, a.gpad);
+                    } else
                     if (L < nslab)                                                        // dY1 (+)= dY2[:, slab L] W2[slab L]
                         issue_layer(tm, sD, sW2 + (uint32_t)L * (a.slab / 4) * a.n1 * 16, a.slab / 4, a.n1, L > 0 ? 1u : 0u);
                     else if (L == nslab) issue_layer(tm, sD, sW1, a.n1 / 4, a.n0);        // dY0 = dY1 W1
@@ -470,7 +543,7 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
     } else {
         const int grp = warp >> 2, wq = warp & 3;
         const int r = threadIdx.x & 127;
-        unsigned char *pD2 = pG + (size_t)grp * szG, *pD1 = pD2, *pD0 = pD2;
+        unsigned char *pD2 = pG + (size_t)grp * tileG, *pD1 = pD2, *pD0 = pD2, *pDl = pD2 + szG;
         const uint32_t b_in = tc::smem_u32(&bar_in[grp]), b_acc = tc::smem_u32(&bar_acc[grp]);
         const uint32_t tl = tmem + grp * gcols + ((uint32_t)(wq * 32) << 16);
         const int w0words = (a.n0 + 31) / 32, w1words = (a.n1 + 31) / 32;
@@ -500,7 +573,10 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
             for (int sl = 0; sl < nslab; ++sl) {
                 if (CP)
                     psg_scatter_warp_rank<8>(a.dout, a.outv, a.arg, a.n2, g, valid, lane, rank, sl * (a.slab / 4), a.slab / 4,
-                                             stg_d[warp], stg_a[warp], [&](int c, float4 q) { *plane_ptr(pD2, c, r) = q; });
+                                             stg_d[warp], stg_a[warp], [&](int c, float4 q) {
+                                                 *plane_ptr(pD2, c, r) = q;
+                                                 if (X3) *plane_ptr(pDl, c, r) = lo4(q);
+                                             });
                 else
                 psg_scatter_warp<K>(a.dout, a.outv, a.arg, a.n2, g, valid, lane, sl * (a.slab / 4), a.slab / 4,
                                     stg_d[warp], stg_a[warp], [&](int c, float4 q) { *plane_ptr(pD2, c, r) = q; });
@@ -511,14 +587,14 @@ __global__ void __launch_bounds__(NG * 160, NG == 1 ? 4 : (NG == 2 ? 2 : 1)) sa_
                 tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();     // this slab's MMAs are done
                 SA_STAMP();
             }
-            epilogue_mask_to_smem(tl, a.n1, a.m1 + (size_t)tile * w1words * 128, pD1, r);
+            epilogue_mask_to_smem<X3>(tl, a.n1, a.m1 + (size_t)tile * w1words * 128, pD1, r, pDl);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
             SA_STAMP();
             tc::mbar_wait(b_acc, ph); ph ^= 1u; tc::fence_after_sync();
             SA_STAMP();
-            epilogue_mask_to_smem(tl, a.n0, a.m0 + (size_t)tile * w0words * 128, pD0, r);
+            epilogue_mask_to_smem<X3>(tl, a.n0, a.m0 + (size_t)tile * w0words * 128, pD0, r, pDl);
             tc::fence_before_sync();
             tc::fence_async_smem();
             tc::mbar_arrive(b_in);
@@ -555,11 +631,12 @@ constexpr size_t kSmemPerCtaMax = 224 * 1024;
 
 inline size_t r1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
 inline int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
-inline size_t fwd_smem(int gpad, int n0, int n1, int n2, int ng, bool cp = false)
+inline size_t fwd_smem(int gpad, int n0, int n1, int n2, int ng, bool cp = false, bool x3 = false)
 {
     size_t g = (size_t)max3(gpad, n0, n1) * 512;
     if (cp && g < 16384) g = 16384;              // the segmented pool's per-warp scratch lives in the operand buffer
-    return (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4) + (size_t)ng * g + 1024;
+    const size_t w = (size_t)gpad * n0 * 4 + (size_t)n0 * n1 * 4 + r1k((size_t)n1 * n2 * 4);
+    return (x3 ? 2 : 1) * (w + (size_t)ng * g) + 1024;      // 3xTF32: hi and lo copies of the weights and of every operand buffer
 }
 // columns of dY2 scattered per pass: the largest 16-multiple divisor of n2 not wider than the hidden layers
 // (the operand buffer has to hold those anyway)
@@ -570,21 +647,21 @@ inline int bwd_slab(int n0, int n1, int n2)
         if (n2 % sl == 0) return sl;
     return n2;
 }
-inline size_t bwd_smem_slab(int gpad, int n0, int n1, int n2, int ng, int slab)
+inline size_t bwd_smem_slab(int gpad, int n0, int n1, int n2, int ng, int slab, bool x3 = false)
 {
-    return (size_t)n2 * n1 * 4 + (size_t)n1 * n0 * 4 + r1k((size_t)n0 * gpad * 4) +
-           (size_t)ng * (size_t)max3(slab, n1, n0) * 512 + 1024;
+    return (x3 ? 2 : 1) * ((size_t)n2 * n1 * 4 + (size_t)n1 * n0 * 4 + r1k((size_t)n0 * gpad * 4) +
+                           (size_t)ng * (size_t)max3(slab, n1, n0) * 512) + 1024;
 }
 // The register file, not shared memory, limits a SM to about four tiles in flight, so when four whole-width
 // operand buffers fit the scatter goes in ONE pass: every extra slab is one more MMA round trip (~1 us) per tile.
-inline int bwd_slab_for(int gpad, int n0, int n1, int n2)
+inline int bwd_slab_for(int gpad, int n0, int n1, int n2, bool x3 = false)
 {
-    if (bwd_smem_slab(gpad, n0, n1, n2, 4, n2) <= kSmemPerCtaMax) return n2;
+    if (bwd_smem_slab(gpad, n0, n1, n2, 4, n2, x3) <= kSmemPerCtaMax) return n2;
     return bwd_slab(n0, n1, n2);
 }
-inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng)
+inline size_t bwd_smem(int gpad, int n0, int n1, int n2, int ng, bool x3 = false)
 {
-    return bwd_smem_slab(gpad, n0, n1, n2, ng, bwd_slab_for(gpad, n0, n1, n2));
+    return bwd_smem_slab(gpad, n0, n1, n2, ng, bwd_slab_for(gpad, n0, n1, n2, x3), x3);
 }
 inline uint32_t pow2cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
@@ -629,6 +706,14 @@ template <int K> void (*bwd_kern(int ng))(SaBwdArgs)
 void (*fwd_kern_cp(int ng))(SaFwdArgs)
 {
     return ng == 1 ? sa_fwd_kernel<32, 1, true> : ng == 2 ? sa_fwd_kernel<32, 2, true> : ng == 3 ? sa_fwd_kernel<32, 3, true> : sa_fwd_kernel<32, 4, true>;
+}
+void (*fwd_kern_cp_x3(int ng))(SaFwdArgs)
+{
+    return ng == 1 ? sa_fwd_kernel<32, 1, true, true> : ng == 2 ? sa_fwd_kernel<32, 2, true, true> : ng == 3 ? sa_fwd_kernel<32, 3, true, true> : sa_fwd_kernel<32, 4, true, true>;
+}
+void (*bwd_kern_cp_x3(int ng))(SaBwdArgs)
+{
+    return ng == 1 ? sa_bwd_kernel<32, 1, true, true> : ng == 2 ? sa_bwd_kernel<32, 2, true, true> : ng == 3 ? sa_bwd_kernel<32, 3, true, true> : sa_bwd_kernel<32, 4, true, true>;
 }
 void (*bwd_kern_cp(int ng))(SaBwdArgs)
 {
@@ -701,6 +786,13 @@ bool psg_sa_compactable(int K, int gpad, int n0, int n1, int n2)
     return psg_sa_fusable(K, gpad, n0, n1, n2) && fwd_smem(gpad, n0, n1, n2, 1, true) <= kSmemPerCtaMax;
 }
 
+// can the branch run as 3xTF32 fused kernels (hi + lo weights and operand buffers in shared memory, one tile in flight)?
+bool psg_sa_fusable_x3(int K, int gpad, int n0, int n1, int n2)
+{
+    if (!psg_sa_compactable(K, gpad, n0, n1, n2)) return false;
+    return fwd_smem(gpad, n0, n1, n2, 1, true, true) <= kSmemPerCtaMax && bwd_smem(gpad, n0, n1, n2, 1, true) <= kSmemPerCtaMax;
+}
+
 size_t psg_sa_mask_words(long long rows, int n)
 {
     return (size_t)((rows + 127) / 128) * ((n + 31) / 32) * 128;
@@ -718,12 +810,16 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     a.ntiles = (int)((f.rows + 127) / 128);
     a.trace = psg_tile_trace_slot();
     a.crow_src = f.crow_src; a.crow_g = f.crow_g; a.ntiles_dev = f.ntiles_dev;
+    a.w0l = f.wf_lo[0]; a.w1l = f.wf_lo[1]; a.w2l = f.wf_lo[2];
     const bool cp = f.crow_src && f.crow_g && f.ntiles_dev;
+    const bool x3 = a.w0l && a.w1l && a.w2l;
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.n2 ? a.n0 : a.n2) : (a.n1 > a.n2 ? a.n1 : a.n2));
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
     if (cp && !psg_sa_compactable(f.K, a.gpad, a.n0, a.n1, a.n2)) return PSG_EUNSUPPORTED;
-    auto smem_of = [&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g, cp); };
-    const Pick pk = cp ? cached_pick(2, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern_cp, smem_of, gc)
+    if (x3 && !cp) return PSG_EUNSUPPORTED;
+    auto smem_of = [&](int g) { return fwd_smem(a.gpad, a.n0, a.n1, a.n2, g, cp, x3); };
+    const Pick pk = x3 ? cached_pick(4, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern_cp_x3, smem_of, gc)
+                  : cp ? cached_pick(2, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern_cp, smem_of, gc)
                   : f.K == 32 ? cached_pick(0, 32, a.gpad, a.n0, a.n1, a.n2, fwd_kern<32>, smem_of, gc)
                               : cached_pick(0, 16, a.gpad, a.n0, a.n1, a.n2, fwd_kern<16>, smem_of, gc);
     if (pk.ng < 1 || pk.occ < 1 || num_sms() < 1) return PSG_EUNSUPPORTED;
@@ -731,7 +827,7 @@ int psg_sa_fused_fwd(const PsgSaFused &f, cudaStream_t st)
     const int tiles_for_grid = cp ? (a.ntiles + g_grid_div - 1) / g_grid_div : a.ntiles;
     const int want = (tiles_for_grid + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
     const int grid = want < cap ? want : cap;
-    auto kern = cp ? fwd_kern_cp(pk.ng) : f.K == 32 ? fwd_kern<32>(pk.ng) : fwd_kern<16>(pk.ng);
+    auto kern = x3 ? fwd_kern_cp_x3(pk.ng) : cp ? fwd_kern_cp(pk.ng) : f.K == 32 ? fwd_kern<32>(pk.ng) : fwd_kern<16>(pk.ng);
     { cudaError_t e__ = psg_launch_pdl(kern, dim3(grid), dim3(pk.ng * 160), smem_of(pk.ng), st, 1, a);
       if (e__ != cudaSuccess) { fprintf(stderr, "sa launch: %s (ng %d occ %d grid %d smem %zu)\n", cudaGetErrorString(e__), pk.ng, pk.occ, grid, smem_of(pk.ng)); return PSG_ECUDA; } }
     PSG_LAUNCH_CHECK();
@@ -745,23 +841,27 @@ int psg_sa_fused_bwd(const PsgSaFused &f, TView dout, TView dG, int gcols, float
     a.wb0 = f.wb[0]; a.wb1 = f.wb[1]; a.wb2 = f.wb[2]; a.nwb0 = f.nwb[0]; a.nwb1 = f.nwb[1]; a.nwb2 = f.nwb[2];
     a.dG = dG; a.gcols = gcols; a.rows = f.rows;
     a.dG_rm = dG_rm; a.rm_only = (dG_rm && rm_only) ? 1 : 0;
-    a.slab = bwd_slab_for(f.gpad, f.n[0], f.n[1], f.n[2]);
+    a.wb0l = f.wb_lo[0]; a.wb1l = f.wb_lo[1]; a.wb2l = f.wb_lo[2];
+    const bool x3 = a.wb0l && a.wb1l && a.wb2l;
+    a.slab = bwd_slab_for(f.gpad, f.n[0], f.n[1], f.n[2], x3);
     a.gpad = f.gpad; a.n0 = f.n[0]; a.n1 = f.n[1]; a.n2 = f.n[2];
     a.ntiles = (int)((f.rows + 127) / 128);
     a.trace = psg_tile_trace_slot();
     a.crow_g = f.crow_g; a.ntiles_dev = f.ntiles_dev;
     const bool cp = f.crow_src && f.crow_g && f.ntiles_dev;
+    if (x3 && !cp) return PSG_EUNSUPPORTED;
     const int gc = (int)pow2cols(a.n0 > a.n1 ? (a.n0 > a.gpad ? a.n0 : a.gpad) : (a.n1 > a.gpad ? a.n1 : a.gpad));
     if (f.K != 16 && f.K != 32) return PSG_EUNSUPPORTED;
-    auto smem_of = [&](int g) { return bwd_smem(a.gpad, a.n0, a.n1, a.n2, g); };
-    const Pick pk = cp ? cached_pick(3, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern_cp, smem_of, gc)
+    auto smem_of = [&](int g) { return bwd_smem(a.gpad, a.n0, a.n1, a.n2, g, x3); };
+    const Pick pk = x3 ? cached_pick(5, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern_cp_x3, smem_of, gc)
+                  : cp ? cached_pick(3, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern_cp, smem_of, gc)
                   : f.K == 32 ? cached_pick(1, 32, a.gpad, a.n0, a.n1, a.n2, bwd_kern<32>, smem_of, gc)
                               : cached_pick(1, 16, a.gpad, a.n0, a.n1, a.n2, bwd_kern<16>, smem_of, gc);
     if (pk.ng < 1 || pk.occ < 1 || num_sms() < 1) return PSG_EUNSUPPORTED;
     const int tiles_for_grid = cp ? (a.ntiles + g_grid_div - 1) / g_grid_div : a.ntiles;
     const int want = (tiles_for_grid + pk.ng - 1) / pk.ng, cap = num_sms() * pk.occ;
     const int grid = want < cap ? want : cap;
-    auto kern = cp ? bwd_kern_cp(pk.ng) : f.K == 32 ? bwd_kern<32>(pk.ng) : bwd_kern<16>(pk.ng);
+    auto kern = x3 ? bwd_kern_cp_x3(pk.ng) : cp ? bwd_kern_cp(pk.ng) : f.K == 32 ? bwd_kern<32>(pk.ng) : bwd_kern<16>(pk.ng);
     { cudaError_t e__ = psg_launch_pdl(kern, dim3(grid), dim3(pk.ng * 160), smem_of(pk.ng), st, 1, a);
       if (e__ != cudaSuccess) { fprintf(stderr, "sa launch: %s (ng %d occ %d grid %d smem %zu)\n", cudaGetErrorString(e__), pk.ng, pk.occ, grid, smem_of(pk.ng)); return PSG_ECUDA; } }
     PSG_LAUNCH_CHECK();
