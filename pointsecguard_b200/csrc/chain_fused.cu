@@ -38,6 +38,7 @@ enum { EPI_NONE = 0, EPI_RELU, EPI_MASK, EPI_HEAD, EPI_STORE, EPI_MAXPOOL };
 
 struct TileOp {
     const float *w;            // packed weights [plane][wstride rows][4]
+    const float *wlo;          // X3 programs: the TF32 residual of w (same packing), or null
     int wstride, wrow0, wplane0;
     int n, planes;             // MMA N; K / 4
     int aplane0;               // first A-buffer plane read
@@ -77,6 +78,7 @@ struct TileArgs {
     int abytes, stage_bytes, tcols;      // A buffer bytes per tile, weight stage bytes, TMEM columns per tile
     int rmstage;                         // 1: a 4 KB per-warp staging area for coalesced row-major stores follows the scatter staging
     int acols;                           // TS programs: TMEM columns of the A operand (after the accumulator's tcols)
+    int lo_off;                          // X3 programs: operand column where the A_lo copy of the operand starts
     int bias_floats;                     // size of the shared-memory bias area
     int mwords, mbytes;                  // ReLU-bit words per mask slot; bytes of the per-tile mask / scratch area
     // head / loss (EPI_HEAD)
@@ -156,9 +158,16 @@ __device__ __forceinline__ void pre_load(const TileSrc &s, unsigned char *pA, lo
 // interpolated chunks [cbeg, cbeg + nch) -> A planes [plane0, plane0 + nch)
 // TS: the A operand lives in tensor memory (tA = TMEM address of this thread's lane, column 0 of the operand):
 // eight chunks are collected and written with one tcgen05.st (nch must then be a multiple of 8)
-template <bool TS>
+// X3 (TS only): the operand is written twice -- as it is (the hardware reads its top 19 bits: A_hi) and its residual
+// A_lo = A - A_hi at column lo_off
+__device__ __forceinline__ void lo32(const float *v, float *l)
+{
+#pragma unroll
+    for (int i = 0; i < 32; ++i) l[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+}
+template <bool TS, bool X3 = false>
 __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, long long row, bool valid, int r, int cbeg, int nch,
-                                           int plane0, uint32_t tA)
+                                           int plane0, uint32_t tA, int lo_off = 0)
 {
     const long long rr = valid ? row : 0;
     const long long p = rr / s.iNf;
@@ -197,6 +206,7 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
                 else if (c0 + j < nch) *plane_ptr(pA, plane0 + c0 + j, r) = q;
             }
             if (TS) tc::tmem_st32(tA + (uint32_t)(plane0 + c0) * 4u, v);
+            if (TS && X3) { float l[32]; lo32(v, l); tc::tmem_st32(tA + (uint32_t)(plane0 + c0) * 4u + (uint32_t)lo_off, l); }
         }
         return;
     }
@@ -227,6 +237,7 @@ __device__ __forceinline__ void pre_interp(const TileSrc &s, unsigned char *pA, 
             else if (c0 + j < nch) *plane_ptr(pA, plane0 + c0 + j, r) = q;
         }
         if (TS) tc::tmem_st32(tA + (uint32_t)(plane0 + c0) * 4u, v);
+        if (TS && X3) { float l[32]; lo32(v, l); tc::tmem_st32(tA + (uint32_t)(plane0 + c0) * 4u + (uint32_t)lo_off, l); }
     }
 }
 
@@ -253,11 +264,15 @@ __device__ __forceinline__ void pre_scatter(const TileSrc &s, unsigned char *pA,
 // write the next operand with tcgen05.st, there is no operand buffer in shared memory at all.  That removes
 // the two biggest shared-memory streams of a layer (MMA A reads, epilogue stores) -- the SS-mode chain was
 // shared-memory bound at about twice its tensor time -- and leaves room for 64 KB weight stages.
-template <int NG, int CS, bool TS>
+// X3: error-compensated 3xTF32 (TS programs, one tile in flight): every GEMM op runs three passes over its K range --
+// A_lo W_hi, A_hi W_lo, A_hi W_hi -- into the same accumulator; the producer streams W_hi, W_lo, W_hi again, the workers
+// write every operand twice (A and, at column lo_off, A_lo).  One hand-off per op, as in the plain program.
+template <int NG, int CS, bool TS, bool X3 = false>
 __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_constant__ TileArgs a)
 {
     static_assert(CS == 1 || NG == 1, "cluster programs keep one tile in flight");
     static_assert(!TS || CS == 1, "peers cannot write each other's tensor memory");
+    static_assert(!X3 || (TS && NG == 1), "3xTF32 programs keep the operand and its residual in tensor memory");
     // no-swizzle UMMA operands and bulk copies need 16-byte alignment only: a 128-byte aligned dynamic
     // segment keeps the static + padding overhead small (every KB decides whether 32 KB weight stages fit)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -314,6 +329,8 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
             for (int o = 0; o < a.nops; ++o) {
                 const TileOp &op = a.ops[o];
                 const int nl = op.n / CS;                     // this CTA's slice of the output columns
+                const int nsub = (X3 && op.wlo) ? 3 : 1;
+                for (int sub = 0; sub < nsub; ++sub)
                 for (int pl = 0; pl < op.planes; pl += op.pps, ++it) {
                     const int np = min(op.pps, op.planes - pl);
                     const int slot = it % kStages;
@@ -325,7 +342,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         tc::mbar_expect_tx(full, (uint32_t)np * nl * 16);
                     }
                     __syncwarp();
-                    const float4 *wsrc = reinterpret_cast<const float4 *>(op.w) + (size_t)(op.wplane0 + pl) * op.wstride +
+                    const float4 *wsrc = reinterpret_cast<const float4 *>((X3 && sub == 1) ? op.wlo : op.w) + (size_t)(op.wplane0 + pl) * op.wstride +
                                          op.wrow0 + q * nl;
                     if (op.wstride == nl) {
                         if (lane == 0) tc::bulk_g2s(dst, wsrc, (uint32_t)np * nl * 16, full);
@@ -383,15 +400,17 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         it += nst;
                         continue;
                     }
+                    const int nsub = (X3 && op.wlo) ? 3 : 1;
+                    for (int sub = 0; sub < nsub; ++sub)
                     for (int pl = 0; pl < op.planes; pl += op.pps, ++it) {
                         const int np = min(op.pps, op.planes - pl);
                         const int slot = it % kStages;
-                        const bool last = pl + op.pps >= op.planes;
+                        const bool last = pl + op.pps >= op.planes && sub == nsub - 1;
                         tc::mbar_spin(tc::smem_u32(&bar_full[slot]), (uint32_t)(it / kStages) & 1u);
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
                             if (tile0 + g >= a.ntiles) continue;
-                            if (pl == 0) {
+                            if (pl == 0 && sub == 0) {
                                 if (CS > 1) tc::mbar_wait_cluster(tc::smem_u32(&bar_in[g]), ph_in[g]);
                                 else tc::mbar_spin(tc::smem_u32(&bar_in[g]), ph_in[g]);
                                 ph_in[g] ^= 1u;
@@ -399,10 +418,12 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                             tc::fence_after_sync();
                             const uint32_t sA = sA0 + g * a.abytes + (uint32_t)(op.aplane0 + pl) * 2048u;
                             const uint32_t sB = sW + slot * a.stage_bytes;
-                            const uint32_t tD = tmem + g * tper, tA = tD + a.tcols + (uint32_t)(op.aplane0 + pl) * 4u;
+                            // X3: the first pass contracts A_lo (operand column lo_off) with W_hi, then A with W_lo, then A with W_hi
+                            const uint32_t tD = tmem + g * tper,
+                                           tA = tD + a.tcols + (uint32_t)(op.aplane0 + pl) * 4u + ((X3 && nsub == 3 && sub == 0) ? (uint32_t)a.lo_off : 0u);
                             for (int j = 0; j < np; j += 2) {
                                 const uint64_t bd = tc::smem_desc(sB + j * nl * 16, (uint32_t)(nl * 16), 128);
-                                const uint32_t acc = (op.accumulate || pl > 0 || j > 0) ? 1u : 0u;
+                                const uint32_t acc = (op.accumulate || pl > 0 || j > 0 || sub > 0) ? 1u : 0u;
                                 if (TS) tc::mma_tf32_ts(tD, tA + j * 4, bd, idesc, acc);
                                 else tc::mma_tf32(tD, tc::smem_desc(sA + j * 2048, 2048, 128), bd, idesc, acc);
                             }
@@ -443,15 +464,24 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
         };
         // 32 / 16 consecutive columns of this thread's row, starting at operand column `col`
         auto put32 = [&](int col, const float *v) {
-            if (TS) tc::tmem_st32(tla + (uint32_t)col, v);
-            else {
+            if (TS) {
+                tc::tmem_st32(tla + (uint32_t)col, v);
+                if (X3) { float l[32]; lo32(v, l); tc::tmem_st32(tla + (uint32_t)(col + a.lo_off), l); }
+            } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) put((col >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
             }
         };
         auto put16 = [&](int col, const float *v) {
-            if (TS) tc::tmem_st16(tla + (uint32_t)col, v);
-            else {
+            if (TS) {
+                tc::tmem_st16(tla + (uint32_t)col, v);
+                if (X3) {
+                    float l[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) l[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+                    tc::tmem_st16(tla + (uint32_t)(col + a.lo_off), l);
+                }
+            } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) put((col >> 2) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
             }
@@ -468,7 +498,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                     // chunks [pre_a, pre_a + planes) of the concatenation [skip | interpolation]
                     const int L = a.src.lcols / 4, kb = op.pre_a, ke = op.pre_a + op.planes;
                     if (kb < L) pre_load(a.src, pA, row, valid, r, kb, min(ke, L) - kb);
-                    if (ke > L) pre_interp<TS>(a.src, pA, row, valid, r, max(kb, L) - L, ke - max(kb, L), max(kb, L) - kb, tla);
+                    if (ke > L) pre_interp<TS, X3>(a.src, pA, row, valid, r, max(kb, L) - L, ke - max(kb, L), max(kb, L) - kb, tla, a.lo_off);
                 }
                 else if (op.pre == PRE_LOAD) pre_load(a.src, pA, row, valid, r, 0, a.src.lcols / 4);
                 else if (op.pre == PRE_SCATTER) pre_scatter(a.src, pA, row, valid, r, op.pre_a, op.planes, stage_d + warp * 32, stage_a + warp * 32);
@@ -671,6 +701,7 @@ struct Builder {
     int amax_cols = 0;    // widest A operand (columns)
     int nmax = 0;         // widest accumulator
     bool ok = true;
+    bool x3 = false;      // 3xTF32 program: every op carries wlo, the operand holds [A | A_lo]
     Builder() { memset(&a, 0, sizeof(a)); }
     TileOp *add(const float *w, int wstride, int wrow0, int wplane0, int n, int planes, int aplane0)
     {
@@ -704,16 +735,16 @@ int pick_cluster(const TileArgs &a, int ntiles, int sms)
     return 1;
 }
 
-template <int NG, int CS, bool TS = false>
+template <int NG, int CS, bool TS = false, bool X3 = false>
 int launch_tile(const TileArgs &a, int grid, size_t smem, cudaStream_t st)
 {
     static PsgDeviceOnce attr_once;
     if (attr_once.need()) {
-        if (cudaFuncSetAttribute(tile_kernel<NG, CS, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
+        if (cudaFuncSetAttribute(tile_kernel<NG, CS, TS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
             return PSG_ECUDA;
         attr_once.mark();
     }
-    if (psg_launch_pdl(tile_kernel<NG, CS, TS>, dim3((unsigned)grid), dim3(NG * 128 + 64), smem, st, CS, a) != cudaSuccess)
+    if (psg_launch_pdl(tile_kernel<NG, CS, TS, X3>, dim3((unsigned)grid), dim3(NG * 128 + 64), smem, st, CS, a) != cudaSuccess)
         return PSG_ECUDA;
     return PSG_OK;
 }
@@ -781,7 +812,15 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     };
     // two tiles in flight share every weight stage; with few tiles one tile per CTA spreads them over more SMs
     int ng = (cs == 1 && a.ntiles > sms && a.tcols * 2 <= 512 && need(2, 16 * 1024) <= kSmemMax) ? 2 : 1;
+    if (b.x3) {
+        // operand = [A | A_lo]: the residual copy starts at the widest operand's width, one tile in flight, tensor memory only
+        if (cs != 1) return PSG_EUNSUPPORTED;
+        ng = 1;
+        a.lo_off = (b.amax_cols + 31) / 32 * 32;
+        b.amax_cols = 2 * a.lo_off;
+    }
     const bool ts = cs == 1 && ts_eligible(b, ng);
+    if (b.x3 && !ts) return PSG_EUNSUPPORTED;
     if (ts) { a.abytes = 0; a.acols = b.amax_cols; }          // no operand buffer in shared memory: room for 64 KB stages
     int stage = (ts && need(ng, 64 * 1024) <= kSmemMax) ? 64 * 1024 : need(ng, 32 * 1024) <= kSmemMax ? 32 * 1024 : 16 * 1024;
     if (need(ng, stage) > kSmemMax || a.tcols * ng > 512) return PSG_EUNSUPPORTED;
@@ -802,7 +841,8 @@ int launch_program(Builder &b, long long rows, cudaStream_t st)
     if (cs == 1) {
         const int want = (a.ntiles + ng - 1) / ng;
         const int grid = want < sms ? want : sms;
-        if (ts) rc = ng == 2 ? launch_tile<2, 1, true>(a, grid, smem, st) : launch_tile<1, 1, true>(a, grid, smem, st);
+        if (b.x3) rc = launch_tile<1, 1, true, true>(a, grid, smem, st);
+        else if (ts) rc = ng == 2 ? launch_tile<2, 1, true>(a, grid, smem, st) : launch_tile<1, 1, true>(a, grid, smem, st);
         else rc = ng == 2 ? launch_tile<2, 1>(a, grid, smem, st) : launch_tile<1, 1>(a, grid, smem, st);
     } else {
         const int grid = a.ntiles * cs;                     // one cluster per tile, all resident in one wave
@@ -822,26 +862,31 @@ int psg_chain_fused(const PsgChain &c, cudaStream_t st)
 {
     if (c.nlayers < 1 || c.nlayers > kMaskSlots || c.kin % 16 || c.kin > 256 || c.ncls > kPsgMaxCls) return PSG_EUNSUPPORTED;
     Builder b;
+    b.x3 = c.head_wf_lo != nullptr;
     int kprev = c.kin;
     for (int j = 0; j < c.nlayers; ++j) {          // hidden layers: bias + ReLU, bits kept in shared-memory slot j
         if (c.n[j] > 256) return PSG_EUNSUPPORTED;
         TileOp *o = b.add(c.wf[j], c.nwf[j], 0, 0, c.n[j], kprev / 4, 0);
+        o->wlo = b.x3 ? c.wf_lo[j] : nullptr;
         o->epi = EPI_RELU; o->bias = c.bias[j]; o->slot = j;
         if (j == 0) o->pre = PRE_FP;
         kprev = c.n[j];
     }
     {                                               // head: N = 16 logits columns (zero-padded classes)
         TileOp *o = b.add(c.head_wf, c.head_nwf, 0, 0, 16, kprev / 4, 0);
+        o->wlo = c.head_wf_lo;
         o->epi = EPI_HEAD; o->bias = c.head_bias;
     }
     if (c.backward) {
         {                                           // d hidden_last = dz W_head, masked by the last hidden layer's bits
             TileOp *o = b.add(c.head_wb, c.head_nwb, 0, 0, kprev, 16 / 4, 0);
+            o->wlo = c.head_wb_lo;
             o->epi = EPI_MASK; o->slot = c.nlayers - 1;
         }
         for (int j = c.nlayers - 1; j >= 0; --j) {
             const int nin = j > 0 ? c.n[j - 1] : c.kin;
             TileOp *o = b.add(c.wb[j], c.nwb[j], 0, 0, nin, c.n[j] / 4, 0);
+            o->wlo = b.x3 ? c.wb_lo[j] : nullptr;
             if (j > 0) { o->epi = EPI_MASK; o->slot = j - 1; }
             else { o->epi = EPI_STORE; o->out = c.dI; o->rm = c.dI_rm; o->rm_stride = c.kin; o->rm_only = (c.dI_rm && c.rm_only) ? 1 : 0; }
         }

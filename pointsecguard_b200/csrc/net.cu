@@ -33,7 +33,7 @@ static int g_sa_compact = 1;
 // direction (deep.cu: phase list + grid barrier) instead of a launch per layer; psg_set_option "deep" 0 restores the launches
 // mode 2 (3xTF32): the narrow SA branches run as fused kernels too when their hi + lo weights and operand buffers fit
 // (psg_set_option "x3_fused" 0: every layer of mode 2 goes through the per-layer GEMM)
-static int g_x3_fused = 1;
+static int g_x3_fused = 3;     // bit 0: the narrow SA branches, bit 1: fp1 + head
 static int g_deep = 0;      // bit 0: on; bit 1: the backward kernel starts with the segmented sum that feeds its first level (OFF by default: measured slower)
 
 // ------------------------------------------------------------------------------------------------
@@ -758,12 +758,18 @@ extern "C" int psg_net_read_geometry(const psg_net *n, int what, int level, int 
 
 static inline TView tv(float *p, int width, int col0 = 0) { return TView{p, width / 4, col0 / 4}; }
 
+// fp1 + head as one forward + backward kernel: the TF32 mode always, the 3xTF32 mode with x3_fused bit 1
+static inline bool head_fused_now(const psg_net *n)
+{
+    return n->head_fused && (n->mode == 1 || (n->mode == 2 && (g_x3_fused & 2)));
+}
+
 // does the branch run as one kernel per direction in the network's current mode?
 static inline bool branch_fused_now(const psg_net *n, const Branch &Br)
 {
     if (n->mode == 1) return Br.fused || Br.streamed;
     if (n->mode == 2)
-        return g_x3_fused && Br.fused && Br.compactable && n->compact_valid && !n->xyz_grad &&
+        return (g_x3_fused & 1) && Br.fused && Br.compactable && n->compact_valid && !n->xyz_grad &&
                psg_sa_fusable_x3(Br.K, Br.gpad, Br.mlp[0]->npad, Br.mlp[1]->npad, Br.mlp[2]->npad);
     return false;
 }
@@ -832,12 +838,15 @@ static PsgChain head_chain_desc(psg_net *n, int t, TView coarse)
     c.src = coarse; c.S = Nc; c.Nf = Nf; c.kin = F.C2; c.rows = (long long)B * Nf;
     c.nn_idx = F.nn_idx + (size_t)t * B * Nf * 3; c.nn_w = F.nn_w + (size_t)t * B * Nf * 3;
     c.nlayers = F.nl + 1;
+    const int wm = n->mode == 2 ? 2 : 1;           // mode 2: hi parts here, residuals below (3xTF32 inside the tile program)
     for (int j = 0; j <= F.nl; ++j) {
         const psg_mlp *m = j < F.nl ? F.mlp[j] : n->conv1;
-        c.n[j] = m->npad; c.wf[j] = w_fwd(m, 1); c.nwf[j] = m->nwf; c.bias[j] = m->bias; c.wb[j] = w_bwd(m, 1); c.nwb[j] = m->nwb;
+        c.n[j] = m->npad; c.wf[j] = w_fwd(m, wm); c.nwf[j] = m->nwf; c.bias[j] = m->bias; c.wb[j] = w_bwd(m, wm); c.nwb[j] = m->nwb;
+        if (wm == 2) { c.wf_lo[j] = m->wf_lo; c.wb_lo[j] = m->wb_lo; }
     }
-    c.head_wf = w_fwd(n->conv2, 1); c.head_nwf = n->conv2->nwf; c.head_bias = n->conv2->bias;
-    c.head_wb = w_bwd(n->conv2, 1); c.head_nwb = n->conv2->nwb;
+    c.head_wf = w_fwd(n->conv2, wm); c.head_nwf = n->conv2->nwf; c.head_bias = n->conv2->bias;
+    c.head_wb = w_bwd(n->conv2, wm); c.head_nwb = n->conv2->nwb;
+    if (wm == 2) { c.head_wf_lo = n->conv2->wf_lo; c.head_wb_lo = n->conv2->wb_lo; }
     c.ncls = n->ncls; c.target = -1;
     c.src_rm = (n->fp[1].streamed && n->mode == 1) ? n->fp[1].Yrm : nullptr;
     return c;
@@ -876,7 +885,7 @@ extern "C" int psg_net_forward(psg_net *n, int t, float *logp, float *l4_points,
     // feature propagation, coarse to fine
     float *up = n->feats[4];
     int upw = n->wfeat[4];
-    const bool fuse_head = mode == 1 && n->head_fused;
+    const bool fuse_head = head_fused_now(n);
     n->z_valid = false;
     n->loss.set = false;
     psg_deep_cancel();
@@ -942,7 +951,7 @@ static int set_loss(psg_net *n, int kind, const float *dlogp, const int32_t *lab
     if (kind == 0 && !dlogp) return PSG_EINVAL;
     if (kind != 0 && !labels && target < 0) return PSG_EINVAL;
     if (kind < 0 || kind > 2) return PSG_EINVAL;
-    if (n->mode == 1 && n->head_fused) {
+    if (head_fused_now(n)) {
         // evaluated inside the fused fp1 + head kernel launched by psg_net_backward
         n->loss.kind = kind; n->loss.dlogp = dlogp; n->loss.labels = labels; n->loss.target = target;
         n->loss.scale = scale; n->loss.kappa = kappa; n->loss.loss_rows = loss_rows; n->loss.hit = hit; n->loss.set = true;
@@ -1022,7 +1031,7 @@ extern "C" int psg_net_backward(psg_net *n, int t, float *grad_x, psg_stream_t s
         int cat_buf = 0;
         const float *rm_src = nullptr; int rm_stride = 0;      // row-major copy of d[interp] when a fused kernel produced it
         bool skip_done = false;                                 // d[skip] already written into dfeat[f] by the producing kernel
-        if (f == 0 && n->mode == 1 && n->head_fused) {
+        if (f == 0 && head_fused_now(n)) {
             if (!n->loss.set) return PSG_EINVAL;
             FpLevel &C = n->fp[1];
             PsgChain c = head_chain_desc(n, t, tv(C.Y[C.nl - 1], C.mlp[C.nl - 1]->npad));

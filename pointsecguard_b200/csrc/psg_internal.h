@@ -150,6 +150,8 @@ struct PsgChain {
     float *loss_rows; unsigned char *hit;
     TView zout, dI;
     float *dI_rm; int rm_only;         // row-major copy of dI ([rows][kin]) for the segmented sum; rm_only: skip the T-layout store
+    // 3xTF32 (mode 2): the TF32 residuals of every weight above (wf / wb / head_* are then the "hi" parts); all null otherwise
+    const float *wf_lo[4], *wb_lo[4], *head_wf_lo, *head_wb_lo;
 };
 int psg_chain_fused(const PsgChain &c, cudaStream_t st);
 // set-abstraction branch with streamed weights (widths beyond what sa_fused.cu keeps resident)

@@ -203,7 +203,9 @@ def test_config4_msg_nb_b64(golden_dir, mode):
     print(f"config4 {mode}: last-step replay identical {replay:.5f}; whole trajectory {same:.5f}; adv acc {got['acc']:.4f} "
           f"(oracle {float(g['adv_acc']):.4f}) mIoU {got['miou']:.4f} ({float(g['adv_miou']):.4f})")
     assert replay >= REPLAY_FLOOR[mode]
-    _check_metrics(got, g, "adv", tol=0.005 if mode != "tf32" else 0.015)     # measured: fp32 0.1 pt, TF32 0.9 pt
+    # measured: fp32 0.1 pt, 3xTF32 0.4-0.5 pt, TF32 0.9 pt (ten chaotic sign steps after the trajectories part: the
+    # last-step replay above is the sharp gate, these are sanity bounds)
+    _check_metrics(got, g, "adv", tol={"fp32": 0.005, "x3": 0.01, "tf32": 0.015}[mode])
 
 
 # ----------------------------------------------------------------------------------------------------------------
