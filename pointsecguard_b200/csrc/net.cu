@@ -121,6 +121,7 @@ struct psg_mlp {
 // What remains is zero-mean rounding noise (std ~0.29 ulp per operand, the same as round-to-nearest would leave), which
 // averages over the K terms of a dot product instead of accumulating.
 static const double kTf32Comp = 3.45e-4;
+static double kX3AccComp = 6.6e-9;       // per column of contraction (psg_set_option "x3_acc_comp_e10": value x 1e-10, for A/B)
 static inline float tf32_rna(double x)
 {
     float f = (float)x;
@@ -159,8 +160,13 @@ extern "C" psg_mlp *psg_mlp_create(const float *w, const float *b, int cin, int 
     for (size_t i = 0; i < hb.size(); ++i) cb[i] = tf32_rna((double)hb[i] * (1.0 + kTf32Comp));
     // 3xTF32 split of the exact weights (both parts TF32-representable: the hardware's truncation leaves them alone)
     std::vector<float> fh(hf.size()), fl(hf.size()), bh(hb.size()), bl(hb.size());
-    for (size_t i = 0; i < hf.size(); ++i) { fh[i] = tf32_rna((double)hf[i]); fl[i] = tf32_rna((double)hf[i] - (double)fh[i]); }
-    for (size_t i = 0; i < hb.size(); ++i) { bh[i] = tf32_rna((double)hb[i]); bl[i] = tf32_rna((double)hb[i] - (double)bh[i]); }
+    // The tensor core's fp32 accumulator TRUNCATES every add (three per 8-column K step in 3xTF32): a layer's output comes
+    // out scaled by 1 - 6.6e-9 K (measured, tools/gemm_precision.py: -8.8e-7 at K = 128, -4.8e-6 at K = 768; the random part
+    // of the same truncation is half as large).  Like the TF32 mode's operand truncation, the systematic part is folded
+    // into the weights: contraction length K = kpad forward, npad in the dgrad.
+    const double cf3 = 1.0 + kX3AccComp * m->kpad, cb3 = 1.0 + kX3AccComp * m->npad;
+    for (size_t i = 0; i < hf.size(); ++i) { const double v = (double)hf[i] * cf3; fh[i] = tf32_rna(v); fl[i] = tf32_rna(v - (double)fh[i]); }
+    for (size_t i = 0; i < hb.size(); ++i) { const double v = (double)hb[i] * cb3; bh[i] = tf32_rna(v); bl[i] = tf32_rna(v - (double)bh[i]); }
     bool ok = cudaMalloc(&m->wf, hf.size() * 4) == cudaSuccess && cudaMalloc(&m->wb, hb.size() * 4) == cudaSuccess &&
               cudaMalloc(&m->wf_tf32, hf.size() * 4) == cudaSuccess && cudaMalloc(&m->wb_tf32, hb.size() * 4) == cudaSuccess &&
               cudaMalloc(&m->bias, hbias.size() * 4) == cudaSuccess &&
@@ -476,6 +482,7 @@ extern "C" int psg_set_option(const char *name, int value)
     if (!strcmp(name, "sa_compact")) { g_sa_compact = value != 0; return PSG_OK; }
     if (!strcmp(name, "deep")) { g_deep = value; return PSG_OK; }
     if (!strcmp(name, "x3_fused")) { g_x3_fused = value; return PSG_OK; }
+    if (!strcmp(name, "x3_acc_comp_e10")) { kX3AccComp = value * 1e-10; return PSG_OK; }     // takes effect for layers created afterwards
     if (!strcmp(name, "deep_bn_min")) { psg_deep_tune(value, 0); return PSG_OK; }
     if (!strcmp(name, "deep_items")) { psg_deep_tune(0, value); return PSG_OK; }
     if (!strcmp(name, "stream_stages")) { psg_stream_tune(value, 0, 0); return PSG_OK; }

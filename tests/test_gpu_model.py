@@ -54,10 +54,11 @@ def test_forward_and_input_gradient_vs_reference_golden(golden_dir, arch, mode):
     # colour (3:6) and normalised-xyz (6:9) channels reach the loss through features only
     rel, sign, close = _grad_report(mine[:, 3:], g["grad"][:, 3:])
     print(f"{arch}: grad rel={rel:.2e} sign={sign:.5f} within-rtol-1e-3={close:.4f}")
-    # SURVEY section 7, hard part 2: >= 99.9 % of the elements within rtol 1e-3, sign agreement >= 99.99 % (measured: fp32
-    # 0.9998 / 1.0000 within rtol, sign 1.00000; 3xTF32 0.9988 / 0.9973 within rtol -- its gate is the stated 0.995 -- sign 0.99996 / 1.00000)
-    assert rel < (1e-4 if mode == 0 else 2e-3) and sign >= 0.9999
-    assert close >= (0.999 if mode == 0 else 0.995)
+    # SURVEY section 7, hard part 2: >= 99.9 % of the elements within rtol 1e-3, sign agreement >= 99.99 %.  Measured: fp32
+    # rel 3.4e-6 / 1.8e-6, within rtol 0.9998 / 1.0000; 3xTF32 rel 4.5e-6 / 1.8e-5, within rtol 0.9998 / 0.9997 (8e-4 / 1.2e-3
+    # and 0.9988 / 0.9973 before the accumulator-truncation bias was folded into its weights); sign 1.00000 everywhere
+    assert rel < 1e-4 and sign >= 0.9999
+    assert close >= 0.999
 
 
 def test_engine_indices_match_reference_trace(golden_dir):
