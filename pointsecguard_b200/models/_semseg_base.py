@@ -51,7 +51,8 @@ class SemSegBase(nn.Module):
     """get_model.forward of pointnet2_sem_seg.py:22-40 / pointnet2_sem_seg_msg.py:23-41."""
 
     arch = "ssg"
-    mlp_mode = MLP_FP32
+    # default MLP mode of the eval-mode (attack) engine; PSG_DEFAULT_MLP overrides it process-wide (A/B of the defaults)
+    mlp_mode = int(__import__("os").environ.get("PSG_DEFAULT_MLP", MLP_FP32))
     # autograd of forward(): False = gradient through the features only (all the colour attacks need);
     # True = also through the geometry (centred neighbour coordinates, interpolation weights), which
     # is what the reference's autograd produces on input channels 0:3
