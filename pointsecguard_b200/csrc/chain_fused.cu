@@ -411,8 +411,11 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                         for (int g = 0; g < NG; ++g) {
                             if (tile0 + g >= a.ntiles) continue;
                             if (pl == 0 && sub == 0) {
-                                if (CS > 1) tc::mbar_wait_cluster(tc::smem_u32(&bar_in[g]), ph_in[g]);
-                                else tc::mbar_spin(tc::smem_u32(&bar_in[g]), ph_in[g]);
+                                // (cluster programs too: what the peers' arrivals publish is SHARED memory -- their operand
+                                // slices in this CTA's buffer -- so a CTA-scope acquire orders everything that is read next.
+                                // The cluster-scope form makes the compiler invalidate the whole L1 after every wait
+                                // (CCTL.IVALL: a quarter of SA4's stall samples, profiles/r2_notes.md))
+                                tc::mbar_spin(tc::smem_u32(&bar_in[g]), ph_in[g]);
                                 ph_in[g] ^= 1u;
                             }
                             tc::fence_after_sync();
@@ -505,8 +508,9 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                 tc::fence_before_sync();
                 if (CS > 1) {
                     tc::fence_async_all();
+                    tc::fence_release_cluster();
 #pragma unroll
-                    for (int pr = 0; pr < CS; ++pr) tc::mbar_arrive_cluster(tc::mapa(b_in, (uint32_t)pr));
+                    for (int pr = 0; pr < CS; ++pr) tc::mbar_arrive_cluster_relaxed(tc::mapa(b_in, (uint32_t)pr));
                 } else {
                     if (TS) tc::tmem_wait_st();        // the operand written by this thread (gather or previous epilogue) has landed
                     else tc::fence_async_smem();
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1) tile_kernel(const __grid_con
                 }
                 if (tr && tn < 510) tr[tn++] = clock64();
                 // ---- epilogue ----
-                if (CS > 1) tc::mbar_wait_cluster(b_acc, ph); else tc::mbar_wait(b_acc, ph);
+                tc::mbar_wait(b_acc, ph);          // (CTA-scope acquire in cluster programs as well: see the issuer's wait)
                 ph ^= 1u; tc::fence_after_sync();
                 if (tr && tn < 510) tr[tn++] = clock64();
                 const int words = (op.n + 31) / 32;

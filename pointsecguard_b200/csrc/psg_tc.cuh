@@ -88,6 +88,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
+// one cluster-scope release fence, then relaxed arrives: a thread that signals several peers pays for ONE fence
+// (mbarrier.arrive.release.cluster costs a MEMBAR.ALL.GPU per arrive)
+__device__ __forceinline__ void fence_release_cluster() { asm volatile("fence.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t caddr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
