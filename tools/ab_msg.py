@@ -8,6 +8,8 @@ from pointsecguard_b200 import _lib as L, synthetic as syn, torchattacks
 from pointsecguard_b200.engine import MLP_TF32
 from pointsecguard_b200.models.pointnet2_sem_seg_msg import get_model
 
+for kv in filter(None, os.environ.get("AB_PRE", "").split(",")):        # options that must be set before the engine is bound
+    k, v = kv.split("="); assert L.psg_set_option(k.encode(), int(v)) == 0, k
 m = get_model(13); m.load_state_dict(syn.make_state_dict("msg", init="he")); m = m.cuda().eval(); m.set_mlp_mode(int(os.environ.get("AB_MODE", MLP_TF32)))
 B = int(os.environ.get("AB_BLOCKS", "64"))
 x = syn.make_blocks(B, 4096, 0).cuda(); torch.manual_seed(5); lab = m(x)[0].argmax(2).cpu().numpy().astype(np.float64)
