@@ -474,6 +474,7 @@ extern "C" int psg_set_option(const char *name, int value)
     if (!name) return PSG_EINVAL;
     if (!strcmp(name, "nn_grid")) { psg_three_nn_grid_mode(value); return PSG_OK; }
     if (!strcmp(name, "fps_cluster")) { psg_fps_use_cluster(value); return PSG_OK; }
+    if (!strcmp(name, "fps_fat_min_p")) { psg_fps_fat_min_p(value); return PSG_OK; }
     if (!strcmp(name, "ts")) { psg_tile_use_ts(value != 0); return PSG_OK; }
     if (!strcmp(name, "clusters")) { psg_tile_use_clusters(value != 0); return PSG_OK; }
     if (!strcmp(name, "fp_min_tiles")) { g_fp_min_tiles = value; return PSG_OK; }

@@ -35,6 +35,7 @@ int psg_scene_gather_k(const double *pts, int ld, int label_col, const int *sel,
 
 // fps.cu
 void psg_fps_use_cluster(int on);
+void psg_fps_fat_min_p(int p);
 size_t psg_fps_workspace_bytes(int P, int N);
 int psg_fps_launch(const float *xyz, long long cloud_stride, int nclouds, int P, int N, int npoint,
                    const int *start, int *out_idx, float *out_xyz, void *ws, size_t ws_bytes, cudaStream_t st);
